@@ -305,6 +305,11 @@ int32_t cae_get_stats(cae_engine* e, cae_stats* out);
  * / NCCL on the caller's side): 0 = fit_count int32[T], 1 = node_count|pod_count int32[2T]. */
 void* cae_device_buffer(cae_engine* e, int32_t which, size_t* bytes);
 
+/* Page-locked host memory for the caller's large input / output buffers (fit_bits, reasons): copies
+ * to and from pinned memory run at full PCIe speed and asynchronously. */
+void* cae_host_alloc(size_t bytes);
+void cae_host_free(void* p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,437 @@
+// api.cu — C ABI of libcaengine.so (include/caengine.h) and the host-side flattener.
+//
+// cae_load turns the interned object tables into the engine's device layout:
+//   * every table is uploaded verbatim (DevObjects) — selectors, tolerations, label sets are
+//     evaluated ON THE GPU, the host never runs a predicate;
+//   * pod specs are interned into "static classes" (tolerations, node affinity/selector, nodeName,
+//     host ports) so the plugins whose verdict does not depend on the pod's size are evaluated once
+//     per (class, node) by class_matrix_kernel and re-used by every pod of the class;
+//   * per-pod request planes [A][P] (A = resource dims any pending pod asks for) and per-template
+//     free-capacity planes [A][T] are laid out SoA for coalesced int64 loads in the dense pass.
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <tuple>
+
+#include "engine.h"
+
+namespace cae {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+int Arena::alloc(void** p, size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) { set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); return -1; }
+  blocks.push_back(*p);
+  return 0;
+}
+void Arena::release() {
+  for (void* b : blocks) cudaFree(b);
+  blocks.clear();
+}
+
+template <class T>
+static int upload(Engine* e, const T* host, size_t n, const T** dev) {
+  void* p = nullptr;
+  if (e->arena.alloc(&p, n * sizeof(T))) return -1;
+  if (n) {
+    cudaError_t err = cudaMemcpyAsync(p, host, n * sizeof(T), cudaMemcpyHostToDevice, e->stream);
+    if (err != cudaSuccess) { set_error(std::string("H2D: ") + cudaGetErrorString(err)); return -1; }
+    e->stats.h2d_bytes += n * sizeof(T);
+  }
+  *dev = static_cast<const T*>(p);
+  return 0;
+}
+template <class T>
+static int dev_alloc(Engine* e, T** dev, size_t n, bool zero = false) {
+  void* p = nullptr;
+  if (e->arena.alloc(&p, n * sizeof(T))) return -1;
+  if (zero) cudaMemsetAsync(p, 0, std::max<size_t>(n * sizeof(T), 16), e->stream);
+  *dev = static_cast<T*>(p);
+  return 0;
+}
+
+#define UP(field, count)                                                           \
+  if (upload(e, o->field, (size_t)(count), &e->dobj.field)) return -1
+
+static int do_load(Engine* e, const cae_objects* o) {
+  if (o->abi_version != CAE_ABI_VERSION) { set_error("cae_objects.abi_version mismatch"); return -2; }
+  if (o->num_res < 3 || o->num_res > CAE_MAX_RES) { set_error("num_res out of range"); return 1; }
+  e->arena.release();
+  e->loaded = false;
+  e->group_reason_valid = false;
+  e->stats.h2d_bytes = 0;
+  const int N = o->num_cluster_nodes, T = o->num_templates, NT = N + T;
+  e->N = N; e->T = T; e->U = N + 2 * T; e->E = o->num_groups; e->P = o->num_pending;
+  e->Tw = (T + 31) / 32;
+  e->num_podspecs = o->num_podspecs;
+  const int W = std::max(1, e->cfg.world_size), rk = e->cfg.rank;
+  e->p_begin = (int)((int64_t)e->P * rk / W);
+  e->p_end = (int)((int64_t)e->P * (rk + 1) / W);
+  e->p_begin = (e->p_begin / 32) * 32;  // word-aligned shards so bit rows concatenate
+  if (rk + 1 < W) e->p_end = (e->p_end / 32) * 32;
+  e->Pl = e->p_end - e->p_begin;
+  e->Plw = (e->Pl + 31) / 32;
+  e->t_begin = (int)((int64_t)T * rk / W);
+  e->t_end = (int)((int64_t)T * (rk + 1) / W);
+
+  cudaEventRecord(e->ev0, e->stream);
+  DevObjects& d = e->dobj;
+  d.num_res = o->num_res; d.num_values = o->num_values; d.hostname_key = o->hostname_key;
+  d.unschedulable_taint_key = o->unschedulable_taint_key; d.N = N; d.T = T;
+  UP(value_is_int, o->num_values); UP(value_int, o->num_values);
+  UP(ns_labelset, o->num_namespaces); UP(ns_exists, o->num_namespaces);
+  UP(ls_off, o->num_labelsets + 1); UP(ls_key, o->ls_off[o->num_labelsets]); UP(ls_val, o->ls_off[o->num_labelsets]);
+  UP(req_key, o->num_reqs); UP(req_op, o->num_reqs); UP(req_val_off, o->num_reqs + 1);
+  UP(req_vals, o->num_reqs ? o->req_val_off[o->num_reqs] : 0);
+  UP(sel_kind, o->num_selectors); UP(sel_req_off, o->num_selectors + 1);
+  UP(naff_nodesel, o->num_naff); UP(naff_has_required, o->num_naff); UP(naff_term_off, o->num_naff + 1);
+  UP(term_expr_sel, o->num_naff_terms); UP(term_field_off, o->num_naff_terms + 1);
+  { int nf = o->term_field_off[o->num_naff_terms]; UP(field_op, nf); UP(field_node_name, nf); }
+  { int n = o->tol_off[o->num_tol_lists]; UP(tol_off, o->num_tol_lists + 1); UP(tol_key, n); UP(tol_op, n); UP(tol_val, n); UP(tol_effect, n); }
+  { int n = o->taint_off[o->num_taint_lists]; UP(taint_off, o->num_taint_lists + 1); UP(taint_key, n); UP(taint_val, n); UP(taint_effect, n); }
+  { int n = o->port_off[o->num_port_lists]; UP(port_off, o->num_port_lists + 1); UP(port_ip, n); UP(port_proto, n); UP(port_num, n); }
+  { int n = o->pts_off[o->num_pts_lists]; UP(pts_off, o->num_pts_lists + 1); UP(pts_max_skew, n); UP(pts_key, n); UP(pts_selector, n);
+    UP(pts_min_domains, n); UP(pts_node_affinity_policy, n); UP(pts_node_taints_policy, n); }
+  { int n = o->num_aterms; UP(aff_off, o->num_aff_lists + 1); UP(aterm_selector, n); UP(aterm_key, n); UP(aterm_ns_off, n + 1);
+    UP(aterm_ns, o->aterm_ns_off[n]); UP(aterm_ns_selector, n); }
+  { int n = o->num_podspecs; UP(ps_namespace, n); UP(ps_labelset, n); UP(ps_req, (size_t)n * R); UP(ps_tol_list, n); UP(ps_naff, n);
+    UP(ps_node_name, n); UP(ps_port_list, n); UP(ps_pts_list, n); UP(ps_aff_list, n); UP(ps_anti_list, n); UP(ps_terminating, n); }
+  UP(node_name, NT); UP(node_labelset, NT); UP(node_taint_list, NT); UP(node_unschedulable, NT);
+  UP(node_alloc, (size_t)NT * R); UP(node_allowed_pods, NT); UP(node_cap_cpu, NT); UP(node_cap_mem, NT);
+  UP(node_has_alloc_cpu, NT); UP(node_has_alloc_mem, NT);
+  UP(node_pod_off, NT + 1); UP(node_pod_spec, o->node_pod_off[NT]);
+  UP(group_off, o->num_groups + 1); UP(pend_spec, o->num_pending);
+
+  // ---- host-side interning of pod specs into classes (no predicate is evaluated here) ----
+  const int S = o->num_podspecs;
+  std::vector<uint8_t> spec_pending(S, 0);
+  for (int p = 0; p < o->num_pending; ++p) spec_pending[o->pend_spec[p]] = 1;
+  std::map<std::tuple<int, int, int, int>, int> sc_ids;
+  std::vector<StaticClass> sclass;
+  std::vector<int32_t> spec_sc(S, 0), spec_dc(S, 0);
+  e->has_dynamic = false;
+  for (int s = 0; s < S; ++s) {
+    if (!spec_pending[s]) continue;
+    auto key = std::make_tuple(o->ps_tol_list[s], o->ps_naff[s], o->ps_node_name[s], o->ps_port_list[s]);
+    auto it = sc_ids.find(key);
+    if (it == sc_ids.end()) {
+      it = sc_ids.emplace(key, (int)sclass.size()).first;
+      sclass.push_back({o->ps_tol_list[s], o->ps_naff[s], o->ps_node_name[s], o->ps_port_list[s]});
+    }
+    spec_sc[s] = it->second;
+    auto nonempty = [&](const int32_t* off, int l) { return off[l + 1] > off[l]; };
+    if (nonempty(o->pts_off, o->ps_pts_list[s]) || nonempty(o->aff_off, o->ps_aff_list[s]) ||
+        nonempty(o->aff_off, o->ps_anti_list[s]))
+      e->has_dynamic = true;
+  }
+  // pods already on nodes with required anti-affinity constrain incoming pods (interpodaffinity/filtering.go:204-228)
+  for (int i = 0; i < o->node_pod_off[NT]; ++i) {
+    int l = o->ps_anti_list[o->node_pod_spec[i]];
+    if (o->aff_off[l + 1] > o->aff_off[l]) e->has_dynamic = true;
+  }
+  // host-port lists of pending pods get compact ids (one bit each in a node's used-port mask)
+  std::vector<int32_t> pc_of(o->num_port_lists, -1);
+  int npc = 0;
+  for (int s = 0; s < S; ++s) {
+    int pl = o->ps_port_list[s];
+    if (!spec_pending[s] || o->port_off[pl + 1] == o->port_off[pl] || pc_of[pl] >= 0) continue;
+    if (npc == 64) { set_error("more than 64 distinct host-port sets among pending pods"); return 1; }
+    pc_of[pl] = npc++;
+  }
+  if (sclass.empty()) sclass.push_back({0, -1, -1, 0});
+  e->SC = (int)sclass.size();
+  e->DC = 1;  // class 0: no topology-spread / inter-pod-affinity involvement
+
+  // active resource dims + per-template free capacity
+  e->A = 0;
+  for (int r = 0; r < R; ++r) {
+    bool used = false;
+    for (int s = 0; s < S && !used; ++s) used = spec_pending[s] && o->ps_req[(size_t)s * R + r] > 0;
+    if (used) e->act_dim[e->A++] = r;
+  }
+  std::vector<int64_t> free_all((size_t)R * T), free_act((size_t)std::max(e->A, 1) * T);
+  std::vector<int32_t> slots(T);
+  for (int t = 0; t < T; ++t) {
+    int node = N + t;
+    int64_t reqd[R] = {0};
+    int npods = o->node_pod_off[node + 1] - o->node_pod_off[node];
+    for (int i = o->node_pod_off[node]; i < o->node_pod_off[node + 1]; ++i)
+      for (int r = 0; r < R; ++r) reqd[r] += o->ps_req[(size_t)o->node_pod_spec[i] * R + r];
+    for (int r = 0; r < R; ++r) free_all[(size_t)r * T + t] = o->node_alloc[(size_t)node * R + r] - reqd[r];
+    for (int a = 0; a < e->A; ++a) free_act[(size_t)a * T + t] = free_all[(size_t)e->act_dim[a] * T + t];
+    slots[t] = o->node_allowed_pods[node] - npods;
+  }
+  const StaticClass* d_sc_c = nullptr; const int32_t *d_ssc = nullptr, *d_sdc = nullptr, *d_slots = nullptr;
+  const int64_t *d_fa = nullptr, *d_fact = nullptr;
+  if (upload(e, sclass.data(), sclass.size(), &d_sc_c) || upload(e, spec_sc.data(), (size_t)S, &d_ssc) ||
+      upload(e, spec_dc.data(), (size_t)S, &d_sdc) || upload(e, slots.data(), (size_t)T, &d_slots) ||
+      upload(e, free_all.data(), free_all.size(), &d_fa) || upload(e, free_act.data(), free_act.size(), &d_fact))
+    return -1;
+  e->d_sclass = const_cast<StaticClass*>(d_sc_c);
+  e->d_spec_sc = const_cast<int32_t*>(d_ssc); e->d_spec_dc = const_cast<int32_t*>(d_sdc);
+  e->d_tmpl_slots = const_cast<int32_t*>(d_slots);
+  e->d_tmpl_free_all = const_cast<int64_t*>(d_fa); e->d_tmpl_free = const_cast<int64_t*>(d_fact);
+
+  if (dev_alloc(e, &e->d_pre_code, (size_t)e->SC * e->U) || dev_alloc(e, &e->d_pre_ok, (size_t)e->SC * std::max(e->Tw, 1)) ||
+      dev_alloc(e, &e->d_post_code, (size_t)e->DC * std::max(T, 1), true) || dev_alloc(e, &e->d_post_ok, (size_t)e->DC * std::max(e->Tw, 1)) ||
+      dev_alloc(e, &e->d_pod_req, (size_t)std::max(e->A, 1) * std::max(e->Pl, 1)) || dev_alloc(e, &e->d_pod_sc, (size_t)std::max(e->Pl, 1)) ||
+      dev_alloc(e, &e->d_pod_dc, (size_t)std::max(e->Pl, 1)) || dev_alloc(e, &e->d_fit_bits, (size_t)std::max(T, 1) * std::max(e->Plw, 1)) ||
+      dev_alloc(e, &e->d_fit_count, (size_t)std::max(T, 1), true) || dev_alloc(e, &e->d_group_reason, (size_t)std::max(T, 1) * std::max(e->E, 1)) ||
+      dev_alloc(e, &e->d_counts2, (size_t)2 * std::max(T, 1), true) || dev_alloc(e, &e->d_sched, (size_t)std::max(T, 1) * std::max(e->E, 1), true) ||
+      dev_alloc(e, &e->d_order, (size_t)std::max(T, 1) * std::max(e->E, 1)) || dev_alloc(e, &e->d_order_n, (size_t)std::max(T, 1), true) ||
+      dev_alloc(e, &e->d_max_nodes, (size_t)std::max(T, 1), true) || dev_alloc(e, &e->d_work_counter, 1, true))
+    return -1;
+  e->d_score = nullptr;
+  e->d_reasons = nullptr;
+  if (e->cfg.want_reasons && dev_alloc(e, &e->d_reasons, (size_t)std::max(T, 1) * std::max(e->Pl, 1))) return -1;
+
+  // host copies for host-side steps (expander chain, homogeneity check)
+  e->h_group_off.assign(o->group_off, o->group_off + o->num_groups + 1);
+  e->h_pend_spec.assign(o->pend_spec, o->pend_spec + o->num_pending);
+
+  { const int32_t* d_pc = nullptr;
+    if (upload(e, pc_of.data(), pc_of.size(), &d_pc)) return -1;
+    e->d_pc_of = const_cast<int32_t*>(d_pc);
+    if (dev_alloc(e, &e->d_port_conf, (size_t)std::max(o->num_port_lists, 1))) return -1;
+    if (launch_port_conflicts(e, o->num_port_lists)) return -1; }
+  if (launch_class_matrices(e)) return -1;
+  if (launch_expand_pods(e)) return -1;
+  cudaEventRecord(e->ev1, e->stream);
+  CAE_CUDA(cudaStreamSynchronize(e->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+  e->stats.h2d_ms = ms;
+  e->loaded = true;
+  return 0;
+}
+
+}  // namespace cae
+
+using cae::Engine;
+
+extern "C" {
+
+const char* cae_last_error(void) { return cae::g_err.c_str(); }
+const char* cae_version(void) { return "caengine/0.1 sm_100a"; }
+
+int32_t cae_create(const cae_config* cfg, cae_engine** out) {
+  if (!cfg || !out) return -2;
+  if (cfg->abi_version != CAE_ABI_VERSION) { cae::set_error("cae_config.abi_version mismatch"); return -2; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cae::set_error("no CUDA device: the engine has no CPU fallback");
+    return -1;
+  }
+  Engine* e = new Engine();
+  e->cfg = *cfg;
+  if (e->cfg.world_size < 1) e->cfg.world_size = 1;
+  if (cudaSetDevice(cfg->device) != cudaSuccess) { cae::set_error("cudaSetDevice failed"); delete e; return -1; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) e->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { cae::set_error("stream create failed"); delete e; return -1; }
+  cudaEventCreate(&e->ev0);
+  cudaEventCreate(&e->ev1);
+  *out = reinterpret_cast<cae_engine*>(e);
+  return 0;
+}
+
+void cae_destroy(cae_engine* h) {
+  if (!h) return;
+  Engine* e = reinterpret_cast<Engine*>(h);
+  cudaSetDevice(e->cfg.device);
+  e->arena.release();
+  if (e->d_pack_scratch) cudaFree(e->d_pack_scratch);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int32_t cae_load(cae_engine* h, const cae_objects* objs) {
+  if (!h || !objs) return -2;
+  Engine* e = reinterpret_cast<Engine*>(h);
+  cudaSetDevice(e->cfg.device);
+  return cae::do_load(e, objs);
+}
+
+int32_t cae_feasibility(cae_engine* h, uint32_t* fit_bits, uint8_t* reasons, int32_t* fit_count) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (!e || !e->loaded) { cae::set_error("cae_feasibility before cae_load"); return -2; }
+  cudaSetDevice(e->cfg.device);
+  if (e->has_dynamic) { cae::set_error("topology spread / inter-pod affinity not supported by this build"); return 1; }
+  bool want_r = e->cfg.want_reasons && e->d_reasons;
+  cudaEventRecord(e->ev0, e->stream);
+  if (cae::launch_feasibility(e, want_r)) return -1;
+  cudaEventRecord(e->ev1, e->stream);
+  e->stats.d2h_bytes = 0;
+  cudaEvent_t c0, c1;
+  cudaEventCreate(&c0); cudaEventCreate(&c1);
+  cudaEventRecord(c0, e->stream);
+  if (fit_bits && e->T && e->Plw) {
+    CAE_CUDA(cudaMemcpyAsync(fit_bits, e->d_fit_bits, sizeof(uint32_t) * (size_t)e->T * e->Plw, cudaMemcpyDeviceToHost, e->stream));
+    e->stats.d2h_bytes += sizeof(uint32_t) * (size_t)e->T * e->Plw;
+  }
+  if (reasons && want_r && e->T && e->Pl) {
+    CAE_CUDA(cudaMemcpyAsync(reasons, e->d_reasons, (size_t)e->T * e->Pl, cudaMemcpyDeviceToHost, e->stream));
+    e->stats.d2h_bytes += (size_t)e->T * e->Pl;
+  }
+  if (fit_count && e->T) {
+    CAE_CUDA(cudaMemcpyAsync(fit_count, e->d_fit_count, sizeof(int32_t) * e->T, cudaMemcpyDeviceToHost, e->stream));
+    e->stats.d2h_bytes += sizeof(int32_t) * e->T;
+  }
+  cudaEventRecord(c1, e->stream);
+  CAE_CUDA(cudaStreamSynchronize(e->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+  e->stats.feasibility_ms = ms;
+  cudaEventElapsedTime(&ms, c0, c1);
+  e->stats.d2h_ms = ms;
+  cudaEventDestroy(c0); cudaEventDestroy(c1);
+  e->stats.evals = (int64_t)e->Pl * e->T;
+  return 0;
+}
+
+int32_t cae_feasibility_groups(cae_engine* h, uint8_t* reasons) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (!e || !e->loaded) { cae::set_error("cae_feasibility_groups before cae_load"); return -2; }
+  cudaSetDevice(e->cfg.device);
+  if (e->has_dynamic) { cae::set_error("topology spread / inter-pod affinity not supported by this build"); return 1; }
+  if (cae::launch_group_feasibility(e)) return -1;
+  if (reasons && e->T && e->E)
+    CAE_CUDA(cudaMemcpyAsync(reasons, e->d_group_reason, (size_t)e->T * e->E, cudaMemcpyDeviceToHost, e->stream));
+  CAE_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int32_t cae_estimate_all(cae_engine* h, const int32_t* max_nodes, int32_t* node_count, int32_t* pod_count,
+                         int32_t* sched_count, int32_t* order) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (!e || !e->loaded) { cae::set_error("cae_estimate_all before cae_load"); return -2; }
+  cudaSetDevice(e->cfg.device);
+  if (e->has_dynamic) { cae::set_error("topology spread / inter-pod affinity not supported by this build"); return 1; }
+  // groups must be homogeneous (equivalence.BuildPodGroups guarantees it: core/scaleup/equivalence/groups.go:40-104)
+  for (int g = 0; g < e->E; ++g)
+    for (int p = e->h_group_off[g] + 1; p < e->h_group_off[g + 1]; ++p)
+      if (e->h_pend_spec[p] != e->h_pend_spec[e->h_group_off[g]]) {
+        cae::set_error("pod group with non-equivalent pods");
+        return 1;
+      }
+  const int T = e->T, E = e->E;
+  if (T == 0) return 0;
+  e->pack_cap = 1;
+  for (int t = e->t_begin; t < e->t_end; ++t) {
+    int m = max_nodes ? max_nodes[t] : 0;
+    e->pack_cap = std::max(e->pack_cap, m > 0 ? m : (m == 0 ? e->P + 1 : 1));
+  }
+  if (max_nodes) CAE_CUDA(cudaMemcpyAsync(e->d_max_nodes, max_nodes, sizeof(int32_t) * T, cudaMemcpyHostToDevice, e->stream));
+  else CAE_CUDA(cudaMemsetAsync(e->d_max_nodes, 0, sizeof(int32_t) * T, e->stream));
+  CAE_CUDA(cudaMemsetAsync(e->d_counts2, 0, sizeof(int32_t) * 2 * T, e->stream));
+  CAE_CUDA(cudaMemsetAsync(e->d_sched, 0, sizeof(int32_t) * (size_t)T * std::max(E, 1), e->stream));
+  CAE_CUDA(cudaMemsetAsync(e->d_order, 0xff, sizeof(int32_t) * (size_t)T * std::max(E, 1), e->stream));
+  cudaEventRecord(e->ev0, e->stream);
+  if (!e->group_reason_valid && cae::launch_group_feasibility(e)) return -1;
+  int rc = cae::launch_order(e);
+  if (rc) return rc;
+  rc = cae::launch_pack(e);
+  if (rc) return rc;
+  cudaEventRecord(e->ev1, e->stream);
+  if (node_count) CAE_CUDA(cudaMemcpyAsync(node_count, e->d_counts2, sizeof(int32_t) * T, cudaMemcpyDeviceToHost, e->stream));
+  if (pod_count) CAE_CUDA(cudaMemcpyAsync(pod_count, e->d_counts2 + T, sizeof(int32_t) * T, cudaMemcpyDeviceToHost, e->stream));
+  if (sched_count && E) CAE_CUDA(cudaMemcpyAsync(sched_count, e->d_sched, sizeof(int32_t) * (size_t)T * E, cudaMemcpyDeviceToHost, e->stream));
+  if (order && E) CAE_CUDA(cudaMemcpyAsync(order, e->d_order, sizeof(int32_t) * (size_t)T * E, cudaMemcpyDeviceToHost, e->stream));
+  CAE_CUDA(cudaStreamSynchronize(e->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+  e->stats.estimate_ms = ms;
+  return 0;
+}
+
+int32_t cae_expander_best(cae_engine* h, const int32_t* chain, int32_t chain_len, const int32_t* node_count,
+                          const int32_t* pod_count, const int32_t* sched_count, uint8_t* best_mask, double* waste_score) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (!e || !e->loaded) { cae::set_error("cae_expander_best before cae_load"); return -2; }
+  cudaSetDevice(e->cfg.device);
+  const int T = e->T, E = e->E;
+  if (T == 0) return 0;
+  // scores on the device from the caller's (all-reduced) option table
+  int32_t *d_nc = nullptr, *d_sched = nullptr;
+  double* d_waste = nullptr;
+  CAE_CUDA(cudaMalloc(&d_nc, sizeof(int32_t) * T));
+  CAE_CUDA(cudaMalloc(&d_sched, sizeof(int32_t) * (size_t)T * std::max(E, 1)));
+  CAE_CUDA(cudaMalloc(&d_waste, sizeof(double) * T));
+  CAE_CUDA(cudaMemcpyAsync(d_nc, node_count, sizeof(int32_t) * T, cudaMemcpyHostToDevice, e->stream));
+  if (E) CAE_CUDA(cudaMemcpyAsync(d_sched, sched_count, sizeof(int32_t) * (size_t)T * E, cudaMemcpyHostToDevice, e->stream));
+  cudaEventRecord(e->ev0, e->stream);
+  if (cae::launch_expander(e, chain, chain_len, d_nc, nullptr, d_sched, nullptr, d_waste)) return -1;
+  cudaEventRecord(e->ev1, e->stream);
+  std::vector<double> waste(T);
+  CAE_CUDA(cudaMemcpyAsync(waste.data(), d_waste, sizeof(double) * T, cudaMemcpyDeviceToHost, e->stream));
+  CAE_CUDA(cudaStreamSynchronize(e->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+  e->stats.expander_ms = ms;
+  cudaFree(d_nc); cudaFree(d_sched); cudaFree(d_waste);
+  if (waste_score) std::copy(waste.begin(), waste.end(), waste_score);
+  // The filter chain itself is a sequential scan over <= T options in option order
+  // (expander/factory/chain.go:36-45) — it keeps the reference's order-dependent quirks
+  // (waste.go:58-65: equality tested before the nil/less-than branch).
+  std::vector<int> opts;
+  for (int t = 0; t < T; ++t) if (node_count[t] > 0) opts.push_back(t);
+  for (int c = 0; c < chain_len; ++c) {
+    std::vector<int> best;
+    if (chain[c] == CAE_EXP_LEAST_WASTE) {
+      double least = 0.0;
+      for (int t : opts) {
+        double w = waste[t];
+        if (w == least) best.push_back(t);
+        if (best.empty() || w < least) { least = w; best.assign(1, t); }
+      }
+    } else if (chain[c] == CAE_EXP_MOST_PODS) {
+      int mx = 0;
+      for (int t : opts) {
+        if (pod_count[t] == mx) { best.push_back(t); continue; }
+        if (pod_count[t] > mx) { mx = pod_count[t]; best.assign(1, t); }
+      }
+    } else if (chain[c] == CAE_EXP_LEAST_NODES) {
+      int least = INT32_MAX;
+      for (int t : opts) {
+        if (node_count[t] == 0) continue;
+        if (node_count[t] == least) { best.push_back(t); continue; }
+        if (node_count[t] < least) { least = node_count[t]; best.assign(1, t); }
+      }
+    } else { cae::set_error("unknown expander filter"); return 1; }
+    opts.swap(best);
+    if (opts.size() == 1) break;
+  }
+  if (best_mask) {
+    std::fill(best_mask, best_mask + T, 0);
+    for (int t : opts) best_mask[t] = 1;
+  }
+  return 0;
+}
+
+int32_t cae_get_stats(cae_engine* h, cae_stats* out) {
+  if (!h || !out) return -2;
+  *out = reinterpret_cast<Engine*>(h)->stats;
+  return 0;
+}
+
+void* cae_device_buffer(cae_engine* h, int32_t which, size_t* bytes) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (!e || !e->loaded) return nullptr;
+  if (which == 0) { if (bytes) *bytes = sizeof(int32_t) * e->T; return e->d_fit_count; }
+  if (which == 1) { if (bytes) *bytes = sizeof(int32_t) * 2 * e->T; return e->d_counts2; }
+  return nullptr;
+}
+
+void* cae_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+void cae_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

@@ -1,0 +1,105 @@
+// engine.h — internal state of the scale-up simulation engine (host side).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/caengine.h"
+#include "tables.cuh"
+
+namespace cae {
+
+void set_error(const std::string& msg);
+
+#define CAE_CUDA(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      cae::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                     \
+      return -1;                                                                              \
+    }                                                                                         \
+  } while (0)
+
+// Bump allocator over one cudaMalloc'ed arena per load (freed as a whole on the next cae_load).
+struct Arena {
+  std::vector<void*> blocks;
+  int alloc(void** p, size_t bytes);
+  void release();
+};
+
+struct Engine {
+  cae_config cfg{};
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  Arena arena;      // tables of the current load
+  cae_stats stats{};
+  bool loaded = false;
+
+  // sizes of the current load
+  int N = 0, T = 0, E = 0, P = 0, U = 0;  // U = N + 2T universe columns
+  int A = 0;                              // active resource dims (some pending pod requests > 0)
+  int act_dim[CAE_MAX_RES] = {0};
+  int SC = 0, DC = 0;                     // static / dynamic classes
+  int Tw = 0;                             // ceil(T/32)
+  int p_begin = 0, p_end = 0;             // pod shard of this rank (feasibility)
+  int t_begin = 0, t_end = 0;             // template shard of this rank (estimate)
+  int Pl = 0, Plw = 0;                    // local pods, ceil(Pl/32)
+  bool has_dynamic = false;               // any PTS / inter-pod affinity in the snapshot
+
+  DevObjects dobj{};                      // device mirror of the object tables
+  // derived device tables
+  StaticClass* d_sclass = nullptr;        // [SC]
+  uint8_t* d_pre_code = nullptr;          // [SC][U] static_code()
+  uint32_t* d_pre_ok = nullptr;           // [SC][Tw] bit t: low nibble of pre_code[sc][N+t] == 0 and template has a pod slot
+  int32_t* d_spec_sc = nullptr;           // [num_podspecs] static class of each spec
+  int32_t* d_spec_dc = nullptr;           // [num_podspecs] dynamic class (0 = none)
+  uint8_t* d_post_code = nullptr;         // [DC][T] PTS / IPA reason on the empty template (0 = ok)
+  uint32_t* d_post_ok = nullptr;          // [DC][Tw]
+  int64_t* d_pod_req = nullptr;           // [A][P] request planes of the pending pods; <=0 stored as INT64_MIN
+  int32_t* d_pod_sc = nullptr;            // [P]
+  int32_t* d_pod_dc = nullptr;            // [P]
+  int64_t* d_tmpl_free = nullptr;         // [A][T] allocatable - DaemonSet requested
+  int64_t* d_tmpl_free_all = nullptr;     // [R][T] same over all R dims (pack kernel)
+  int32_t* d_tmpl_slots = nullptr;        // [T] allowed pods - DaemonSet pods
+  int64_t* d_spec_req_t = nullptr;        // [num_podspecs][R] request (raw)
+  // results kept on device
+  uint32_t* d_fit_bits = nullptr;         // [T][Plw]
+  uint8_t* d_reasons = nullptr;           // [T][Pl] (want_reasons)
+  int32_t* d_fit_count = nullptr;         // [T]
+  uint8_t* d_group_reason = nullptr;      // [T][E]
+  bool group_reason_valid = false;
+  int32_t* d_counts2 = nullptr;           // [2T] node_count | pod_count
+  int32_t* d_sched = nullptr;             // [T][E]
+  int32_t* d_order = nullptr;             // [T][E]
+  int32_t* d_order_n = nullptr;           // [T]
+  double* d_score = nullptr;              // [T][E]
+  int32_t* d_max_nodes = nullptr;         // [T]
+  int32_t* d_pc_of = nullptr;             // [num_port_lists] compact id of a pending pod's port list, -1 otherwise
+  unsigned long long* d_port_conf = nullptr;  // [num_port_lists] conflict mask over compact ids
+  int pack_cap = 1 << 30;                 // node capacity of a pack slab (from the limiter caps)
+  // pack scratch
+  void* d_pack_scratch = nullptr;
+  size_t pack_scratch_bytes = 0;
+  int32_t* d_work_counter = nullptr;
+  // host copies needed by host-side steps
+  std::vector<int32_t> h_group_off, h_pend_spec;
+  std::vector<int64_t> h_spec_req;        // [num_podspecs][R]
+  std::vector<int64_t> h_cap_cpu, h_cap_mem;  // per template
+  int num_podspecs = 0;
+  int sm_count = 148;
+};
+
+// kernels.cu
+int launch_class_matrices(Engine* e);
+int launch_expand_pods(Engine* e);
+int launch_port_conflicts(Engine* e, int num_port_lists);
+int launch_feasibility(Engine* e, bool want_reasons);
+int launch_group_feasibility(Engine* e);
+int launch_order(Engine* e);
+int launch_pack(Engine* e);
+int launch_expander(Engine* e, const int32_t* chain, int chain_len, const int32_t* d_node_count,
+                    const int32_t* d_pod_count, const int32_t* d_sched, uint8_t* d_mask, double* d_waste);
+
+}  // namespace cae

@@ -1,0 +1,662 @@
+// kernels.cu — sm_100a kernels of the scale-up simulation engine.
+//
+//   class_matrix_kernel   (static class x universe node) -> reason/flag byte     [tables.cuh static_code]
+//   pack_ok_bits_kernel   byte matrix -> per-class template bit words
+//   expand_pods_kernel    podspec table -> per-pod SoA planes resident in HBM
+//   feasibility_kernel    K1: dense pods x templates Filter pass, warp-ballot bit matrix + counts
+//   group_reason_kernel   exemplar x template reasons (what SchedulablePodGroups asks)
+//   order_kernel          K0: DecreasingPodOrderer per template (float64 score, stable bitonic sort)
+//   pack_kernel           K3: BinpackingNodeEstimator.Estimate, one warp per template
+//   waste_kernel          K4: least-waste score per option
+//
+// Integer / bitset work only: no tensor cores.  Grid sizes are multiples of the SM
+// count where the work allows; per-template rows are staged in shared memory and broadcast.
+#include <cfloat>
+#include <climits>
+
+#include "engine.h"
+
+namespace cae {
+
+// ------------------------------------------------------------------------------------------------
+// class matrices
+// ------------------------------------------------------------------------------------------------
+__global__ void class_matrix_kernel(DevObjects o, const StaticClass* __restrict__ sclass, int SC, int U,
+                                    uint8_t* __restrict__ pre_code) {
+  int u = blockIdx.x * blockDim.x + threadIdx.x;
+  int c = blockIdx.y;
+  if (u >= U || c >= SC) return;
+  pre_code[(size_t)c * U + u] = static_code(o, sclass[c], u);
+}
+
+// bit t of word (c, t/32) = template t passes every static plugin for class c AND has a free pod slot
+// (the "Too many pods" part of NodeResourcesFit is pod independent: fit.go:652-661)
+__global__ void pack_ok_bits_kernel(const uint8_t* __restrict__ code, int ld, int col0, int rows, int T, int Tw,
+                                    const int32_t* __restrict__ tmpl_slots, uint32_t* __restrict__ ok) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  int c = blockIdx.y;
+  if (w >= Tw || c >= rows) return;
+  uint32_t bits = 0;
+  for (int j = 0; j < 32; ++j) {
+    int t = w * 32 + j;
+    if (t < T && (code[(size_t)c * ld + col0 + t] & 0x0F) == 0 && (tmpl_slots == nullptr || tmpl_slots[t] >= 1)) bits |= 1u << j;
+  }
+  ok[(size_t)c * Tw + w] = bits;
+}
+
+// port_conf[pl] = bit mask (over the compact ids of the pending pods' port lists) of the lists that
+// conflict with list pl: HostPortInfo.CheckConflict lifted to whole lists
+__global__ void port_conflict_kernel(DevObjects o, int num_port_lists, const int32_t* __restrict__ pc_of,
+                                     unsigned long long* __restrict__ port_conf) {
+  int pl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pl >= num_port_lists) return;
+  unsigned long long m = 0;
+  if (pc_of[pl] >= 0)
+    for (int q = 0; q < num_port_lists; ++q)
+      if (pc_of[q] >= 0 && port_lists_conflict(o, pl, q)) m |= 1ull << pc_of[q];
+  port_conf[pl] = m;
+}
+
+// per-pod SoA planes from the podspec table: the dense pass reads one row per pending pod
+__global__ void expand_pods_kernel(const int32_t* __restrict__ pend_spec, int p_begin, int Pl,
+                                   const int64_t* __restrict__ ps_req, const int32_t* __restrict__ spec_sc,
+                                   const int32_t* __restrict__ spec_dc, int A, const int* __restrict__ act_dim_dev,
+                                   int64_t* __restrict__ pod_req, int32_t* __restrict__ pod_sc,
+                                   int32_t* __restrict__ pod_dc) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Pl) return;
+  int spec = pend_spec[p_begin + p];
+  for (int a = 0; a < A; ++a) {
+    int64_t v = ps_req[(size_t)spec * R + act_dim_dev[a]];
+    pod_req[(size_t)a * Pl + p] = v > 0 ? v : LLONG_MIN;  // fit.go:670-704: a resource is only checked when requested > 0
+  }
+  pod_sc[p] = spec_sc[spec];
+  pod_dc[p] = spec_dc[spec];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: dense feasibility.  thread = pod (row in registers), template rows staged in smem and
+// broadcast, 32 templates per class-word, warp ballot = one output word (template-major bit matrix).
+// ------------------------------------------------------------------------------------------------
+constexpr int K1_THREADS = 256;
+constexpr int K1_TCHUNK = 128;  // templates per CTA
+constexpr int K1_WARPS = K1_THREADS / 32;
+constexpr int K1_PAD = K1_TCHUNK + 4;
+
+template <int A, bool REASONS>
+__global__ void __launch_bounds__(K1_THREADS)
+feasibility_kernel(int Pl, int Plw, int T, int Tw, int N, int U,
+                   const int64_t* __restrict__ pod_req, const int32_t* __restrict__ pod_sc,
+                   const int32_t* __restrict__ pod_dc, const int64_t* __restrict__ tmpl_free,
+                   const int32_t* __restrict__ tmpl_slots,
+                   const uint32_t* __restrict__ pre_ok, const uint32_t* __restrict__ post_ok,
+                   const uint8_t* __restrict__ pre_code, const uint8_t* __restrict__ post_code,
+                   uint32_t* __restrict__ fit_bits, int32_t* __restrict__ fit_count,
+                   uint8_t* __restrict__ reasons) {
+  __shared__ int64_t s_free[A > 0 ? A : 1][K1_TCHUNK];
+  __shared__ uint32_t s_out[K1_WARPS][K1_PAD];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int p = blockIdx.x * K1_THREADS + tid;
+  const int t0 = blockIdx.y * K1_TCHUNK;
+  const int tn = min(K1_TCHUNK, T - t0);
+
+  for (int i = tid; i < A * K1_TCHUNK; i += K1_THREADS) {
+    int a = i / K1_TCHUNK, j = i % K1_TCHUNK;
+    s_free[a][j] = (j < tn) ? tmpl_free[(size_t)a * T + t0 + j] : LLONG_MIN;
+  }
+  const bool valid = p < Pl;
+  int64_t req[A > 0 ? A : 1];
+#pragma unroll
+  for (int a = 0; a < A; ++a) req[a] = valid ? pod_req[(size_t)a * Pl + p] : LLONG_MAX;
+  const int sc = valid ? pod_sc[p] : 0;
+  const int dc = valid ? pod_dc[p] : 0;
+  __syncthreads();
+
+  for (int tw = 0; tw < K1_TCHUNK / 32; ++tw) {
+    const int wglob = t0 / 32 + tw;
+    if (wglob >= Tw) {
+      s_out[warp][tw * 32 + lane] = 0;
+      continue;
+    }
+    uint32_t w = valid ? (pre_ok[(size_t)sc * Tw + wglob] & post_ok[(size_t)dc * Tw + wglob]) : 0u;
+    uint32_t mine = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int tl = tw * 32 + j;
+      bool fail = false;
+#pragma unroll
+      for (int a = 0; a < A; ++a) fail |= req[a] > s_free[a][tl];
+      const bool fit = ((w >> j) & 1u) && !fail;
+      const uint32_t b = __ballot_sync(0xffffffffu, fit);
+      if (lane == j) mine = b;
+      if (REASONS) {
+        const int t = t0 + tl;
+        if (valid && t < T) {
+          // first failing plugin in Filter order: static plugins, NodeResourcesFit, then PTS / IPA
+          uint8_t r = pre_code[(size_t)sc * U + N + t] & 0x0F;
+          if (r == 0) r = (fail || tmpl_slots[t] < 1) ? CAE_R_FIT : post_code[(size_t)dc * T + t];
+          reasons[(size_t)t * Pl + p] = r;
+        }
+      }
+    }
+    s_out[warp][tw * 32 + lane] = mine;  // word for template t0 + tw*32 + lane, pods of this warp
+  }
+  __syncthreads();
+  // flush: 8 consecutive words (one 32 B sector) per template row; popcount -> per-template counts
+  const int pw0 = blockIdx.x * K1_WARPS;
+  for (int i = tid; i < K1_TCHUNK * K1_WARPS; i += K1_THREADS) {
+    const int tl = i / K1_WARPS, wv = i % K1_WARPS;
+    const int t = t0 + tl;
+    uint32_t word = (t < T) ? s_out[wv][tl] : 0u;
+    int c = __popc(word);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    c += __shfl_xor_sync(0xffffffffu, c, 4);
+    if (t < T) {
+      if (pw0 + wv < Plw && fit_bits) fit_bits[(size_t)t * Plw + pw0 + wv] = word;
+      if (wv == 0 && c) atomicAdd(&fit_count[t], c);
+    }
+  }
+}
+
+template <int A>
+static int launch_feas_a(Engine* e, bool want_reasons) {
+  dim3 grid((e->Pl + K1_THREADS - 1) / K1_THREADS, (e->T + K1_TCHUNK - 1) / K1_TCHUNK);
+  if (grid.x == 0 || grid.y == 0) return 0;
+  if (want_reasons)
+    feasibility_kernel<A, true><<<grid, K1_THREADS, 0, e->stream>>>(
+        e->Pl, e->Plw, e->T, e->Tw, e->N, e->U, e->d_pod_req, e->d_pod_sc, e->d_pod_dc, e->d_tmpl_free,
+        e->d_tmpl_slots, e->d_pre_ok, e->d_post_ok, e->d_pre_code, e->d_post_code, e->d_fit_bits, e->d_fit_count, e->d_reasons);
+  else
+    feasibility_kernel<A, false><<<grid, K1_THREADS, 0, e->stream>>>(
+        e->Pl, e->Plw, e->T, e->Tw, e->N, e->U, e->d_pod_req, e->d_pod_sc, e->d_pod_dc, e->d_tmpl_free,
+        e->d_tmpl_slots, e->d_pre_ok, e->d_post_ok, e->d_pre_code, e->d_post_code, e->d_fit_bits, e->d_fit_count, e->d_reasons);
+  e->stats.kernel_launches++;
+  return 0;
+}
+
+int launch_feasibility(Engine* e, bool want_reasons) {
+  CAE_CUDA(cudaMemsetAsync(e->d_fit_count, 0, sizeof(int32_t) * e->T, e->stream));
+  switch (e->A) {
+    case 0: launch_feas_a<0>(e, want_reasons); break;
+    case 1: launch_feas_a<1>(e, want_reasons); break;
+    case 2: launch_feas_a<2>(e, want_reasons); break;
+    case 3: launch_feas_a<3>(e, want_reasons); break;
+    case 4: launch_feas_a<4>(e, want_reasons); break;
+    case 5: launch_feas_a<5>(e, want_reasons); break;
+    case 6: launch_feas_a<6>(e, want_reasons); break;
+    case 7: launch_feas_a<7>(e, want_reasons); break;
+    default: launch_feas_a<8>(e, want_reasons); break;
+  }
+  CAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// exemplar x template reasons
+// ------------------------------------------------------------------------------------------------
+__global__ void group_reason_kernel(DevObjects o, int E, int T, int N, int U, const int32_t* __restrict__ spec_sc,
+                                    const int32_t* __restrict__ spec_dc, const uint8_t* __restrict__ pre_code,
+                                    const uint8_t* __restrict__ post_code, const int64_t* __restrict__ tmpl_free_all,
+                                    const int32_t* __restrict__ tmpl_slots, uint8_t* __restrict__ out) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  int t = blockIdx.y;
+  if (g >= E || t >= T) return;
+  uint8_t r = CAE_R_OK;
+  if (o.group_off[g + 1] > o.group_off[g]) {
+    int spec = o.pend_spec[o.group_off[g]];
+    r = pre_code[(size_t)spec_sc[spec] * U + N + t] & 0x0F;
+    if (r == 0) {
+      bool fail = tmpl_slots[t] < 1;
+      for (int a = 0; a < R; ++a) {
+        int64_t q = o.ps_req[(size_t)spec * R + a];
+        fail |= (q > 0 && q > tmpl_free_all[(size_t)a * T + t]);
+      }
+      r = fail ? CAE_R_FIT : post_code[(size_t)spec_dc[spec] * T + t];
+    }
+  }
+  out[(size_t)t * E + g] = r;
+}
+
+int launch_group_feasibility(Engine* e) {
+  if (e->E == 0 || e->T == 0) return 0;
+  dim3 grid((e->E + 127) / 128, e->T);
+  group_reason_kernel<<<grid, 128, 0, e->stream>>>(e->dobj, e->E, e->T, e->N, e->U, e->d_spec_sc, e->d_spec_dc,
+                                                    e->d_pre_code, e->d_post_code, e->d_tmpl_free_all,
+                                                    e->d_tmpl_slots, e->d_group_reason);
+  e->stats.kernel_launches++;
+  CAE_CUDA(cudaGetLastError());
+  e->group_reason_valid = true;
+  return 0;
+}
+
+int launch_class_matrices(Engine* e) {
+  if (e->SC > 0 && e->U > 0) {
+    dim3 grid((e->U + 127) / 128, e->SC);
+    class_matrix_kernel<<<grid, 128, 0, e->stream>>>(e->dobj, e->d_sclass, e->SC, e->U, e->d_pre_code);
+    e->stats.kernel_launches++;
+  }
+  if (e->Tw > 0) {
+    dim3 g1((e->Tw + 63) / 64, e->SC);
+    pack_ok_bits_kernel<<<g1, 64, 0, e->stream>>>(e->d_pre_code, e->U, e->N, e->SC, e->T, e->Tw, e->d_tmpl_slots, e->d_pre_ok);
+    dim3 g2((e->Tw + 63) / 64, e->DC);
+    pack_ok_bits_kernel<<<g2, 64, 0, e->stream>>>(e->d_post_code, e->T, 0, e->DC, e->T, e->Tw, nullptr, e->d_post_ok);
+    e->stats.kernel_launches += 2;
+  }
+  CAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_port_conflicts(Engine* e, int num_port_lists) {
+  port_conflict_kernel<<<(num_port_lists + 63) / 64, 64, 0, e->stream>>>(e->dobj, num_port_lists, e->d_pc_of, e->d_port_conf);
+  e->stats.kernel_launches++;
+  CAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_expand_pods(Engine* e) {
+  if (e->Pl == 0) return 0;
+  int* d_act = nullptr;
+  CAE_CUDA(cudaMalloc(&d_act, sizeof(int) * CAE_MAX_RES));
+  CAE_CUDA(cudaMemcpyAsync(d_act, e->act_dim, sizeof(int) * CAE_MAX_RES, cudaMemcpyHostToDevice, e->stream));
+  expand_pods_kernel<<<(e->Pl + 255) / 256, 256, 0, e->stream>>>(e->dobj.pend_spec, e->p_begin, e->Pl, e->dobj.ps_req,
+                                                                   e->d_spec_sc, e->d_spec_dc, e->A, d_act,
+                                                                   e->d_pod_req, e->d_pod_sc, e->d_pod_dc);
+  e->stats.kernel_launches++;
+  CAE_CUDA(cudaGetLastError());
+  CAE_CUDA(cudaStreamSynchronize(e->stream));
+  cudaFree(d_act);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0: DecreasingPodOrderer (estimator/decreasing_pod_orderer.go:46-88).  One CTA per template:
+// float64 score of every feasible group exemplar vs the template's allocatable, bitonic sort in
+// shared memory by (score desc, original index asc) — the stable order the oracle pins.
+// ------------------------------------------------------------------------------------------------
+__global__ void order_kernel(DevObjects o, int E, int T, int N, int t_begin, int n_sort,
+                             const uint8_t* __restrict__ group_reason, double* __restrict__ score_out,
+                             int32_t* __restrict__ order, int32_t* __restrict__ order_n) {
+  extern __shared__ unsigned char smem_raw[];
+  double* s_key = reinterpret_cast<double*>(smem_raw);
+  int32_t* s_idx = reinterpret_cast<int32_t*>(s_key + n_sort);
+  const int t = t_begin + blockIdx.x;
+  if (t >= T) return;
+  const int node = N + t;
+  const int64_t acpu = o.node_alloc[(size_t)node * R + CAE_RES_CPU], amem = o.node_alloc[(size_t)node * R + CAE_RES_MEM];
+  const bool use_cpu = o.node_has_alloc_cpu[node] && acpu > 0, use_mem = o.node_has_alloc_mem[node] && amem > 0;
+  for (int g = threadIdx.x; g < n_sort; g += blockDim.x) {
+    double sc = -DBL_MAX;  // infeasible / padding sinks to the end
+    int idx = INT_MAX;
+    if (g < E && o.group_off[g + 1] > o.group_off[g] && group_reason[(size_t)t * E + g] == CAE_R_OK) {
+      int spec = o.pend_spec[o.group_off[g]];
+      sc = 0.0;
+      // calculatePodScore: separate IEEE division and addition, no FMA contraction
+      if (use_cpu) sc = __dadd_rn(sc, __ddiv_rn(__ll2double_rn(o.ps_req[(size_t)spec * R + CAE_RES_CPU]), __ll2double_rn(acpu)));
+      if (use_mem) sc = __dadd_rn(sc, __ddiv_rn(__ll2double_rn(o.ps_req[(size_t)spec * R + CAE_RES_MEM]), __ll2double_rn(amem)));
+      idx = g;
+      if (score_out) score_out[(size_t)t * E + g] = sc;
+    }
+    s_key[g] = sc;
+    s_idx[g] = idx;
+  }
+  __syncthreads();
+  for (int k = 2; k <= n_sort; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n_sort; i += blockDim.x) {
+        int l = i ^ j;
+        if (l > i) {
+          double ki = s_key[i], kl = s_key[l];
+          int ii = s_idx[i], il = s_idx[l];
+          bool i_first = (ki > kl) || (ki == kl && ii < il);  // "i sorts before l"
+          bool up = (i & k) == 0;
+          if (up ? !i_first : i_first) {
+            s_key[i] = kl; s_key[l] = ki;
+            s_idx[i] = il; s_idx[l] = ii;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  int n = 0;
+  for (int g = threadIdx.x; g < E; g += blockDim.x) {
+    int idx = s_idx[g];
+    order[(size_t)t * E + g] = (idx == INT_MAX) ? -1 : idx;
+  }
+  if (threadIdx.x == 0) {
+    // feasible entries are a prefix
+    int lo = 0, hi = min(E, n_sort);
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (s_idx[mid] != INT_MAX) lo = mid + 1; else hi = mid; }
+    n = lo;
+    order_n[t] = n;
+  }
+}
+
+int launch_order(Engine* e) {
+  int nt = e->t_end - e->t_begin;
+  if (nt <= 0 || e->E == 0) return 0;
+  int n_sort = 1;
+  while (n_sort < e->E) n_sort <<= 1;
+  size_t smem = (size_t)n_sort * (sizeof(double) + sizeof(int32_t));
+  if (smem > 200 * 1024) { set_error("too many pod groups for the in-smem orderer"); return 1; }
+  CAE_CUDA(cudaFuncSetAttribute(order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  order_kernel<<<nt, 256, smem, e->stream>>>(e->dobj, e->E, e->T, e->N, e->t_begin, n_sort, e->d_group_reason,
+                                              e->d_score, e->d_order, e->d_order_n);
+  e->stats.kernel_launches++;
+  CAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: BinpackingNodeEstimator.Estimate (estimator/binpacking_estimator.go:97-247), one WARP per
+// template (templates are independent simulations; inside one, placement order is sequential by
+// construction).  Per-template node state lives in a per-warp global scratch slab (L1/L2 resident),
+// lanes stride over the open nodes.  Groups of identical pods without topology-spread / inter-pod
+// affinity are placed in closed form:
+//   * tryToScheduleOnExistingNodes (:141-164): SchedulePodOnAnyNodeMatching scans cyclically from
+//     lastIndex (plugin_runner.go:81,123), i.e. identical pods are dealt round-robin over the new
+//     nodes with spare capacity k_j.  n pods => every node gets min(k_j, L) plus one more for the
+//     first `rem` nodes (cyclic order from the start index) with k_j > L.
+//   * tryToScheduleOnNewNodes (:168-247): only the last added node is tried, so after the pass above
+//     each new node simply takes min(remaining, k_new) pods until the limiter denies (:222).
+// ------------------------------------------------------------------------------------------------
+struct PackParams {
+  int E, T, N, U, A, t_begin, t_end, cap;
+  const int32_t* order; const int32_t* order_n;
+  const uint8_t* pre_code; const int32_t* spec_sc;
+  const int64_t* tmpl_free;  // [A][T]
+  const int32_t* tmpl_slots;
+  const int32_t* max_nodes;
+  const int32_t* pc_of; const unsigned long long* port_conf;
+  int act_dim[CAE_MAX_RES];
+  int32_t* node_count; int32_t* pod_count; int32_t* sched;  // sched [T][E]
+  int32_t* work_counter;
+  unsigned char* scratch; size_t scratch_per_warp;
+};
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_max(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// how many more copies of the pod fit: min over requested dims of floor(free/req), pod slots, ports
+__device__ __forceinline__ int capacity_of(const int64_t* req, int A, const int64_t* nfree, int cap_stride, int j,
+                                           int slots, bool port_block, bool has_ports, int limit) {
+  int k = min(slots, limit);
+  if (k <= 0) return 0;
+#pragma unroll 1
+  for (int a = 0; a < A; ++a) {
+    int64_t q = req[a];
+    if (q <= 0) continue;
+    int64_t f = nfree[(size_t)a * cap_stride + j];
+    if (f < q) return 0;
+    int64_t c = f / q;
+    if (c < k) k = (int)c;
+  }
+  if (has_ports) k = port_block ? 0 : min(k, 1);
+  return k;
+}
+
+__global__ void __launch_bounds__(128) pack_kernel(DevObjects o, PackParams p) {
+  const int lane = threadIdx.x & 31;
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  unsigned char* slab = p.scratch + (size_t)warp_global * p.scratch_per_warp;
+  const int cap = p.cap;
+  // slab layout: nfree[A][cap] int64 | slots[cap] int32 | kbuf[cap] int32 | ports[cap] u64 | sched flag [cap] u8
+  int64_t* nfree = reinterpret_cast<int64_t*>(slab);
+  unsigned long long* nports = reinterpret_cast<unsigned long long*>(nfree + (size_t)p.A * cap);
+  int32_t* nslots = reinterpret_cast<int32_t*>(nports + cap);
+  int32_t* kbuf = nslots + cap;
+  uint8_t* nsched = reinterpret_cast<uint8_t*>(kbuf + cap);
+
+  for (;;) {
+    int t = 0;
+    if (lane == 0) t = p.t_begin + atomicAdd(p.work_counter, 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= p.t_end) break;
+
+    int64_t tfree[CAE_MAX_RES];
+    for (int a = 0; a < p.A; ++a) tfree[a] = p.tmpl_free[(size_t)a * p.T + t];
+    const int tslots = p.tmpl_slots[t];
+    // DaemonSet host ports on a fresh node: evaluated through pre_code (NodePorts vs pods on node)
+    const int max_nodes = p.max_nodes ? p.max_nodes[t] : 0;
+    int n_new = 0;         // nodes added so far (estimationState.newNodeNameIndex)
+    int nodes_with_pods = 0;
+    int pods_total = 0;
+    int last_index = 0;    // SchedulerPluginRunner.lastIndex, fresh per Estimate
+    bool new_nodes_available = true;
+    const int n_groups = p.order_n[t];
+
+    for (int gi = 0; gi < n_groups; ++gi) {
+      const int g = p.order[(size_t)t * p.E + gi];
+      const int pb = o.group_off[g];
+      int n = o.group_off[g + 1] - pb;
+      const int spec = o.pend_spec[pb];
+      int64_t req[CAE_MAX_RES];
+      for (int a = 0; a < p.A; ++a) req[a] = o.ps_req[(size_t)spec * R + p.act_dim[a]];
+      const int sc = p.spec_sc[spec];
+      const uint8_t code_new = p.pre_code[(size_t)sc * p.U + p.N + p.T + t];  // sanitized copy of the template
+      const bool static_ok = (code_new & 0x0F) == 0;
+      const int plist = o.ps_port_list[spec];
+      const bool has_ports = o.port_off[plist + 1] > o.port_off[plist];
+      const unsigned long long pconf = has_ports ? p.port_conf[plist] : 0ull;   // lists this pod collides with
+      const unsigned long long pbit = has_ports ? (1ull << p.pc_of[plist]) : 0ull;
+      int placed = 0;
+
+      // ---- tryToScheduleOnExistingNodes: round-robin over the nodes added so far -------------
+      if (n_new > 0 && static_ok) {
+        const int list_len = p.N + n_new;
+        const int s = last_index >= p.N ? last_index - p.N : 0;  // first new node in cyclic scan order
+        long long total = 0;
+        int kmax = 0;
+        for (int j = lane; j < n_new; j += 32) {
+          bool pblock = (nports[j] & pconf) != 0ull;
+          int k = capacity_of(req, p.A, nfree, cap, j, nslots[j], pblock, has_ports, n);
+          kbuf[j] = k;
+          total += k;
+          kmax = max(kmax, k);
+        }
+        total = warp_sum_ll(total);
+        kmax = warp_max(kmax);
+        __syncwarp();
+        if (total > 0) {
+          int L, rem;
+          if (total <= n) { L = kmax; rem = 0; }
+          else {
+            // largest L with sum_j min(k_j, L) <= n
+            int lo = 0, hi = kmax;  // f(lo) <= n < f(hi)
+            while (hi - lo > 1) {
+              int mid = (lo + hi) >> 1;
+              long long f = 0;
+              for (int j = lane; j < n_new; j += 32) f += min(kbuf[j], mid);
+              f = warp_sum_ll(f);
+              if (f <= n) lo = mid; else hi = mid;
+            }
+            L = lo;
+            long long f = 0;
+            for (int j = lane; j < n_new; j += 32) f += min(kbuf[j], L);
+            f = warp_sum_ll(f);
+            rem = (int)(n - f);
+          }
+          // walk the nodes in cyclic order from s; the first `rem` with k > L get one extra pod
+          int seen = 0, last_pos = -1, newly = 0, got = 0;
+          for (int base = 0; base < n_new; base += 32) {
+            int pos = base + lane;
+            bool in = pos < n_new;
+            int j = in ? (s + pos) % n_new : 0;
+            int k = in ? kbuf[j] : 0;
+            bool extra_c = in && k > L;
+            unsigned m = __ballot_sync(0xffffffffu, extra_c);
+            int rank = seen + __popc(m & ((1u << lane) - 1));
+            int mj = in ? min(k, L) + ((extra_c && rank < rem) ? 1 : 0) : 0;
+            seen += __popc(m);
+            if (mj > 0) {
+              for (int a = 0; a < p.A; ++a) if (req[a] > 0) nfree[(size_t)a * cap + j] -= (int64_t)mj * req[a];
+              nslots[j] -= mj;
+              nports[j] |= pbit;
+              if (!nsched[j]) { nsched[j] = 1; newly++; }
+              got += mj;
+              // the pod placed last: in the final (partial or full) lap, the furthest position served
+              bool final_lap = rem > 0 ? (extra_c && rank < rem) : (k >= L);
+              if (final_lap) last_pos = pos;
+            }
+          }
+          got = warp_sum(got);
+          newly = warp_sum(newly);
+          last_pos = warp_max(last_pos);
+          placed += got;
+          nodes_with_pods += newly;
+          n -= got;
+          if (last_pos >= 0) {
+            int jl = (s + last_pos) % n_new;
+            last_index = (p.N + jl + 1) % list_len;
+          }
+          __syncwarp();
+        }
+      }
+
+      // ---- tryToScheduleOnNewNodes ----------------------------------------------------------
+      if (n > 0 && new_nodes_available) {
+        // after the pass above no added node (incl. the last one) can take this pod any more
+        bool stop = (n_new > 0) && !nsched[n_new - 1];  // last node still empty (:212)
+        stop = __shfl_sync(0xffffffffu, stop, 0);
+        if (!stop) {
+          int k_new = 0;
+          if (static_ok) {
+            k_new = min(tslots, n);
+            for (int a = 0; a < p.A && k_new > 0; ++a) {
+              if (req[a] <= 0) continue;
+              if (tfree[a] < req[a]) { k_new = 0; break; }
+              int64_t c = tfree[a] / req[a];
+              if (c < k_new) k_new = (int)c;
+            }
+            if (has_ports) k_new = min(k_new, 1);  // DaemonSet port conflicts already in static_ok
+          }
+          long long allowed = max_nodes < 0 ? 0 : (max_nodes == 0 ? (long long)INT_MAX : max((long long)max_nodes - n_new, 0ll));
+          allowed = min(allowed, (long long)(cap - n_new));
+          int add;
+          int fill = 0;
+          if (k_new <= 0) {
+            add = allowed >= 1 ? 1 : 0;  // one node is added, the pod still fails on it (:235-240)
+            if (allowed < 1) new_nodes_available = false;
+          } else {
+            long long need = ((long long)n + k_new - 1) / k_new;
+            if (need > allowed) { add = (int)allowed; new_nodes_available = false; }
+            else add = (int)need;
+            fill = (int)min((long long)n, (long long)add * k_new);
+          }
+          for (int i = lane; i < add; i += 32) {
+            int j = n_new + i;
+            int mj = k_new <= 0 ? 0 : min(k_new, fill - i * k_new);
+            for (int a = 0; a < p.A; ++a) nfree[(size_t)a * cap + j] = tfree[a] - (req[a] > 0 ? (int64_t)mj * req[a] : 0);
+            nslots[j] = tslots - mj;
+            nports[j] = mj > 0 ? pbit : 0ull;
+            nsched[j] = mj > 0;
+          }
+          if (k_new > 0) { nodes_with_pods += add; placed += fill; n -= fill; }
+          n_new += add;
+          __syncwarp();
+        }
+      }
+      pods_total += placed;
+      if (lane == 0 && p.sched) p.sched[(size_t)t * p.E + g] = placed;
+    }
+    if (lane == 0) {
+      p.node_count[t] = nodes_with_pods;
+      p.pod_count[t] = pods_total;
+    }
+    __syncwarp();
+  }
+}
+
+int launch_pack(Engine* e) {
+  int nt = e->t_end - e->t_begin;
+  if (nt <= 0) return 0;
+  PackParams p{};
+  p.E = e->E; p.T = e->T; p.N = e->N; p.U = e->U; p.A = e->A; p.t_begin = e->t_begin; p.t_end = e->t_end;
+  for (int a = 0; a < CAE_MAX_RES; ++a) p.act_dim[a] = e->act_dim[a];
+  p.order = e->d_order; p.order_n = e->d_order_n; p.pre_code = e->d_pre_code; p.spec_sc = e->d_spec_sc;
+  p.tmpl_free = e->d_tmpl_free; p.tmpl_slots = e->d_tmpl_slots; p.max_nodes = e->d_max_nodes;
+  p.pc_of = e->d_pc_of; p.port_conf = e->d_port_conf;
+  p.node_count = e->d_counts2; p.pod_count = e->d_counts2 + e->T; p.sched = e->d_sched;
+  p.work_counter = e->d_work_counter;
+  // node capacity of a slab: the largest limiter cap, or (unlimited) one node per pod + 1
+  // (every added node but possibly the last holds >= 1 pod)
+  int cap = std::max(1, std::min(e->P + 1, e->pack_cap));
+  p.cap = cap;
+  size_t per_warp = (size_t)cap * ((size_t)e->A * 8 + 8 + 4 + 4 + 1);
+  per_warp = (per_warp + 255) & ~(size_t)255;
+  int warps = std::min(nt, e->sm_count * 16);
+  const size_t budget = (size_t)16 << 30;  // keep the slabs within 16 GiB of the 180 GB HBM
+  if (per_warp * warps > budget) warps = (int)std::max<size_t>(1, budget / per_warp);
+  int blocks = (warps + 3) / 4;
+  warps = blocks * 4;
+  size_t need = per_warp * warps;
+  if (need > e->pack_scratch_bytes) {
+    if (e->d_pack_scratch) cudaFree(e->d_pack_scratch);
+    e->d_pack_scratch = nullptr;
+    CAE_CUDA(cudaMalloc(&e->d_pack_scratch, need));
+    e->pack_scratch_bytes = need;
+  }
+  p.scratch = static_cast<unsigned char*>(e->d_pack_scratch);
+  p.scratch_per_warp = per_warp;
+  CAE_CUDA(cudaMemsetAsync(e->d_work_counter, 0, sizeof(int32_t), e->stream));
+  pack_kernel<<<blocks, 128, 0, e->stream>>>(e->dobj, p);
+  e->stats.kernel_launches++;
+  CAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: least-waste score per option (expander/waste/waste.go:37-73): one warp per template sums the
+// requests of its scheduled pods (sched[t][g] x exemplar request; groups are homogeneous).
+// ------------------------------------------------------------------------------------------------
+__global__ void waste_kernel(DevObjects o, int E, int T, int N, const int32_t* __restrict__ node_count,
+                             const int32_t* __restrict__ sched, double* __restrict__ waste) {
+  int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (t >= T) return;
+  long long cpu = 0, mem = 0;
+  for (int g = lane; g < E; g += 32) {
+    int c = sched[(size_t)t * E + g];
+    if (c > 0) {
+      int spec = o.pend_spec[o.group_off[g]];
+      cpu += (long long)c * o.ps_req[(size_t)spec * R + CAE_RES_CPU];
+      mem += (long long)c * o.ps_req[(size_t)spec * R + CAE_RES_MEM];
+    }
+  }
+  cpu = warp_sum_ll(cpu);
+  mem = warp_sum_ll(mem);
+  if (lane == 0) {
+    long long nc = node_count[t];
+    long long acpu = o.node_cap_cpu[N + t] * nc, amem = o.node_cap_mem[N + t] * nc;
+    double wc = __ddiv_rn(__ll2double_rn(acpu - cpu), __ll2double_rn(acpu));
+    double wm = __ddiv_rn(__ll2double_rn(amem - mem), __ll2double_rn(amem));
+    waste[t] = nc > 0 ? __dadd_rn(wc, wm) : 0.0;
+  }
+}
+
+int launch_expander(Engine* e, const int32_t*, int, const int32_t* d_node_count, const int32_t*,
+                    const int32_t* d_sched, uint8_t*, double* d_waste) {
+  if (e->T == 0) return 0;
+  int threads = 128, warps_per_block = threads / 32;
+  waste_kernel<<<(e->T + warps_per_block - 1) / warps_per_block, threads, 0, e->stream>>>(e->dobj, e->E, e->T, e->N,
+                                                                                           d_node_count, d_sched, d_waste);
+  e->stats.kernel_launches++;
+  CAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace cae

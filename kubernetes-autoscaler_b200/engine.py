@@ -1,0 +1,177 @@
+"""Python binding of the engine's C ABI (``include/caengine.h``) — what the cgo shim does in Go.
+
+There is no CPU path here: if ``libcaengine.so`` or a CUDA device is missing every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import capi
+from .encode import EncodedObjects
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class EngineUnsupported(EngineError):
+    """Status > 0: the input uses something the engine refuses; the caller must use the stock path."""
+
+
+class PinnedArray:
+    """numpy view over page-locked memory from cae_host_alloc."""
+
+    def __init__(self, lib, shape, dtype) -> None:
+        self._lib = lib
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self._ptr = lib.cae_host_alloc(max(self.nbytes, 16))
+        if not self._ptr:
+            raise EngineError("cae_host_alloc failed")
+        buf = (C.c_uint8 * max(self.nbytes, 1)).from_address(self._ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def close(self) -> None:
+        if self._ptr:
+            self.array = None
+            self._lib.cae_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine:
+    def __init__(self, device: int = 0, rank: int = 0, world_size: int = 1, want_reasons: bool = False) -> None:
+        self.lib = capi.load_engine_lib()
+        self.lib.cae_host_alloc.argtypes = [C.c_size_t]
+        self.lib.cae_host_alloc.restype = C.c_void_p
+        self.lib.cae_host_free.argtypes = [C.c_void_p]
+        self.lib.cae_host_free.restype = None
+        cfg = capi.cae_config()
+        cfg.abi_version = capi.CONST["CAE_ABI_VERSION"]
+        cfg.device, cfg.rank, cfg.world_size, cfg.want_reasons = device, rank, world_size, int(want_reasons)
+        self.rank, self.world_size, self.want_reasons = rank, world_size, want_reasons
+        h = C.c_void_p()
+        self._check(self.lib.cae_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+        self.enc: Optional[EncodedObjects] = None
+        self._pinned = {}
+
+    # ---- plumbing ---------------------------------------------------------------------------
+    def _check(self, rc: int) -> None:
+        if rc == 0:
+            return
+        msg = (self.lib.cae_last_error() or b"").decode()
+        if rc > 0:
+            raise EngineUnsupported(msg)
+        raise EngineError("caengine status %d: %s" % (rc, msg))
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            for p in self._pinned.values():
+                p.close()
+            self._pinned = {}
+            self.lib.cae_destroy(self.h)
+            self.h = None
+
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _pin(self, name: str, shape, dtype) -> np.ndarray:
+        cur = self._pinned.get(name)
+        if cur is None or cur.array.shape != tuple(shape) or cur.array.dtype != np.dtype(dtype):
+            if cur is not None:
+                cur.close()
+            cur = PinnedArray(self.lib, tuple(shape), dtype)
+            self._pinned[name] = cur
+        return cur.array
+
+    # ---- shards -------------------------------------------------------------------------------
+    def pod_shard(self, P: int) -> Tuple[int, int]:
+        W, r = self.world_size, self.rank
+        b = (P * r // W) // 32 * 32
+        e = P * (r + 1) // W
+        if r + 1 < W:
+            e = e // 32 * 32
+        return b, e
+
+    def template_shard(self, T: int) -> Tuple[int, int]:
+        W, r = self.world_size, self.rank
+        return T * r // W, T * (r + 1) // W
+
+    # ---- API ------------------------------------------------------------------------------------
+    def load(self, enc: EncodedObjects) -> None:
+        self.enc = enc
+        self._check(self.lib.cae_load(self.h, enc.ptr()))
+
+    def feasibility(self, want_bits: bool = True):
+        """Dense pods x templates pass. Returns (fit_bits [T][ceil(Pl/32)] uint32 | None,
+        reasons [T][Pl] uint8 | None, fit_count [T] int32) for this rank's pod shard."""
+        enc = self.enc
+        pb, pe = self.pod_shard(enc.P)
+        Pl, T = pe - pb, enc.T
+        bits = self._pin("bits", (T, (Pl + 31) // 32), np.uint32) if want_bits else None
+        reasons = self._pin("reasons", (T, Pl), np.uint8) if self.want_reasons else None
+        count = self._pin("count", (T,), np.int32)
+        self._check(self.lib.cae_feasibility(
+            self.h, bits.ctypes.data_as(C.c_void_p) if bits is not None else None,
+            reasons.ctypes.data_as(C.c_void_p) if reasons is not None else None,
+            count.ctypes.data_as(C.c_void_p)))
+        return bits, reasons, count
+
+    def feasibility_groups(self) -> np.ndarray:
+        enc = self.enc
+        out = np.zeros((enc.T, enc.E), np.uint8)
+        self._check(self.lib.cae_feasibility_groups(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def estimate_all(self, max_nodes: Optional[Sequence[int]] = None):
+        """Returns node_count[T], pod_count[T], sched_count[T][E], order[T][E] (rows outside this
+        rank's template shard are zero / -1)."""
+        enc = self.enc
+        T, E = enc.T, enc.E
+        mn = None if max_nodes is None else np.ascontiguousarray(max_nodes, np.int32)
+        node_count = np.zeros(T, np.int32)
+        pod_count = np.zeros(T, np.int32)
+        sched = np.zeros((T, E), np.int32)
+        order = np.full((T, E), -1, np.int32)
+        vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        self._check(self.lib.cae_estimate_all(self.h, vp(mn), vp(node_count), vp(pod_count), vp(sched), vp(order)))
+        return node_count, pod_count, sched, order
+
+    def expander_best(self, chain: Sequence[int], node_count, pod_count, sched):
+        enc = self.enc
+        ch = np.asarray(chain, np.int32)
+        nc = np.ascontiguousarray(node_count, np.int32)
+        pc = np.ascontiguousarray(pod_count, np.int32)
+        sc = np.ascontiguousarray(sched, np.int32)
+        mask = np.zeros(enc.T, np.uint8)
+        waste = np.zeros(enc.T, np.float64)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        self._check(self.lib.cae_expander_best(self.h, vp(ch), len(ch), vp(nc), vp(pc), vp(sc), vp(mask), vp(waste)))
+        return mask, waste
+
+    def stats(self) -> capi.cae_stats:
+        s = capi.cae_stats()
+        self._check(self.lib.cae_get_stats(self.h, C.byref(s)))
+        return s
+
+    def device_buffer(self, which: int) -> Tuple[int, int]:
+        n = C.c_size_t(0)
+        p = self.lib.cae_device_buffer(self.h, which, C.byref(n))
+        return int(p or 0), int(n.value)
+
+
+def unpack_bits(bits: np.ndarray, P: int) -> np.ndarray:
+    """fit_bits [T][Pw] uint32 -> bool [T][P]."""
+    b = np.unpackbits(bits.view(np.uint8), axis=1, bitorder="little")
+    return b[:, :P].astype(bool)

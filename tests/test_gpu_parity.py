@@ -1,0 +1,195 @@
+"""GPU parity: the CUDA engine (through the C ABI) vs the CPU oracle on the same inputs.
+Bit-exact bar: integer / index work (reasons, bit matrix, counts, node counts, orders) and the
+float64 expander / orderer scores (IEEE div+add restated without FMA) must be IDENTICAL."""
+import numpy as np
+import pytest
+
+from kubernetes_autoscaler_b200 import synth
+from kubernetes_autoscaler_b200.encode import encode
+from kubernetes_autoscaler_b200.objects import (BuildTestNode, BuildTestPod, HostPort, NodeInfo, NodeSelectorTerm,
+                                                Requirement, Taint, Toleration, WithHostPort, WithLabels,
+                                                WithNamespace, WithNodeNamesAffinity, WithNodeSelector, WithResource,
+                                                WithTolerations, makeNode, makePodEquivalenceGroup)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import __graft_entry__ as g
+    g.build()
+    from kubernetes_autoscaler_b200.engine import Engine
+    e = Engine(device=0, want_reasons=True)
+    yield e
+    e.close()
+
+
+def _check_dense(eng, oracle, enc):
+    from kubernetes_autoscaler_b200.engine import unpack_bits
+    eng.load(enc)
+    bits, reasons, count = eng.feasibility()
+    want, _ = oracle.feasibility_dense(enc)
+    assert np.array_equal(reasons, want)
+    assert np.array_equal(unpack_bits(bits, enc.P), want == 0)
+    assert np.array_equal(count, (want == 0).sum(axis=1))
+    assert np.array_equal(eng.feasibility_groups(), oracle.feasibility_groups(enc))
+
+
+def _check_estimate(eng, oracle, enc, caps):
+    eng.load(enc)
+    caps = np.asarray(caps, np.int32)
+    nc, pc, sched, order = eng.estimate_all(caps)
+    onc, opc, osched, oorder, _ = oracle.estimate_all(enc, caps)
+    assert np.array_equal(nc, onc), (nc, onc)
+    assert np.array_equal(pc, opc)
+    assert np.array_equal(sched, osched)
+    assert np.array_equal(order, oorder)
+    for chain in ([0], [1], [2], [0, 1, 2], [2, 0]):
+        mask, waste = eng.expander_best(chain, nc, pc, sched)
+        omask, owaste = oracle.expander(enc, chain, nc, pc, sched)
+        assert np.array_equal(mask, omask), chain
+        assert np.array_equal(waste, owaste)  # float64, bit-identical
+    return nc, pc
+
+
+def test_c1_dense_and_estimate(eng, oracle):
+    """BASELINE config 1: 1000 pods x 50 templates, NodeResourcesFit only."""
+    enc = synth.generate(1)
+    _check_dense(eng, oracle, enc)
+    _check_estimate(eng, oracle, enc, np.full(enc.T, 1000))
+    _check_estimate(eng, oracle, enc, np.zeros(enc.T))          # unlimited
+    _check_estimate(eng, oracle, enc, np.full(enc.T, -1))       # limiter forbids any node
+    _check_estimate(eng, oracle, enc, np.arange(enc.T) % 7)     # mixed caps incl. 0
+
+
+def test_c2_shaped_dense(eng, oracle):
+    """Config 2 predicates (taints/tolerations, nodeSelector) at a size the oracle finishes in seconds."""
+    enc = synth.generate(2, pods=20_000, templates=300)
+    _check_dense(eng, oracle, enc)
+
+
+def test_c2_shaped_estimate(eng, oracle):
+    enc = synth.generate(2, pods=6_000, templates=96)
+    _check_estimate(eng, oracle, enc, np.full(enc.T, 1000))
+    _check_estimate(eng, oracle, enc, np.full(enc.T, 25))
+
+
+def _kat_fixture(millicores, memory, pods_per_node, groups):
+    cluster = [NodeInfo(makeNode(100, 100, 10, "oldnode", "zone-jupiter"))]
+    return encode(cluster, [NodeInfo(makeNode(millicores, memory, pods_per_node, "template", "zone-mars"))], groups)
+
+
+def _pod(cpu, mem, *opts):
+    return BuildTestPod("estimatee", cpu, mem, WithNamespace("universe"), WithLabels({"app": "estimatee"}), *opts)
+
+
+@pytest.mark.parametrize("cpu,mem,ppn,max_nodes,groups,exp", [
+    (350 * 3 - 50, 2000, 10, 0, lambda: [makePodEquivalenceGroup(_pod(350, 1000), 10)], (5, 10)),
+    (10000, 20000, 10, 0, lambda: [makePodEquivalenceGroup(_pod(10, 100), 20)], (2, 20)),
+    (1000, 5000, 10, 0, lambda: [makePodEquivalenceGroup(_pod(200, 1000, WithHostPort(5555)), 8)], (8, 8)),
+    (1000, 5000, 10, 5, lambda: [makePodEquivalenceGroup(_pod(500, 1000), 20)], (5, 10)),
+    (1000, 5000, 10, 5, lambda: [makePodEquivalenceGroup(_pod(50, 1000), 10), makePodEquivalenceGroup(_pod(500, 1000), 10)], (5, 10)),
+    (1000, 5000, 100, 3000, lambda: [makePodEquivalenceGroup(_pod(50, 100), 50000), makePodEquivalenceGroup(_pod(95, 190), 1000)], (2595, 51000)),
+], ids=["simple", "pods-per-node", "hostport", "limiter", "decreasing-order", "benchmark-vector"])
+def test_reference_kats_on_gpu(eng, oracle, cpu, mem, ppn, max_nodes, groups, exp):
+    """estimator/binpacking_estimator_test.go:91-172 and :249-296 through the engine."""
+    enc = _kat_fixture(cpu, mem, ppn, groups())
+    nc, pc = _check_estimate(eng, oracle, enc, [max_nodes])
+    assert (int(nc[0]), int(pc[0])) == exp
+
+
+def test_estimator_facade_reads_like_the_reference(eng):
+    """binpacking_estimator_test.go:226-246 with the reference's call shape."""
+    from kubernetes_autoscaler_b200.estimator import (GpuBinpackingNodeEstimator, NewStaticThreshold,
+                                                      NewThresholdBasedEstimationLimiter)
+    high = makePodEquivalenceGroup(_pod(500, 1000), 10)
+    groups = [makePodEquivalenceGroup(_pod(50, 1000), 10), high]
+    snapshot = [NodeInfo(makeNode(100, 100, 10, "oldnode", "zone-jupiter"))]
+    limiter = NewThresholdBasedEstimationLimiter([NewStaticThreshold(5, 0)])
+    estimator = GpuBinpackingNodeEstimator(snapshot, limiter, None, engine=eng)
+    nodes, pods = estimator.Estimate(groups, NodeInfo(makeNode(1000, 5000, 10, "template", "zone-mars")), None)
+    assert nodes == 5 and len(pods) == 10
+    assert all(a is b for a, b in zip(pods, high.pods))   # expectProcessedPods: same objects, same order
+
+
+def test_static_predicates_edge_cases(eng, oracle):
+    """Tolerations (wildcards, Equal/Exists, effects), PreferNoSchedule ignored, unschedulable nodes,
+    nodeSelector + affinity (In/NotIn/Exists/DoesNotExist/Gt/Lt, empty terms, metadata.name fields),
+    extended resources absent from the node, zero-request pods, host-port wildcard rules."""
+    def node(name, labels=None, taints=None, unsched=False, cpu=4000, mem=8 << 30, extra=None, pods=10):
+        n = BuildTestNode(name, cpu, mem)
+        n.labels = dict(labels or {})
+        n.labels["kubernetes.io/hostname"] = name
+        n.taints = list(taints or [])
+        n.unschedulable = unsched
+        n.allocatable["pods"] = pods
+        for k, v in (extra or {}).items():
+            n.allocatable[k] = v
+            n.capacity[k] = v
+        return n
+    ds = BuildTestPod("ds", 100, 100)
+    ds.host_ports = [HostPort(8080, "TCP", "10.0.0.1"), HostPort(53, "UDP", "")]
+    templates = [
+        NodeInfo(node("plain")),
+        NodeInfo(node("tainted", taints=[Taint("dedicated", "gpu", "NoSchedule")])),
+        NodeInfo(node("tainted2", taints=[Taint("dedicated", "gpu", "NoSchedule"), Taint("x", "", "NoExecute")])),
+        NodeInfo(node("prefer", taints=[Taint("soft", "1", "PreferNoSchedule")])),
+        NodeInfo(node("cordoned", unsched=True)),
+        NodeInfo(node("labeled", labels={"pool": "a", "gen": "7", "zone": "z1"})),
+        NodeInfo(node("labeled-b", labels={"pool": "b", "gen": "12", "zone": "z2"})),
+        NodeInfo(node("gpu", extra={"nvidia.com/gpu": 4})),
+        NodeInfo(node("full", pods=1), [ds]),
+        NodeInfo(node("ds-ports"), [ds]),
+        NodeInfo(node("tiny", cpu=100, mem=100)),
+    ]
+    T = Toleration
+    pods = [
+        BuildTestPod("p-plain", 100, 100),
+        BuildTestPod("p-zero", 0, 0),
+        BuildTestPod("p-noreq", -1, -1),
+        BuildTestPod("p-big", 5000, 100),
+        BuildTestPod("p-tol-eq", 100, 100, WithTolerations(T("dedicated", "Equal", "gpu", "NoSchedule"))),
+        BuildTestPod("p-tol-eq-wrong", 100, 100, WithTolerations(T("dedicated", "Equal", "cpu", "NoSchedule"))),
+        BuildTestPod("p-tol-exists", 100, 100, WithTolerations(T("dedicated", "Exists", "", ""))),
+        BuildTestPod("p-tol-all", 100, 100, WithTolerations(T("", "Exists", "", ""))),
+        BuildTestPod("p-tol-noexec", 100, 100, WithTolerations(T("", "Exists", "", "NoExecute"))),
+        BuildTestPod("p-tol-unsched", 100, 100, WithTolerations(T("node.kubernetes.io/unschedulable", "Exists", "", "NoSchedule"))),
+        BuildTestPod("p-tol-lt", 100, 100, WithTolerations(T("dedicated", "Lt", "5", "NoSchedule"))),
+        BuildTestPod("p-sel", 100, 100, WithNodeSelector({"pool": "a"})),
+        BuildTestPod("p-sel2", 100, 100, WithNodeSelector({"pool": "a", "zone": "z2"})),
+        BuildTestPod("p-gpu", 100, 100, WithResource("nvidia.com/gpu", 2)),
+        BuildTestPod("p-gpu8", 100, 100, WithResource("nvidia.com/gpu", 8)),
+        BuildTestPod("p-port", 100, 100, WithHostPort(8080)),
+        BuildTestPod("p-port-udp", 100, 100),
+        BuildTestPod("p-port-otherip", 100, 100),
+        BuildTestPod("p-name", 100, 100, WithNodeNamesAffinity("labeled")),
+        BuildTestPod("p-nodename", 100, 100),
+    ]
+    pods[16].host_ports = [HostPort(53, "UDP", "1.2.3.4")]
+    pods[17].host_ports = [HostPort(8080, "TCP", "10.0.0.2")]
+    pods[19].node_name = "gpu"
+
+    def aff(*terms):
+        p = BuildTestPod("p-aff%d" % len(pods), 100, 100)
+        p.node_affinity_terms = list(terms)
+        pods.append(p)
+    R = Requirement
+    aff(NodeSelectorTerm([R("pool", "In", ["a", "c"])]))
+    aff(NodeSelectorTerm([R("pool", "NotIn", ["a"])]))
+    aff(NodeSelectorTerm([R("pool", "Exists")]), NodeSelectorTerm([R("gen", "DoesNotExist")]))
+    aff(NodeSelectorTerm([R("gen", "Gt", ["8"])]))
+    aff(NodeSelectorTerm([R("gen", "Lt", ["8"])]))
+    aff(NodeSelectorTerm([R("zone", "Gt", ["1"])]))                      # non-integer label value
+    aff(NodeSelectorTerm())                                              # only an empty term: matches nothing
+    aff()                                                                # required with zero terms
+    aff(NodeSelectorTerm([R("pool", "In", ["a"])], [R("metadata.name", "NotIn", ["labeled"])]))
+    aff(NodeSelectorTerm(match_fields=[R("metadata.name", "In", ["labeled"])]),
+        NodeSelectorTerm(match_fields=[R("metadata.name", "In", ["gpu"])]))
+    aff(NodeSelectorTerm(match_fields=[R("metadata.name", "In", ["labeled"]), R("metadata.name", "In", ["gpu"])]))
+    groups = [makePodEquivalenceGroup(p, 3) for p in pods]
+    cluster = [NodeInfo(node("existing", labels={"pool": "a"}))]
+    enc = encode(cluster, templates, groups)
+    _check_dense(eng, oracle, enc)
+    _check_estimate(eng, oracle, enc, np.full(enc.T, 10))
+    want = oracle.feasibility_groups(enc)
+    assert len(set(want.ravel().tolist())) >= 7   # the case really exercises many distinct reasons
