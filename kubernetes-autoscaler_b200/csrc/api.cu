@@ -48,7 +48,10 @@ template <class T>
 static int dev_alloc(Engine* e, T** dev, size_t n, bool zero = false) {
   void* p = nullptr;
   if (e->arena.alloc(&p, n * sizeof(T))) return -1;
-  if (zero) cudaMemsetAsync(p, 0, std::max<size_t>(n * sizeof(T), 16), e->stream);
+  if (zero && n) {
+    cudaError_t err = cudaMemsetAsync(p, 0, n * sizeof(T), e->stream);
+    if (err != cudaSuccess) { set_error(std::string("memset: ") + cudaGetErrorString(err)); return -1; }
+  }
   *dev = static_cast<T*>(p);
   return 0;
 }

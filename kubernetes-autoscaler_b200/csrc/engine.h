@@ -22,6 +22,15 @@ void set_error(const std::string& msg);
     }                                                                                         \
   } while (0)
 
+#define CAE_KERNEL_OK()                                                                       \
+  do {                                                                                        \
+    cudaError_t _e = cudaGetLastError();                                                      \
+    if (_e != cudaSuccess) {                                                                  \
+      cae::set_error(std::string(__func__) + ": " + cudaGetErrorString(_e));                  \
+      return -1;                                                                              \
+    }                                                                                         \
+  } while (0)
+
 // Bump allocator over one cudaMalloc'ed arena per load (freed as a whole on the next cae_load).
 struct Arena {
   std::vector<void*> blocks;

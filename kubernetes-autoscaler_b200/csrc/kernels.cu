@@ -188,7 +188,7 @@ int launch_feasibility(Engine* e, bool want_reasons) {
     case 7: launch_feas_a<7>(e, want_reasons); break;
     default: launch_feas_a<8>(e, want_reasons); break;
   }
-  CAE_CUDA(cudaGetLastError());
+  CAE_KERNEL_OK();
   return 0;
 }
 
@@ -225,7 +225,7 @@ int launch_group_feasibility(Engine* e) {
                                                     e->d_pre_code, e->d_post_code, e->d_tmpl_free_all,
                                                     e->d_tmpl_slots, e->d_group_reason);
   e->stats.kernel_launches++;
-  CAE_CUDA(cudaGetLastError());
+  CAE_KERNEL_OK();
   e->group_reason_valid = true;
   return 0;
 }
@@ -243,14 +243,14 @@ int launch_class_matrices(Engine* e) {
     pack_ok_bits_kernel<<<g2, 64, 0, e->stream>>>(e->d_post_code, e->T, 0, e->DC, e->T, e->Tw, nullptr, e->d_post_ok);
     e->stats.kernel_launches += 2;
   }
-  CAE_CUDA(cudaGetLastError());
+  CAE_KERNEL_OK();
   return 0;
 }
 
 int launch_port_conflicts(Engine* e, int num_port_lists) {
   port_conflict_kernel<<<(num_port_lists + 63) / 64, 64, 0, e->stream>>>(e->dobj, num_port_lists, e->d_pc_of, e->d_port_conf);
   e->stats.kernel_launches++;
-  CAE_CUDA(cudaGetLastError());
+  CAE_KERNEL_OK();
   return 0;
 }
 
@@ -263,7 +263,7 @@ int launch_expand_pods(Engine* e) {
                                                                    e->d_spec_sc, e->d_spec_dc, e->A, d_act,
                                                                    e->d_pod_req, e->d_pod_sc, e->d_pod_dc);
   e->stats.kernel_launches++;
-  CAE_CUDA(cudaGetLastError());
+  CAE_KERNEL_OK();
   CAE_CUDA(cudaStreamSynchronize(e->stream));
   cudaFree(d_act);
   return 0;
@@ -344,7 +344,7 @@ int launch_order(Engine* e) {
   order_kernel<<<nt, 256, smem, e->stream>>>(e->dobj, e->E, e->T, e->N, e->t_begin, n_sort, e->d_group_reason,
                                               e->d_score, e->d_order, e->d_order_n);
   e->stats.kernel_launches++;
-  CAE_CUDA(cudaGetLastError());
+  CAE_KERNEL_OK();
   return 0;
 }
 
@@ -615,7 +615,7 @@ int launch_pack(Engine* e) {
   CAE_CUDA(cudaMemsetAsync(e->d_work_counter, 0, sizeof(int32_t), e->stream));
   pack_kernel<<<blocks, 128, 0, e->stream>>>(e->dobj, p);
   e->stats.kernel_launches++;
-  CAE_CUDA(cudaGetLastError());
+  CAE_KERNEL_OK();
   return 0;
 }
 
@@ -655,7 +655,7 @@ int launch_expander(Engine* e, const int32_t*, int, const int32_t* d_node_count,
   waste_kernel<<<(e->T + warps_per_block - 1) / warps_per_block, threads, 0, e->stream>>>(e->dobj, e->E, e->T, e->N,
                                                                                            d_node_count, d_sched, d_waste);
   e->stats.kernel_launches++;
-  CAE_CUDA(cudaGetLastError());
+  CAE_KERNEL_OK();
   return 0;
 }
 
