@@ -193,6 +193,8 @@ typedef struct cae_objects {
   const int32_t* ps_aff_list;  /* required pod affinity terms */
   const int32_t* ps_anti_list; /* required pod anti-affinity terms */
   const uint8_t* ps_terminating; /* DeletionTimestamp != nil */
+  const uint8_t* ps_hostname_spread; /* isPodUsingHostNameTopologyKey (estimator/binpacking_estimator.go:280-292):
+                                        ANY topologySpreadConstraint (also ScheduleAnyway) uses kubernetes.io/hostname */
 
   /* nodes: cluster nodes [0, num_cluster_nodes) in snapshot list order, then the node-group
    * templates [num_cluster_nodes, num_cluster_nodes + num_templates) */

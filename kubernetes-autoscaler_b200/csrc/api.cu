@@ -20,34 +20,59 @@ namespace cae {
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 
-int Arena::alloc(void** p, size_t bytes) {
-  if (bytes == 0) bytes = 16;
-  cudaError_t e = cudaMalloc(p, bytes);
-  if (e != cudaSuccess) { set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); return -1; }
-  blocks.push_back(*p);
+// ---- arenas: chunked bump allocators that persist across loads (no cudaMalloc on the hot path) ----
+int Arena::alloc(void** dev, void** stage, size_t bytes) {
+  bytes = (std::max<size_t>(bytes, 16) + 255) & ~(size_t)255;
+  for (;;) {
+    if (cur < chunks.size() && chunks[cur].used + bytes <= chunks[cur].size) break;
+    if (cur + 1 < chunks.size()) { ++cur; continue; }
+    Chunk c;
+    c.size = std::max(bytes, min_chunk);
+    if (cudaMalloc(&c.dev, c.size) != cudaSuccess) { set_error("cudaMalloc failed"); return -1; }
+    if (mirrored && cudaHostAlloc(&c.host, c.size, cudaHostAllocDefault) != cudaSuccess) { set_error("cudaHostAlloc failed"); return -1; }
+    chunks.push_back(c);
+    cur = chunks.size() - 1;
+  }
+  Chunk& c = chunks[cur];
+  *dev = static_cast<char*>(c.dev) + c.used;
+  if (stage) *stage = mirrored ? static_cast<char*>(c.host) + c.used : nullptr;
+  c.used += bytes;
   return 0;
 }
+void Arena::reset() { for (auto& c : chunks) c.used = 0; cur = 0; }
 void Arena::release() {
-  for (void* b : blocks) cudaFree(b);
-  blocks.clear();
+  for (auto& c : chunks) { cudaFree(c.dev); if (c.host) cudaFreeHost(c.host); }
+  chunks.clear();
+  cur = 0;
+}
+int Arena::flush(cudaStream_t st, int64_t* bytes) {
+  for (auto& c : chunks)
+    if (c.used) {
+      if (cudaMemcpyAsync(c.dev, c.host, c.used, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("H2D failed"); return -1; }
+      if (bytes) *bytes += (int64_t)c.used;
+    }
+  return 0;
 }
 
 template <class T>
 static int upload(Engine* e, const T* host, size_t n, const T** dev) {
-  void* p = nullptr;
-  if (e->arena.alloc(&p, n * sizeof(T))) return -1;
-  if (n) {
-    cudaError_t err = cudaMemcpyAsync(p, host, n * sizeof(T), cudaMemcpyHostToDevice, e->stream);
-    if (err != cudaSuccess) { set_error(std::string("H2D: ") + cudaGetErrorString(err)); return -1; }
-    e->stats.h2d_bytes += n * sizeof(T);
-  }
+  void *p = nullptr, *h = nullptr;
+  if (e->up.alloc(&p, &h, n * sizeof(T))) return -1;
+  if (n) memcpy(h, host, n * sizeof(T));
   *dev = static_cast<const T*>(p);
+  return 0;
+}
+template <class T>
+static int upload_mut(Engine* e, const std::vector<T>& v, T** dev) {
+  const T* p = nullptr;
+  if (upload(e, v.data(), v.size(), &p)) return -1;
+  *dev = const_cast<T*>(p);
   return 0;
 }
 template <class T>
 static int dev_alloc(Engine* e, T** dev, size_t n, bool zero = false) {
   void* p = nullptr;
-  if (e->arena.alloc(&p, n * sizeof(T))) return -1;
+  if (e->scratch.alloc(&p, nullptr, n * sizeof(T))) return -1;
   if (zero && n) {
     cudaError_t err = cudaMemsetAsync(p, 0, n * sizeof(T), e->stream);
     if (err != cudaSuccess) { set_error(std::string("memset: ") + cudaGetErrorString(err)); return -1; }
@@ -59,10 +84,122 @@ static int dev_alloc(Engine* e, T** dev, size_t n, bool zero = false) {
 #define UP(field, count)                                                           \
   if (upload(e, o->field, (size_t)(count), &e->dobj.field)) return -1
 
+static bool host_label(const cae_objects* o, int ls, int key, int* val) {
+  for (int i = o->ls_off[ls]; i < o->ls_off[ls + 1]; ++i)
+    if (o->ls_key[i] == key) { *val = o->ls_val[i]; return true; }
+  return false;
+}
+
+// Interning for the pod-state dependent plugins (dyn.cuh): topology keys -> compact ids, label values
+// -> domain indices, pod specs -> dynamic classes, and the list of counters each class needs.
+// Structure only; every match / count is computed on the device (dyn_kernels.cu).
+static int build_dynamic(Engine* e, const cae_objects* o, const std::vector<uint8_t>& spec_pending,
+                         const std::vector<int32_t>& spec_sc, std::vector<int32_t>& spec_dc) {
+  DynTables& d = e->dyn;
+  d = DynTables();
+  const int N = e->N, T = e->T, NT = N + T, S = o->num_podspecs;
+  d.S = S;
+  auto nonempty = [&](const int32_t* off, int l) { return off[l + 1] > off[l]; };
+  std::vector<uint8_t> spec_used(spec_pending);
+  for (int i = 0; i < o->node_pod_off[NT]; ++i) spec_used[o->node_pod_spec[i]] = 1;
+  bool any = false;
+  std::vector<int> keys;
+  auto add_key = [&](int key) { if (std::find(keys.begin(), keys.end(), key) == keys.end()) keys.push_back(key); };
+  std::vector<int> exist_keys;  // topology keys of anti-affinity terms held by any pod in the snapshot
+  for (int s = 0; s < S; ++s) {
+    if (!spec_used[s]) continue;
+    int al = o->ps_anti_list[s];
+    for (int t = o->aff_off[al]; t < o->aff_off[al + 1]; ++t) {
+      any = true;
+      add_key(o->aterm_key[t]);
+      if (std::find(exist_keys.begin(), exist_keys.end(), o->aterm_key[t]) == exist_keys.end()) exist_keys.push_back(o->aterm_key[t]);
+    }
+    if (!spec_pending[s]) continue;
+    int pl = o->ps_pts_list[s], fl = o->ps_aff_list[s];
+    for (int c = o->pts_off[pl]; c < o->pts_off[pl + 1]; ++c) { any = true; add_key(o->pts_key[c]); }
+    for (int t = o->aff_off[fl]; t < o->aff_off[fl + 1]; ++t) { any = true; add_key(o->aterm_key[t]); }
+  }
+  e->has_dynamic = any;
+  if (!any) return 0;
+  if ((int)keys.size() > DYN_MAX_KEYS) { set_error("more than 8 distinct topology keys"); return 1; }
+  d.K = (int)keys.size();
+  std::vector<int32_t> dom((size_t)d.K * NT, -1);
+  for (int k = 0; k < d.K; ++k) {
+    d.key_id[k] = keys[k];
+    d.is_host[k] = keys[k] == o->hostname_key;
+    std::map<int, int> ids;
+    for (int row = 0; row < NT; ++row) {
+      if (row == N) d.Dc[k] = (int)ids.size();
+      int v;
+      if (!host_label(o, o->node_labelset[row], keys[k], &v)) continue;
+      auto it = ids.find(v);
+      if (it == ids.end()) it = ids.emplace(v, (int)ids.size()).first;
+      dom[(size_t)k * NT + row] = it->second;
+    }
+    if (T == 0) d.Dc[k] = (int)ids.size();
+    d.D[k] = (int)ids.size();
+  }
+  auto kidx = [&](int key) { return (int)(std::find(keys.begin(), keys.end(), key) - keys.begin()); };
+  // dynamic classes
+  std::map<std::tuple<int, int, int, int, int, int>, int> dc_ids;
+  std::vector<int32_t> dc_spec(1, 0), dc_sc(1, 0), dc_q_off(1, 0), dc_ngroups(1, 0);
+  std::vector<uint8_t> q_kind;
+  std::vector<int32_t> q_k, q_dc, q_p0, q_base_off(1, 0);
+  dc_q_off.push_back(0);
+  for (int s = 0; s < S; ++s) {
+    if (!spec_pending[s]) continue;
+    int pl = o->ps_pts_list[s], fl = o->ps_aff_list[s], al = o->ps_anti_list[s];
+    if (!nonempty(o->pts_off, pl) && !nonempty(o->aff_off, fl) && !nonempty(o->aff_off, al) && exist_keys.empty()) continue;
+    auto key = std::make_tuple(o->ps_namespace[s], o->ps_labelset[s], pl, fl, al, spec_sc[s]);
+    auto it = dc_ids.find(key);
+    if (it == dc_ids.end()) {
+      int dc = (int)dc_spec.size();
+      it = dc_ids.emplace(key, dc).first;
+      dc_spec.push_back(s);
+      dc_sc.push_back(spec_sc[s]);
+      dc_ngroups.push_back(0);
+      auto add_q = [&](int kind, int k, int p0) {
+        q_kind.push_back((uint8_t)kind); q_k.push_back(k); q_dc.push_back(dc); q_p0.push_back(p0);
+        q_base_off.push_back(q_base_off.back() + d.Dc[k]);
+      };
+      for (int c = o->pts_off[pl]; c < o->pts_off[pl + 1]; ++c) add_q(Q_PTS, kidx(o->pts_key[c]), c);
+      for (int t = o->aff_off[fl]; t < o->aff_off[fl + 1]; ++t) add_q(Q_AFF, kidx(o->aterm_key[t]), t);
+      for (int t = o->aff_off[al]; t < o->aff_off[al + 1]; ++t) add_q(Q_ANTI, kidx(o->aterm_key[t]), t);
+      for (int key2 : exist_keys) add_q(Q_EXIST, kidx(key2), -1);
+      if ((int)q_kind.size() - dc_q_off.back() > DYN_MAX_Q) { set_error("a pod needs more than 8 topology counters"); return 1; }
+      dc_q_off.push_back((int)q_kind.size());
+    }
+    spec_dc[s] = it->second;
+  }
+  for (int g = 0; g < o->num_groups; ++g)
+    if (o->group_off[g + 1] > o->group_off[g]) dc_ngroups[spec_dc[o->pend_spec[o->group_off[g]]]]++;
+  d.DC = (int)dc_spec.size();
+  d.Q = (int)q_kind.size();
+  e->DC = d.DC;
+  const int32_t* p32 = nullptr; const uint8_t* p8 = nullptr;
+#define UPV(vec, field) { if (upload(e, (vec).data(), (vec).size(), &field)) return -1; }
+  UPV(dom, d.dom); UPV(dc_spec, d.dc_spec); UPV(dc_sc, d.dc_sc); UPV(dc_q_off, d.dc_q_off); UPV(q_kind, d.q_kind);
+  UPV(q_k, d.q_k); UPV(q_dc, d.q_dc); UPV(q_p0, d.q_p0); UPV(q_base_off, d.q_base_off);
+  UPV(spec_used, p8); e->d_spec_used = p8;
+  UPV(dc_ngroups, p32); e->d_dc_ngroups = p32;
+#undef UPV
+  const size_t Q = std::max(d.Q, 1), pool = std::max(q_base_off.back(), 1);
+  if (dev_alloc(e, &d.wmat, Q * S) || dev_alloc(e, &d.q_self, Q) || dev_alloc(e, &d.q_wown, Q) || dev_alloc(e, &d.q_active, Q) ||
+      dev_alloc(e, &d.dc_aff_self, (size_t)d.DC) || dev_alloc(e, &d.dc_active, (size_t)d.DC) || dev_alloc(e, &d.elig, Q * e->U) ||
+      dev_alloc(e, &d.base_cnt, pool, true) || dev_alloc(e, &d.base_pres, pool, true) || dev_alloc(e, &d.base_tot, Q, true) ||
+      dev_alloc(e, &d.ds_w, Q * std::max(T, 1)) || dev_alloc(e, &d.st_min1, Q) || dev_alloc(e, &d.st_arg1, Q) ||
+      dev_alloc(e, &d.st_min2, Q) || dev_alloc(e, &d.st_ndom, Q) || dev_alloc(e, &d.q_nfeed, Q, true) ||
+      dev_alloc(e, &d.group_feeds, (size_t)std::max(e->E, 1), true))
+    return -1;
+  e->h_dc_of_spec_valid = true;
+  return 0;
+}
+
 static int do_load(Engine* e, const cae_objects* o) {
   if (o->abi_version != CAE_ABI_VERSION) { set_error("cae_objects.abi_version mismatch"); return -2; }
   if (o->num_res < 3 || o->num_res > CAE_MAX_RES) { set_error("num_res out of range"); return 1; }
-  e->arena.release();
+  e->up.reset();
+  e->scratch.reset();
   e->loaded = false;
   e->group_reason_valid = false;
   e->stats.h2d_bytes = 0;
@@ -101,7 +238,8 @@ static int do_load(Engine* e, const cae_objects* o) {
   { int n = o->num_aterms; UP(aff_off, o->num_aff_lists + 1); UP(aterm_selector, n); UP(aterm_key, n); UP(aterm_ns_off, n + 1);
     UP(aterm_ns, o->aterm_ns_off[n]); UP(aterm_ns_selector, n); }
   { int n = o->num_podspecs; UP(ps_namespace, n); UP(ps_labelset, n); UP(ps_req, (size_t)n * R); UP(ps_tol_list, n); UP(ps_naff, n);
-    UP(ps_node_name, n); UP(ps_port_list, n); UP(ps_pts_list, n); UP(ps_aff_list, n); UP(ps_anti_list, n); UP(ps_terminating, n); }
+    UP(ps_node_name, n); UP(ps_port_list, n); UP(ps_pts_list, n); UP(ps_aff_list, n); UP(ps_anti_list, n); UP(ps_terminating, n);
+    UP(ps_hostname_spread, n); }
   UP(node_name, NT); UP(node_labelset, NT); UP(node_taint_list, NT); UP(node_unschedulable, NT);
   UP(node_alloc, (size_t)NT * R); UP(node_allowed_pods, NT); UP(node_cap_cpu, NT); UP(node_cap_mem, NT);
   UP(node_has_alloc_cpu, NT); UP(node_has_alloc_mem, NT);
@@ -115,7 +253,6 @@ static int do_load(Engine* e, const cae_objects* o) {
   std::map<std::tuple<int, int, int, int>, int> sc_ids;
   std::vector<StaticClass> sclass;
   std::vector<int32_t> spec_sc(S, 0), spec_dc(S, 0);
-  e->has_dynamic = false;
   for (int s = 0; s < S; ++s) {
     if (!spec_pending[s]) continue;
     auto key = std::make_tuple(o->ps_tol_list[s], o->ps_naff[s], o->ps_node_name[s], o->ps_port_list[s]);
@@ -125,15 +262,6 @@ static int do_load(Engine* e, const cae_objects* o) {
       sclass.push_back({o->ps_tol_list[s], o->ps_naff[s], o->ps_node_name[s], o->ps_port_list[s]});
     }
     spec_sc[s] = it->second;
-    auto nonempty = [&](const int32_t* off, int l) { return off[l + 1] > off[l]; };
-    if (nonempty(o->pts_off, o->ps_pts_list[s]) || nonempty(o->aff_off, o->ps_aff_list[s]) ||
-        nonempty(o->aff_off, o->ps_anti_list[s]))
-      e->has_dynamic = true;
-  }
-  // pods already on nodes with required anti-affinity constrain incoming pods (interpodaffinity/filtering.go:204-228)
-  for (int i = 0; i < o->node_pod_off[NT]; ++i) {
-    int l = o->ps_anti_list[o->node_pod_spec[i]];
-    if (o->aff_off[l + 1] > o->aff_off[l]) e->has_dynamic = true;
   }
   // host-port lists of pending pods get compact ids (one bit each in a node's used-port mask)
   std::vector<int32_t> pc_of(o->num_port_lists, -1);
@@ -147,60 +275,74 @@ static int do_load(Engine* e, const cae_objects* o) {
   if (sclass.empty()) sclass.push_back({0, -1, -1, 0});
   e->SC = (int)sclass.size();
   e->DC = 1;  // class 0: no topology-spread / inter-pod-affinity involvement
+  e->h_dc_of_spec_valid = false;
+  { int rc = build_dynamic(e, o, spec_pending, spec_sc, spec_dc); if (rc) return rc; }
 
-  // active resource dims + per-template free capacity
+  // active resource dims + free capacity of templates and cluster nodes
   e->A = 0;
   for (int r = 0; r < R; ++r) {
     bool used = false;
     for (int s = 0; s < S && !used; ++s) used = spec_pending[s] && o->ps_req[(size_t)s * R + r] > 0;
     if (used) e->act_dim[e->A++] = r;
   }
-  std::vector<int64_t> free_all((size_t)R * T), free_act((size_t)std::max(e->A, 1) * T);
-  std::vector<int32_t> slots(T);
-  for (int t = 0; t < T; ++t) {
-    int node = N + t;
+  const int A1 = std::max(e->A, 1);
+  std::vector<int64_t> free_all((size_t)R * T), free_act((size_t)A1 * T), cfree((size_t)A1 * std::max(N, 1));
+  std::vector<int32_t> slots(T), cslots(std::max(N, 1));
+  for (int row = 0; row < NT; ++row) {
     int64_t reqd[R] = {0};
-    int npods = o->node_pod_off[node + 1] - o->node_pod_off[node];
-    for (int i = o->node_pod_off[node]; i < o->node_pod_off[node + 1]; ++i)
+    int npods = o->node_pod_off[row + 1] - o->node_pod_off[row];
+    for (int i = o->node_pod_off[row]; i < o->node_pod_off[row + 1]; ++i)
       for (int r = 0; r < R; ++r) reqd[r] += o->ps_req[(size_t)o->node_pod_spec[i] * R + r];
-    for (int r = 0; r < R; ++r) free_all[(size_t)r * T + t] = o->node_alloc[(size_t)node * R + r] - reqd[r];
-    for (int a = 0; a < e->A; ++a) free_act[(size_t)a * T + t] = free_all[(size_t)e->act_dim[a] * T + t];
-    slots[t] = o->node_allowed_pods[node] - npods;
+    if (row >= N) {
+      int t = row - N;
+      for (int r = 0; r < R; ++r) free_all[(size_t)r * T + t] = o->node_alloc[(size_t)row * R + r] - reqd[r];
+      for (int a = 0; a < e->A; ++a) free_act[(size_t)a * T + t] = free_all[(size_t)e->act_dim[a] * T + t];
+      slots[t] = o->node_allowed_pods[row] - npods;
+    } else if (e->has_dynamic) {
+      for (int a = 0; a < e->A; ++a) cfree[(size_t)a * N + row] = o->node_alloc[(size_t)row * R + e->act_dim[a]] - reqd[e->act_dim[a]];
+      cslots[row] = o->node_allowed_pods[row] - npods;
+    }
   }
-  const StaticClass* d_sc_c = nullptr; const int32_t *d_ssc = nullptr, *d_sdc = nullptr, *d_slots = nullptr;
-  const int64_t *d_fa = nullptr, *d_fact = nullptr;
-  if (upload(e, sclass.data(), sclass.size(), &d_sc_c) || upload(e, spec_sc.data(), (size_t)S, &d_ssc) ||
-      upload(e, spec_dc.data(), (size_t)S, &d_sdc) || upload(e, slots.data(), (size_t)T, &d_slots) ||
-      upload(e, free_all.data(), free_all.size(), &d_fa) || upload(e, free_act.data(), free_act.size(), &d_fact))
+  if (upload_mut(e, sclass, &e->d_sclass) || upload_mut(e, spec_sc, &e->d_spec_sc) || upload_mut(e, slots, &e->d_tmpl_slots) ||
+      upload_mut(e, free_all, &e->d_tmpl_free_all) || upload_mut(e, free_act, &e->d_tmpl_free) || upload_mut(e, cfree, &e->d_c_free) ||
+      upload_mut(e, cslots, &e->d_c_slots) || upload_mut(e, pc_of, &e->d_pc_of) || upload_mut(e, spec_dc, &e->d_spec_dc))
     return -1;
-  e->d_sclass = const_cast<StaticClass*>(d_sc_c);
-  e->d_spec_sc = const_cast<int32_t*>(d_ssc); e->d_spec_dc = const_cast<int32_t*>(d_sdc);
-  e->d_tmpl_slots = const_cast<int32_t*>(d_slots);
-  e->d_tmpl_free_all = const_cast<int64_t*>(d_fa); e->d_tmpl_free = const_cast<int64_t*>(d_fact);
 
   if (dev_alloc(e, &e->d_pre_code, (size_t)e->SC * e->U) || dev_alloc(e, &e->d_pre_ok, (size_t)e->SC * std::max(e->Tw, 1)) ||
       dev_alloc(e, &e->d_post_code, (size_t)e->DC * std::max(T, 1), true) || dev_alloc(e, &e->d_post_ok, (size_t)e->DC * std::max(e->Tw, 1)) ||
-      dev_alloc(e, &e->d_pod_req, (size_t)std::max(e->A, 1) * std::max(e->Pl, 1)) || dev_alloc(e, &e->d_pod_sc, (size_t)std::max(e->Pl, 1)) ||
+      dev_alloc(e, &e->d_pod_req, (size_t)A1 * std::max(e->Pl, 1)) || dev_alloc(e, &e->d_pod_sc, (size_t)std::max(e->Pl, 1)) ||
       dev_alloc(e, &e->d_pod_dc, (size_t)std::max(e->Pl, 1)) || dev_alloc(e, &e->d_fit_bits, (size_t)std::max(T, 1) * std::max(e->Plw, 1)) ||
       dev_alloc(e, &e->d_fit_count, (size_t)std::max(T, 1), true) || dev_alloc(e, &e->d_group_reason, (size_t)std::max(T, 1) * std::max(e->E, 1)) ||
       dev_alloc(e, &e->d_counts2, (size_t)2 * std::max(T, 1), true) || dev_alloc(e, &e->d_sched, (size_t)std::max(T, 1) * std::max(e->E, 1), true) ||
       dev_alloc(e, &e->d_order, (size_t)std::max(T, 1) * std::max(e->E, 1)) || dev_alloc(e, &e->d_order_n, (size_t)std::max(T, 1), true) ||
-      dev_alloc(e, &e->d_max_nodes, (size_t)std::max(T, 1), true) || dev_alloc(e, &e->d_work_counter, 1, true))
+      dev_alloc(e, &e->d_max_nodes, (size_t)std::max(T, 1), true) || dev_alloc(e, &e->d_work_counter, 4, true) ||
+      dev_alloc(e, &e->d_port_conf, (size_t)std::max(o->num_port_lists, 1)) || dev_alloc(e, &e->d_act_dim, CAE_MAX_RES))
     return -1;
   e->d_score = nullptr;
   e->d_reasons = nullptr;
   if (e->cfg.want_reasons && dev_alloc(e, &e->d_reasons, (size_t)std::max(T, 1) * std::max(e->Pl, 1))) return -1;
 
-  // host copies for host-side steps (expander chain, homogeneity check)
+  // host copies for host-side steps (homogeneity check)
   e->h_group_off.assign(o->group_off, o->group_off + o->num_groups + 1);
   e->h_pend_spec.assign(o->pend_spec, o->pend_spec + o->num_pending);
 
-  { const int32_t* d_pc = nullptr;
-    if (upload(e, pc_of.data(), pc_of.size(), &d_pc)) return -1;
-    e->d_pc_of = const_cast<int32_t*>(d_pc);
-    if (dev_alloc(e, &e->d_port_conf, (size_t)std::max(o->num_port_lists, 1))) return -1;
-    if (launch_port_conflicts(e, o->num_port_lists)) return -1; }
+  if (e->up.flush(e->stream, &e->stats.h2d_bytes)) return -1;   // ONE pinned H2D copy per arena chunk
+  CAE_CUDA(cudaMemcpyAsync(e->d_act_dim, e->act_dim, sizeof(int) * CAE_MAX_RES, cudaMemcpyHostToDevice, e->stream));
+  if (launch_port_conflicts(e, o->num_port_lists)) return -1;
   if (launch_class_matrices(e)) return -1;
+  if (e->has_dynamic) {
+    if (launch_dynamic_tables(e, e->d_spec_used, e->d_dc_ngroups)) return -1;
+    // classes none of whose counters can ever be non-zero are plain: fold them back into class 0
+    std::vector<uint8_t> act(e->dyn.DC);
+    CAE_CUDA(cudaMemcpyAsync(act.data(), e->dyn.dc_active, act.size(), cudaMemcpyDeviceToHost, e->stream));
+    CAE_CUDA(cudaStreamSynchronize(e->stream));
+    bool changed = false;
+    for (int s = 0; s < S; ++s) if (spec_dc[s] && !act[spec_dc[s]]) { spec_dc[s] = 0; changed = true; }
+    if (changed) CAE_CUDA(cudaMemcpyAsync(e->d_spec_dc, spec_dc.data(), sizeof(int32_t) * S, cudaMemcpyHostToDevice, e->stream));
+    e->h_spec_dc = spec_dc;
+    CAE_CUDA(cudaStreamSynchronize(e->stream));
+  }
+  if (launch_post_bits(e)) return -1;
   if (launch_expand_pods(e)) return -1;
   cudaEventRecord(e->ev1, e->stream);
   CAE_CUDA(cudaStreamSynchronize(e->stream));
@@ -245,7 +387,8 @@ void cae_destroy(cae_engine* h) {
   if (!h) return;
   Engine* e = reinterpret_cast<Engine*>(h);
   cudaSetDevice(e->cfg.device);
-  e->arena.release();
+  e->up.release();
+  e->scratch.release();
   if (e->d_pack_scratch) cudaFree(e->d_pack_scratch);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
@@ -264,7 +407,6 @@ int32_t cae_feasibility(cae_engine* h, uint32_t* fit_bits, uint8_t* reasons, int
   Engine* e = reinterpret_cast<Engine*>(h);
   if (!e || !e->loaded) { cae::set_error("cae_feasibility before cae_load"); return -2; }
   cudaSetDevice(e->cfg.device);
-  if (e->has_dynamic) { cae::set_error("topology spread / inter-pod affinity not supported by this build"); return 1; }
   bool want_r = e->cfg.want_reasons && e->d_reasons;
   cudaEventRecord(e->ev0, e->stream);
   if (cae::launch_feasibility(e, want_r)) return -1;
@@ -301,7 +443,6 @@ int32_t cae_feasibility_groups(cae_engine* h, uint8_t* reasons) {
   Engine* e = reinterpret_cast<Engine*>(h);
   if (!e || !e->loaded) { cae::set_error("cae_feasibility_groups before cae_load"); return -2; }
   cudaSetDevice(e->cfg.device);
-  if (e->has_dynamic) { cae::set_error("topology spread / inter-pod affinity not supported by this build"); return 1; }
   if (cae::launch_group_feasibility(e)) return -1;
   if (reasons && e->T && e->E)
     CAE_CUDA(cudaMemcpyAsync(reasons, e->d_group_reason, (size_t)e->T * e->E, cudaMemcpyDeviceToHost, e->stream));
@@ -314,7 +455,6 @@ int32_t cae_estimate_all(cae_engine* h, const int32_t* max_nodes, int32_t* node_
   Engine* e = reinterpret_cast<Engine*>(h);
   if (!e || !e->loaded) { cae::set_error("cae_estimate_all before cae_load"); return -2; }
   cudaSetDevice(e->cfg.device);
-  if (e->has_dynamic) { cae::set_error("topology spread / inter-pod affinity not supported by this build"); return 1; }
   // groups must be homogeneous (equivalence.BuildPodGroups guarantees it: core/scaleup/equivalence/groups.go:40-104)
   for (int g = 0; g < e->E; ++g)
     for (int p = e->h_group_off[g] + 1; p < e->h_group_off[g + 1]; ++p)
@@ -341,6 +481,8 @@ int32_t cae_estimate_all(cae_engine* h, const int32_t* max_nodes, int32_t* node_
   rc = cae::launch_pack(e);
   if (rc) return rc;
   cudaEventRecord(e->ev1, e->stream);
+  int32_t pack_status = 0;
+  CAE_CUDA(cudaMemcpyAsync(&pack_status, e->d_work_counter + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
   if (node_count) CAE_CUDA(cudaMemcpyAsync(node_count, e->d_counts2, sizeof(int32_t) * T, cudaMemcpyDeviceToHost, e->stream));
   if (pod_count) CAE_CUDA(cudaMemcpyAsync(pod_count, e->d_counts2 + T, sizeof(int32_t) * T, cudaMemcpyDeviceToHost, e->stream));
   if (sched_count && E) CAE_CUDA(cudaMemcpyAsync(sched_count, e->d_sched, sizeof(int32_t) * (size_t)T * E, cudaMemcpyDeviceToHost, e->stream));
@@ -349,6 +491,7 @@ int32_t cae_estimate_all(cae_engine* h, const int32_t* max_nodes, int32_t* node_
   float ms = 0;
   cudaEventElapsedTime(&ms, e->ev0, e->ev1);
   e->stats.estimate_ms = ms;
+  if (pack_status) { cae::set_error("placement log overflow (cross-group topology counters)"); return 1; }
   return 0;
 }
 

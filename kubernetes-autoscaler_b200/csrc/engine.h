@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/caengine.h"
+#include "dyn.cuh"
 #include "tables.cuh"
 
 namespace cae {
@@ -31,10 +32,17 @@ void set_error(const std::string& msg);
     }                                                                                         \
   } while (0)
 
-// Bump allocator over one cudaMalloc'ed arena per load (freed as a whole on the next cae_load).
+// Chunked bump allocator that persists across loads.  `mirrored` arenas pair every device chunk with a
+// pinned host chunk at the same offsets so a whole load is ONE cudaMemcpyAsync per chunk.
 struct Arena {
-  std::vector<void*> blocks;
-  int alloc(void** p, size_t bytes);
+  struct Chunk { void* dev = nullptr; void* host = nullptr; size_t size = 0, used = 0; };
+  std::vector<Chunk> chunks;
+  size_t cur = 0;
+  size_t min_chunk = (size_t)32 << 20;
+  bool mirrored = false;
+  int alloc(void** dev, void** stage, size_t bytes);
+  int flush(cudaStream_t st, int64_t* bytes);
+  void reset();
   void release();
 };
 
@@ -42,7 +50,17 @@ struct Engine {
   cae_config cfg{};
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  Arena arena;      // tables of the current load
+  Arena up;         // uploaded tables (pinned mirror), reset per load
+  Arena scratch;    // device-only tables of the current load
+  Engine() { up.mirrored = true; }
+  DynTables dyn;    // PodTopologySpread / InterPodAffinity tables (dyn.cuh)
+  const uint8_t* d_spec_used = nullptr;
+  const int32_t* d_dc_ngroups = nullptr;
+  int64_t* d_c_free = nullptr;            // [A][N] free capacity of the cluster nodes (fallback placements)
+  int32_t* d_c_slots = nullptr;           // [N]
+  int* d_act_dim = nullptr;               // [CAE_MAX_RES]
+  std::vector<int32_t> h_spec_dc;
+  bool h_dc_of_spec_valid = false;
   cae_stats stats{};
   bool loaded = false;
 
@@ -102,6 +120,8 @@ struct Engine {
 
 // kernels.cu
 int launch_class_matrices(Engine* e);
+int launch_post_bits(Engine* e);
+int launch_dynamic_tables(Engine* e, const uint8_t* d_spec_used, const int32_t* d_dc_ngroups);
 int launch_expand_pods(Engine* e);
 int launch_port_conflicts(Engine* e, int num_port_lists);
 int launch_feasibility(Engine* e, bool want_reasons);

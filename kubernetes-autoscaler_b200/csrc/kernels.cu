@@ -239,9 +239,17 @@ int launch_class_matrices(Engine* e) {
   if (e->Tw > 0) {
     dim3 g1((e->Tw + 63) / 64, e->SC);
     pack_ok_bits_kernel<<<g1, 64, 0, e->stream>>>(e->d_pre_code, e->U, e->N, e->SC, e->T, e->Tw, e->d_tmpl_slots, e->d_pre_ok);
+    e->stats.kernel_launches += 1;
+  }
+  CAE_KERNEL_OK();
+  return 0;
+}
+
+int launch_post_bits(Engine* e) {
+  if (e->Tw > 0) {
     dim3 g2((e->Tw + 63) / 64, e->DC);
     pack_ok_bits_kernel<<<g2, 64, 0, e->stream>>>(e->d_post_code, e->T, 0, e->DC, e->T, e->Tw, nullptr, e->d_post_ok);
-    e->stats.kernel_launches += 2;
+    e->stats.kernel_launches += 1;
   }
   CAE_KERNEL_OK();
   return 0;
@@ -256,16 +264,11 @@ int launch_port_conflicts(Engine* e, int num_port_lists) {
 
 int launch_expand_pods(Engine* e) {
   if (e->Pl == 0) return 0;
-  int* d_act = nullptr;
-  CAE_CUDA(cudaMalloc(&d_act, sizeof(int) * CAE_MAX_RES));
-  CAE_CUDA(cudaMemcpyAsync(d_act, e->act_dim, sizeof(int) * CAE_MAX_RES, cudaMemcpyHostToDevice, e->stream));
   expand_pods_kernel<<<(e->Pl + 255) / 256, 256, 0, e->stream>>>(e->dobj.pend_spec, e->p_begin, e->Pl, e->dobj.ps_req,
-                                                                   e->d_spec_sc, e->d_spec_dc, e->A, d_act,
+                                                                   e->d_spec_sc, e->d_spec_dc, e->A, e->d_act_dim,
                                                                    e->d_pod_req, e->d_pod_sc, e->d_pod_dc);
   e->stats.kernel_launches++;
   CAE_KERNEL_OK();
-  CAE_CUDA(cudaStreamSynchronize(e->stream));
-  cudaFree(d_act);
   return 0;
 }
 
@@ -348,275 +351,10 @@ int launch_order(Engine* e) {
   return 0;
 }
 
-// ------------------------------------------------------------------------------------------------
-// K3: BinpackingNodeEstimator.Estimate (estimator/binpacking_estimator.go:97-247), one WARP per
-// template (templates are independent simulations; inside one, placement order is sequential by
-// construction).  Per-template node state lives in a per-warp global scratch slab (L1/L2 resident),
-// lanes stride over the open nodes.  Groups of identical pods without topology-spread / inter-pod
-// affinity are placed in closed form:
-//   * tryToScheduleOnExistingNodes (:141-164): SchedulePodOnAnyNodeMatching scans cyclically from
-//     lastIndex (plugin_runner.go:81,123), i.e. identical pods are dealt round-robin over the new
-//     nodes with spare capacity k_j.  n pods => every node gets min(k_j, L) plus one more for the
-//     first `rem` nodes (cyclic order from the start index) with k_j > L.
-//   * tryToScheduleOnNewNodes (:168-247): only the last added node is tried, so after the pass above
-//     each new node simply takes min(remaining, k_new) pods until the limiter denies (:222).
-// ------------------------------------------------------------------------------------------------
-struct PackParams {
-  int E, T, N, U, A, t_begin, t_end, cap;
-  const int32_t* order; const int32_t* order_n;
-  const uint8_t* pre_code; const int32_t* spec_sc;
-  const int64_t* tmpl_free;  // [A][T]
-  const int32_t* tmpl_slots;
-  const int32_t* max_nodes;
-  const int32_t* pc_of; const unsigned long long* port_conf;
-  int act_dim[CAE_MAX_RES];
-  int32_t* node_count; int32_t* pod_count; int32_t* sched;  // sched [T][E]
-  int32_t* work_counter;
-  unsigned char* scratch; size_t scratch_per_warp;
-};
-
-__device__ __forceinline__ int warp_sum(int v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 __device__ __forceinline__ long long warp_sum_ll(long long v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
-}
-__device__ __forceinline__ int warp_max(int v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-
-// how many more copies of the pod fit: min over requested dims of floor(free/req), pod slots, ports
-__device__ __forceinline__ int capacity_of(const int64_t* req, int A, const int64_t* nfree, int cap_stride, int j,
-                                           int slots, bool port_block, bool has_ports, int limit) {
-  int k = min(slots, limit);
-  if (k <= 0) return 0;
-#pragma unroll 1
-  for (int a = 0; a < A; ++a) {
-    int64_t q = req[a];
-    if (q <= 0) continue;
-    int64_t f = nfree[(size_t)a * cap_stride + j];
-    if (f < q) return 0;
-    int64_t c = f / q;
-    if (c < k) k = (int)c;
-  }
-  if (has_ports) k = port_block ? 0 : min(k, 1);
-  return k;
-}
-
-__global__ void __launch_bounds__(128) pack_kernel(DevObjects o, PackParams p) {
-  const int lane = threadIdx.x & 31;
-  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  unsigned char* slab = p.scratch + (size_t)warp_global * p.scratch_per_warp;
-  const int cap = p.cap;
-  // slab layout: nfree[A][cap] int64 | slots[cap] int32 | kbuf[cap] int32 | ports[cap] u64 | sched flag [cap] u8
-  int64_t* nfree = reinterpret_cast<int64_t*>(slab);
-  unsigned long long* nports = reinterpret_cast<unsigned long long*>(nfree + (size_t)p.A * cap);
-  int32_t* nslots = reinterpret_cast<int32_t*>(nports + cap);
-  int32_t* kbuf = nslots + cap;
-  uint8_t* nsched = reinterpret_cast<uint8_t*>(kbuf + cap);
-
-  for (;;) {
-    int t = 0;
-    if (lane == 0) t = p.t_begin + atomicAdd(p.work_counter, 1);
-    t = __shfl_sync(0xffffffffu, t, 0);
-    if (t >= p.t_end) break;
-
-    int64_t tfree[CAE_MAX_RES];
-    for (int a = 0; a < p.A; ++a) tfree[a] = p.tmpl_free[(size_t)a * p.T + t];
-    const int tslots = p.tmpl_slots[t];
-    // DaemonSet host ports on a fresh node: evaluated through pre_code (NodePorts vs pods on node)
-    const int max_nodes = p.max_nodes ? p.max_nodes[t] : 0;
-    int n_new = 0;         // nodes added so far (estimationState.newNodeNameIndex)
-    int nodes_with_pods = 0;
-    int pods_total = 0;
-    int last_index = 0;    // SchedulerPluginRunner.lastIndex, fresh per Estimate
-    bool new_nodes_available = true;
-    const int n_groups = p.order_n[t];
-
-    for (int gi = 0; gi < n_groups; ++gi) {
-      const int g = p.order[(size_t)t * p.E + gi];
-      const int pb = o.group_off[g];
-      int n = o.group_off[g + 1] - pb;
-      const int spec = o.pend_spec[pb];
-      int64_t req[CAE_MAX_RES];
-      for (int a = 0; a < p.A; ++a) req[a] = o.ps_req[(size_t)spec * R + p.act_dim[a]];
-      const int sc = p.spec_sc[spec];
-      const uint8_t code_new = p.pre_code[(size_t)sc * p.U + p.N + p.T + t];  // sanitized copy of the template
-      const bool static_ok = (code_new & 0x0F) == 0;
-      const int plist = o.ps_port_list[spec];
-      const bool has_ports = o.port_off[plist + 1] > o.port_off[plist];
-      const unsigned long long pconf = has_ports ? p.port_conf[plist] : 0ull;   // lists this pod collides with
-      const unsigned long long pbit = has_ports ? (1ull << p.pc_of[plist]) : 0ull;
-      int placed = 0;
-
-      // ---- tryToScheduleOnExistingNodes: round-robin over the nodes added so far -------------
-      if (n_new > 0 && static_ok) {
-        const int list_len = p.N + n_new;
-        const int s = last_index >= p.N ? last_index - p.N : 0;  // first new node in cyclic scan order
-        long long total = 0;
-        int kmax = 0;
-        for (int j = lane; j < n_new; j += 32) {
-          bool pblock = (nports[j] & pconf) != 0ull;
-          int k = capacity_of(req, p.A, nfree, cap, j, nslots[j], pblock, has_ports, n);
-          kbuf[j] = k;
-          total += k;
-          kmax = max(kmax, k);
-        }
-        total = warp_sum_ll(total);
-        kmax = warp_max(kmax);
-        __syncwarp();
-        if (total > 0) {
-          int L, rem;
-          if (total <= n) { L = kmax; rem = 0; }
-          else {
-            // largest L with sum_j min(k_j, L) <= n
-            int lo = 0, hi = kmax;  // f(lo) <= n < f(hi)
-            while (hi - lo > 1) {
-              int mid = (lo + hi) >> 1;
-              long long f = 0;
-              for (int j = lane; j < n_new; j += 32) f += min(kbuf[j], mid);
-              f = warp_sum_ll(f);
-              if (f <= n) lo = mid; else hi = mid;
-            }
-            L = lo;
-            long long f = 0;
-            for (int j = lane; j < n_new; j += 32) f += min(kbuf[j], L);
-            f = warp_sum_ll(f);
-            rem = (int)(n - f);
-          }
-          // walk the nodes in cyclic order from s; the first `rem` with k > L get one extra pod
-          int seen = 0, last_pos = -1, newly = 0, got = 0;
-          for (int base = 0; base < n_new; base += 32) {
-            int pos = base + lane;
-            bool in = pos < n_new;
-            int j = in ? (s + pos) % n_new : 0;
-            int k = in ? kbuf[j] : 0;
-            bool extra_c = in && k > L;
-            unsigned m = __ballot_sync(0xffffffffu, extra_c);
-            int rank = seen + __popc(m & ((1u << lane) - 1));
-            int mj = in ? min(k, L) + ((extra_c && rank < rem) ? 1 : 0) : 0;
-            seen += __popc(m);
-            if (mj > 0) {
-              for (int a = 0; a < p.A; ++a) if (req[a] > 0) nfree[(size_t)a * cap + j] -= (int64_t)mj * req[a];
-              nslots[j] -= mj;
-              nports[j] |= pbit;
-              if (!nsched[j]) { nsched[j] = 1; newly++; }
-              got += mj;
-              // the pod placed last: in the final (partial or full) lap, the furthest position served
-              bool final_lap = rem > 0 ? (extra_c && rank < rem) : (k >= L);
-              if (final_lap) last_pos = pos;
-            }
-          }
-          got = warp_sum(got);
-          newly = warp_sum(newly);
-          last_pos = warp_max(last_pos);
-          placed += got;
-          nodes_with_pods += newly;
-          n -= got;
-          if (last_pos >= 0) {
-            int jl = (s + last_pos) % n_new;
-            last_index = (p.N + jl + 1) % list_len;
-          }
-          __syncwarp();
-        }
-      }
-
-      // ---- tryToScheduleOnNewNodes ----------------------------------------------------------
-      if (n > 0 && new_nodes_available) {
-        // after the pass above no added node (incl. the last one) can take this pod any more
-        bool stop = (n_new > 0) && !nsched[n_new - 1];  // last node still empty (:212)
-        stop = __shfl_sync(0xffffffffu, stop, 0);
-        if (!stop) {
-          int k_new = 0;
-          if (static_ok) {
-            k_new = min(tslots, n);
-            for (int a = 0; a < p.A && k_new > 0; ++a) {
-              if (req[a] <= 0) continue;
-              if (tfree[a] < req[a]) { k_new = 0; break; }
-              int64_t c = tfree[a] / req[a];
-              if (c < k_new) k_new = (int)c;
-            }
-            if (has_ports) k_new = min(k_new, 1);  // DaemonSet port conflicts already in static_ok
-          }
-          long long allowed = max_nodes < 0 ? 0 : (max_nodes == 0 ? (long long)INT_MAX : max((long long)max_nodes - n_new, 0ll));
-          allowed = min(allowed, (long long)(cap - n_new));
-          int add;
-          int fill = 0;
-          if (k_new <= 0) {
-            add = allowed >= 1 ? 1 : 0;  // one node is added, the pod still fails on it (:235-240)
-            if (allowed < 1) new_nodes_available = false;
-          } else {
-            long long need = ((long long)n + k_new - 1) / k_new;
-            if (need > allowed) { add = (int)allowed; new_nodes_available = false; }
-            else add = (int)need;
-            fill = (int)min((long long)n, (long long)add * k_new);
-          }
-          for (int i = lane; i < add; i += 32) {
-            int j = n_new + i;
-            int mj = k_new <= 0 ? 0 : min(k_new, fill - i * k_new);
-            for (int a = 0; a < p.A; ++a) nfree[(size_t)a * cap + j] = tfree[a] - (req[a] > 0 ? (int64_t)mj * req[a] : 0);
-            nslots[j] = tslots - mj;
-            nports[j] = mj > 0 ? pbit : 0ull;
-            nsched[j] = mj > 0;
-          }
-          if (k_new > 0) { nodes_with_pods += add; placed += fill; n -= fill; }
-          n_new += add;
-          __syncwarp();
-        }
-      }
-      pods_total += placed;
-      if (lane == 0 && p.sched) p.sched[(size_t)t * p.E + g] = placed;
-    }
-    if (lane == 0) {
-      p.node_count[t] = nodes_with_pods;
-      p.pod_count[t] = pods_total;
-    }
-    __syncwarp();
-  }
-}
-
-int launch_pack(Engine* e) {
-  int nt = e->t_end - e->t_begin;
-  if (nt <= 0) return 0;
-  PackParams p{};
-  p.E = e->E; p.T = e->T; p.N = e->N; p.U = e->U; p.A = e->A; p.t_begin = e->t_begin; p.t_end = e->t_end;
-  for (int a = 0; a < CAE_MAX_RES; ++a) p.act_dim[a] = e->act_dim[a];
-  p.order = e->d_order; p.order_n = e->d_order_n; p.pre_code = e->d_pre_code; p.spec_sc = e->d_spec_sc;
-  p.tmpl_free = e->d_tmpl_free; p.tmpl_slots = e->d_tmpl_slots; p.max_nodes = e->d_max_nodes;
-  p.pc_of = e->d_pc_of; p.port_conf = e->d_port_conf;
-  p.node_count = e->d_counts2; p.pod_count = e->d_counts2 + e->T; p.sched = e->d_sched;
-  p.work_counter = e->d_work_counter;
-  // node capacity of a slab: the largest limiter cap, or (unlimited) one node per pod + 1
-  // (every added node but possibly the last holds >= 1 pod)
-  int cap = std::max(1, std::min(e->P + 1, e->pack_cap));
-  p.cap = cap;
-  size_t per_warp = (size_t)cap * ((size_t)e->A * 8 + 8 + 4 + 4 + 1);
-  per_warp = (per_warp + 255) & ~(size_t)255;
-  int warps = std::min(nt, e->sm_count * 16);
-  const size_t budget = (size_t)16 << 30;  // keep the slabs within 16 GiB of the 180 GB HBM
-  if (per_warp * warps > budget) warps = (int)std::max<size_t>(1, budget / per_warp);
-  int blocks = (warps + 3) / 4;
-  warps = blocks * 4;
-  size_t need = per_warp * warps;
-  if (need > e->pack_scratch_bytes) {
-    if (e->d_pack_scratch) cudaFree(e->d_pack_scratch);
-    e->d_pack_scratch = nullptr;
-    CAE_CUDA(cudaMalloc(&e->d_pack_scratch, need));
-    e->pack_scratch_bytes = need;
-  }
-  p.scratch = static_cast<unsigned char*>(e->d_pack_scratch);
-  p.scratch_per_warp = per_warp;
-  CAE_CUDA(cudaMemsetAsync(e->d_work_counter, 0, sizeof(int32_t), e->stream));
-  pack_kernel<<<blocks, 128, 0, e->stream>>>(e->dobj, p);
-  e->stats.kernel_launches++;
-  CAE_KERNEL_OK();
-  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1,0 +1,652 @@
+// pack.cu — K3: BinpackingNodeEstimator.Estimate (estimator/binpacking_estimator.go:97-247) on the GPU.
+//
+// One WARP per template (templates are independent simulations; inside one, placement order is
+// sequential by construction), persistent with an atomic work counter.  Per-template node state
+// lives in a per-warp global slab (L1/L2 resident); lanes stride over the nodes.
+//
+// Plain groups (identical pods, no topology spread / inter-pod affinity involvement) are placed in
+// CLOSED FORM:
+//   * tryToScheduleOnExistingNodes (:141-164): SchedulePodOnAnyNodeMatching scans cyclically from
+//     lastIndex (predicate/plugin_runner.go:81,123), so identical pods are dealt round-robin over the
+//     added nodes with spare capacity k_j: every node gets min(k_j, L), the first `rem` nodes in
+//     cyclic order with k_j > L get one more (L = largest lap count with sum min(k_j, L) <= n).
+//   * tryToScheduleOnNewNodes (:168-247): only the last added node is tried, so each new node takes
+//     min(remaining, k_new) until the limiter denies (:222); an empty last node stops the group (:212);
+//     a pod that fits no fresh node still adds one (:227-240).
+// Dynamic groups (dyn.cuh) run the reference's per-pod loop, but against INCREMENTAL counters
+// instead of a PreFilter rescan per pod: per-domain counts are seeded from the cluster base counts,
+// the nodes added so far and the run's placement log, then updated on every placement; nodes that
+// failed are stamped and skipped until a counter minimum / presence changes (only then can a failed
+// node become feasible again).
+#include <climits>
+
+#include "engine.h"
+
+namespace cae {
+
+struct PackParams {
+  int E, T, N, U, t_begin, t_end, cap, has_dyn, dstride, log_cap;
+  const int32_t *order, *order_n;
+  const uint8_t* pre_code;
+  const int32_t *spec_sc, *spec_dc;
+  const int64_t* tmpl_free;  // [A][T]
+  const int32_t *tmpl_slots, *max_nodes, *pc_of;
+  const unsigned long long* port_conf;
+  const int64_t* c_free;  // [A][N]
+  const int32_t* c_slots;
+  int act_dim[CAE_MAX_RES];
+  int32_t *node_count, *pod_count, *sched, *work_counter, *status;
+  unsigned char* scratch;
+  size_t scratch_per_warp;
+};
+
+__device__ __forceinline__ int wsum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ long long wsum_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int wmax(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int wmin(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// per-warp description of the dynamic group being placed (shared memory, uniform reads)
+struct WarpDyn {
+  int nq;
+  int qid[DYN_MAX_Q], kind[DYN_MAX_Q], k[DYN_MAX_Q], host[DYN_MAX_Q], Dc[DYN_MAX_Q], tslot[DYN_MAX_Q];
+  int wown[DYN_MAX_Q], self[DYN_MAX_Q], maxskew[DYN_MAX_Q], mindom[DYN_MAX_Q], elig_new[DYN_MAX_Q], dsw[DYN_MAX_Q];
+  int minv[DYN_MAX_Q], nmin[DYN_MAX_Q], ndom[DYN_MAX_Q], tot[DYN_MAX_Q];
+  int aff_self;
+};
+
+constexpr int PACK_WARPS = 4;
+
+template <int A>
+__global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, DynTables d, PackParams p) {
+  __shared__ WarpDyn s_wd[PACK_WARPS];
+  const int lane = threadIdx.x & 31;
+  WarpDyn& wd = s_wd[threadIdx.x >> 5];
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  unsigned char* slab = p.scratch + (size_t)warp_global * p.scratch_per_warp;
+  const int N = p.N, NT = p.N + p.T;
+  const int Neff = p.has_dyn ? N : 0;  // cluster nodes carry run state only when a fallback can reach them
+  const int X = Neff + p.cap;
+  int64_t* nfree = reinterpret_cast<int64_t*>(slab);                                  // [A][X]
+  unsigned long long* nports = reinterpret_cast<unsigned long long*>(nfree + (size_t)(A > 0 ? A : 1) * X);  // [X]
+  int32_t* nslots = reinterpret_cast<int32_t*>(nports + X);                           // [X]
+  int32_t* kbuf = nslots + X;                                                         // [X] capacities of the current pass
+  int32_t* stamp = kbuf + X;                                                          // [X] "failed at stamp"
+  int32_t* wcnt = stamp + X;                                                          // [DYN_MAX_Q][dstride]
+  int32_t* wpres = wcnt + (size_t)DYN_MAX_Q * p.dstride;                              // [DYN_MAX_Q][dstride]
+  int32_t* logbuf = wpres + (size_t)DYN_MAX_Q * p.dstride;                            // [log_cap][3]
+  uint8_t* nsched = reinterpret_cast<uint8_t*>(logbuf + (size_t)p.log_cap * 3);       // [X]
+  int stamp_ctr = 1;
+
+  for (;;) {
+    int t = 0;
+    if (lane == 0) t = p.t_begin + atomicAdd(p.work_counter, 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= p.t_end) break;
+
+    int64_t tfree[A > 0 ? A : 1];
+#pragma unroll
+    for (int a = 0; a < A; ++a) tfree[a] = p.tmpl_free[(size_t)a * p.T + t];
+    const int tslots = p.tmpl_slots[t];
+    const int max_nodes = p.max_nodes ? p.max_nodes[t] : 0;
+    const int col_new = N + p.T + t;  // universe column of the sanitized template
+    int n_new = 0, nodes_with_pods = 0, pods_total = 0, last_index = 0, log_n = 0;
+    bool new_nodes_available = true, cl_init = false, overflow = false;
+    const int n_groups = p.order_n[t];
+
+    // ---- shared helpers -----------------------------------------------------------------------
+    auto slot_of = [&](int q, int x) -> int {
+      if (x < Neff) return d.dom[(size_t)wd.k[q] * NT + x];
+      if (wd.host[q]) return wd.Dc[q] + 1 + (x - Neff);
+      return wd.tslot[q];
+    };
+    auto elig_of = [&](int q, int x) -> bool {
+      return x < Neff ? d.elig[(size_t)wd.qid[q] * p.U + x] != 0 : wd.elig_new[q] != 0;
+    };
+    auto log_append = [&](bool mine, int x, int spec, int cnt) {  // warp-aggregated append
+      unsigned m = __ballot_sync(0xffffffffu, mine);
+      if (!m) return;
+      int rank = __popc(m & ((1u << lane) - 1));
+      if (mine) {
+        int idx = log_n + rank;
+        if (idx < p.log_cap) { logbuf[idx * 3] = x; logbuf[idx * 3 + 1] = spec; logbuf[idx * 3 + 2] = cnt; }
+      }
+      log_n += __popc(m);
+      if (log_n > p.log_cap) overflow = true;
+    };
+
+    for (int gi = 0; gi < n_groups; ++gi) {
+      const int g = p.order[(size_t)t * p.E + gi];
+      const int pb = o.group_off[g];
+      int n = o.group_off[g + 1] - pb;
+      const int spec = o.pend_spec[pb];
+      int64_t req[A > 0 ? A : 1];
+#pragma unroll
+      for (int a = 0; a < A; ++a) req[a] = o.ps_req[(size_t)spec * R + p.act_dim[a]];
+      const int sc = p.spec_sc[spec];
+      const int dc = p.has_dyn ? p.spec_dc[spec] : 0;
+      const bool static_new = (p.pre_code[(size_t)sc * p.U + col_new] & 0x0F) == 0;
+      const int plist = o.ps_port_list[spec];
+      const bool has_ports = o.port_off[plist + 1] > o.port_off[plist];
+      const unsigned long long pconf = has_ports ? p.port_conf[plist] : 0ull;  // port sets this pod collides with
+      const unsigned long long pbit = has_ports ? (1ull << p.pc_of[plist]) : 0ull;
+      const bool feeds = p.has_dyn && d.group_feeds[g];
+      int placed = 0;
+
+      if (dc == 0) {
+        // ======================= plain group: closed form =======================================
+        if (n_new > 0 && static_new) {
+          const int list_len = N + n_new;
+          const int s = last_index >= N ? last_index - N : 0;  // first added node in cyclic scan order
+          long long total = 0;
+          int kmax = 0;
+          for (int j = lane; j < n_new; j += 32) {
+            const int x = Neff + j;
+            int k = min(nslots[x], n);
+            if (k > 0 && (nports[x] & pconf)) k = 0;
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+              if (req[a] > 0 && k > 0) {
+                const int64_t f = nfree[(size_t)a * X + x];
+                if (f < req[a]) k = 0;
+                else if (f < (int64_t)k * req[a]) k = (int)(f / req[a]);
+              }
+            }
+            if (has_ports) k = min(k, 1);
+            kbuf[x] = k;
+            total += k;
+            kmax = max(kmax, k);
+          }
+          total = wsum_ll(total);
+          kmax = wmax(kmax);
+          __syncwarp();
+          if (total > 0) {
+            int L, rem;
+            if (total <= n) { L = kmax; rem = 0; }
+            else {
+              int lo = 0, hi = kmax;  // f(lo) <= n < f(hi), f(L) = sum min(k_j, L)
+              while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                long long f = 0;
+                for (int j = lane; j < n_new; j += 32) f += min(kbuf[Neff + j], mid);
+                f = wsum_ll(f);
+                if (f <= n) lo = mid; else hi = mid;
+              }
+              L = lo;
+              long long f = 0;
+              for (int j = lane; j < n_new; j += 32) f += min(kbuf[Neff + j], L);
+              rem = (int)(n - wsum_ll(f));
+            }
+            int seen = 0, last_pos = -1, newly = 0, got = 0;
+            for (int base = 0; base < n_new; base += 32) {
+              const int pos = base + lane;
+              const bool in = pos < n_new;
+              int j = s + pos;
+              if (j >= n_new) j -= n_new;
+              const int x = Neff + (in ? j : 0);
+              const int k = in ? kbuf[x] : 0;
+              const bool extra_c = in && k > L;
+              const unsigned m = __ballot_sync(0xffffffffu, extra_c);
+              const int rank = seen + __popc(m & ((1u << lane) - 1));
+              const int mj = in ? min(k, L) + ((extra_c && rank < rem) ? 1 : 0) : 0;
+              seen += __popc(m);
+              if (mj > 0) {
+#pragma unroll
+                for (int a = 0; a < A; ++a) if (req[a] > 0) nfree[(size_t)a * X + x] -= (int64_t)mj * req[a];
+                nslots[x] -= mj;
+                nports[x] |= pbit;
+                if (!nsched[x]) { nsched[x] = 1; newly++; }
+                got += mj;
+                // the pod placed last sits at the furthest position served in the final lap
+                if (rem > 0 ? (extra_c && rank < rem) : (k >= L)) last_pos = pos;
+              }
+              if (feeds) log_append(mj > 0, x, spec, mj);
+            }
+            got = wsum(got);
+            newly = wsum(newly);
+            last_pos = wmax(last_pos);
+            placed += got;
+            nodes_with_pods += newly;
+            n -= got;
+            if (last_pos >= 0) {
+              int jl = s + last_pos;
+              if (jl >= n_new) jl -= n_new;
+              last_index = (N + jl + 1) % list_len;
+            }
+            __syncwarp();
+          }
+        }
+        if (n > 0 && new_nodes_available) {
+          // after the pass above no added node (the last one included) can take this pod any more
+          const bool stop = (n_new > 0) && !nsched[Neff + n_new - 1];  // last node still empty (:212)
+          if (!stop) {
+            int k_new = 0;
+            if (static_new) {
+              k_new = min(tslots, n);
+#pragma unroll
+              for (int a = 0; a < A; ++a) {
+                if (req[a] > 0 && k_new > 0) {
+                  if (tfree[a] < req[a]) k_new = 0;
+                  else if (tfree[a] < (int64_t)k_new * req[a]) k_new = (int)(tfree[a] / req[a]);
+                }
+              }
+              if (has_ports) k_new = min(k_new, 1);  // DaemonSet port conflicts are part of static_new
+            }
+            long long allowed = max_nodes < 0 ? 0 : (max_nodes == 0 ? (long long)INT_MAX : max((long long)max_nodes - n_new, 0ll));
+            if (allowed > p.cap - n_new) { allowed = p.cap - n_new; }
+            int add, fill = 0;
+            if (k_new <= 0) {
+              add = allowed >= 1 ? 1 : 0;  // the node is added, the pod still fails on it (:235-240)
+              if (allowed < 1) new_nodes_available = false;
+            } else {
+              const long long need = ((long long)n + k_new - 1) / k_new;
+              if (need > allowed) { add = (int)allowed; new_nodes_available = false; }
+              else add = (int)need;
+              fill = (int)min((long long)n, (long long)add * k_new);
+            }
+            for (int base = 0; base < add; base += 32) {
+              const int i = base + lane;
+              const bool in = i < add;
+              const int x = Neff + n_new + (in ? i : 0);
+              const int mj = (!in || k_new <= 0) ? 0 : min(k_new, fill - i * k_new);
+              if (in) {
+#pragma unroll
+                for (int a = 0; a < A; ++a) nfree[(size_t)a * X + x] = tfree[a] - (req[a] > 0 ? (int64_t)mj * req[a] : 0);
+                nslots[x] = tslots - mj;
+                nports[x] = mj > 0 ? pbit : 0ull;
+                nsched[x] = mj > 0;
+                stamp[x] = 0;
+              }
+              if (feeds) log_append(in && mj > 0, x, spec, mj);
+            }
+            if (k_new > 0) { nodes_with_pods += add; placed += fill; n -= fill; }
+            n_new += add;
+            __syncwarp();
+          }
+        }
+      } else {
+        // ======================= dynamic group: per-pod loop on incremental counters ===============
+        const bool host_spread = o.ps_hostname_spread[spec] != 0;
+        int cur_stamp = ++stamp_ctr;
+        int fb_fail_stamp = -1, fb_mark = 0;
+        // ---- describe the group's counters ----
+        __syncwarp();
+        if (lane == 0) {
+          int nq = 0;
+          for (int q = d.dc_q_off[dc]; q < d.dc_q_off[dc + 1]; ++q) {
+            if (!d.q_active[q]) continue;
+            const int k = d.q_k[q], kind = d.q_kind[q];
+            wd.qid[nq] = q; wd.kind[nq] = kind; wd.k[nq] = k; wd.host[nq] = d.is_host[k]; wd.Dc[nq] = d.Dc[k];
+            const int td = d.dom[(size_t)k * NT + N + t];
+            wd.tslot[nq] = td < 0 ? -1 : (td < d.Dc[k] ? td : d.Dc[k]);
+            wd.wown[nq] = d.q_wown[q]; wd.self[nq] = d.q_self[q];
+            wd.maxskew[nq] = kind == Q_PTS ? o.pts_max_skew[d.q_p0[q]] : 0;
+            wd.mindom[nq] = kind == Q_PTS ? o.pts_min_domains[d.q_p0[q]] : 0;
+            wd.elig_new[nq] = d.elig[(size_t)q * p.U + col_new];
+            wd.dsw[nq] = d.ds_w[(size_t)q * p.T + t];
+            wd.tot[nq] = d.base_tot[q];
+            ++nq;
+          }
+          wd.nq = nq;
+          wd.aff_self = d.dc_aff_self[dc];
+        }
+        __syncwarp();
+        const int nq = wd.nq;
+        // ---- seed the working counters: cluster base + nodes added so far ----
+        bool need_log = false;
+        for (int q = 0; q < nq; ++q) {
+          const int qid = wd.qid[q], off = d.q_base_off[qid], Dc = wd.Dc[q];
+          int32_t* wc = wcnt + (size_t)q * p.dstride;
+          int32_t* wp = wpres + (size_t)q * p.dstride;
+          for (int i = lane; i < Dc; i += 32) { wc[i] = d.base_cnt[off + i]; wp[i] = d.base_pres[off + i]; }
+          const int extra = 1 + (wd.host[q] ? n_new : 0);
+          const int en = wd.elig_new[q], dsw = wd.dsw[q];
+          for (int i = lane; i < extra; i += 32) {
+            int c = 0, pr = 0;
+            if (i >= 1 && en) { c = dsw; pr = 1; }  // fresh hostname domain of an added node
+            wc[Dc + i] = c; wp[Dc + i] = pr;
+          }
+          __syncwarp();
+          if (lane == 0 && en && n_new > 0) {
+            if (wd.host[q]) wd.tot[q] += n_new * dsw;
+            else if (wd.tslot[q] >= 0) { wc[wd.tslot[q]] += n_new * dsw; wp[wd.tslot[q]] += n_new; wd.tot[q] += n_new * dsw; }
+          }
+          if (d.q_nfeed[qid] - (wd.wown[q] > 0 ? 1 : 0) > 0) need_log = true;
+        }
+        __syncwarp();
+        if (need_log && log_n > 0) {  // pods other groups placed earlier in this run
+          for (int q = 0; q < nq; ++q) {
+            const int qid = wd.qid[q];
+            int32_t* wc = wcnt + (size_t)q * p.dstride;
+            int add = 0;
+            for (int i = lane; i < min(log_n, p.log_cap); i += 32) {
+              const int x = logbuf[i * 3], w = d.wmat[(size_t)qid * d.S + logbuf[i * 3 + 1]];
+              if (w == 0 || !elig_of(q, x)) continue;
+              const int sl = slot_of(q, x);
+              if (sl < 0) continue;
+              atomicAdd(&wc[sl], w * logbuf[i * 3 + 2]);
+              add += w * logbuf[i * 3 + 2];
+            }
+            add = wsum(add);
+            if (lane == 0) wd.tot[q] += add;
+          }
+          __syncwarp();
+        }
+        auto recompute = [&](int q) {  // min / #domains over the present domains of a spread counter
+          const int32_t* wc = wcnt + (size_t)q * p.dstride;
+          const int32_t* wp = wpres + (size_t)q * p.dstride;
+          const int len = wd.Dc[q] + 1 + (wd.host[q] ? n_new : 0);
+          int mn = INT_MAX, nd = 0;
+          for (int i = lane; i < len; i += 32) if (wp[i] > 0) { mn = min(mn, wc[i]); ++nd; }
+          mn = wmin(mn);
+          nd = wsum(nd);
+          int nm = 0;
+          for (int i = lane; i < len; i += 32) if (wp[i] > 0 && wc[i] == mn) ++nm;
+          nm = wsum(nm);
+          __syncwarp();
+          if (lane == 0) { wd.minv[q] = mn; wd.nmin[q] = nm; wd.ndom[q] = nd; }
+          __syncwarp();
+        };
+        for (int q = 0; q < nq; ++q) if (wd.kind[q] == Q_PTS) recompute(q);
+
+        auto ensure_cluster = [&]() {  // run state of the cluster nodes, needed once a fallback can place onto them
+          if (cl_init) return;
+          for (int x = lane; x < N; x += 32) {
+#pragma unroll
+            for (int a = 0; a < A; ++a) nfree[(size_t)a * X + x] = p.c_free[(size_t)a * N + x];
+            nslots[x] = p.c_slots[x];
+            nports[x] = 0ull;
+            nsched[x] = 0;
+            stamp[x] = 0;
+          }
+          cl_init = true;
+          __syncwarp();
+        };
+        // RunFilterPlugins on node x (default plugin order), per lane
+        auto eval = [&](int x) -> int {
+          const int col = x < Neff ? x : col_new;
+          const int code = p.pre_code[(size_t)sc * p.U + col] & 0x0F;
+          if (code) return code;
+          if (nports[x] & pconf) return CAE_R_NODE_PORTS;
+          bool fail = nslots[x] < 1;
+#pragma unroll
+          for (int a = 0; a < A; ++a) fail |= (req[a] > 0 && req[a] > nfree[(size_t)a * X + x]);
+          if (fail) return CAE_R_FIT;
+          bool aff_any = false, pods_exist = true;
+          long long aff_tot = 0;
+          for (int q = 0; q < nq; ++q) {
+            const int kind = wd.kind[q];
+            const int sl = slot_of(q, x);
+            const int c = sl >= 0 ? wcnt[(size_t)q * p.dstride + sl] : 0;
+            if (kind == Q_PTS) {  // podtopologyspread/filtering.go:314-359
+              if (sl < 0) return CAE_R_PTS_MISSING_LABEL;
+              const long long minm = wd.ndom[q] < wd.mindom[q] ? 0 : wd.minv[q];
+              if ((long long)c + wd.self[q] - minm > wd.maxskew[q]) return CAE_R_PTS_SKEW;
+            } else if (kind == Q_AFF) {  // interpodaffinity/filtering.go:382-408
+              aff_any = true;
+              if (sl < 0) return CAE_R_IPA_AFFINITY;
+              if (c <= 0) pods_exist = false;
+              aff_tot += wd.tot[q];
+            } else {
+              if (aff_any) {
+                if (!pods_exist && !(aff_tot == 0 && wd.aff_self)) return CAE_R_IPA_AFFINITY;
+                aff_any = false;
+              }
+              if (sl >= 0 && c > 0) return kind == Q_ANTI ? CAE_R_IPA_ANTI_AFFINITY : CAE_R_IPA_EXISTING_ANTI_AFFINITY;
+            }
+          }
+          if (aff_any && !pods_exist && !(aff_tot == 0 && wd.aff_self)) return CAE_R_IPA_AFFINITY;
+          return CAE_R_OK;
+        };
+        // ForceAddPod on node x (uniform x) + counter upkeep
+        auto place = [&](int x) {
+          const bool newly = !nsched[x];
+          __syncwarp();
+          if (lane == 0) {
+#pragma unroll
+            for (int a = 0; a < A; ++a) if (req[a] > 0) nfree[(size_t)a * X + x] -= req[a];
+            nslots[x] -= 1;
+            nports[x] |= pbit;
+            nsched[x] = 1;
+          }
+          if (newly) ++nodes_with_pods;
+          bool bump = false;
+          for (int q = 0; q < nq; ++q) {
+            const int w = wd.wown[q];
+            if (w == 0 || !elig_of(q, x)) continue;
+            const int sl = slot_of(q, x);
+            if (sl < 0) continue;
+            int32_t* wc = wcnt + (size_t)q * p.dstride;
+            const int old = wc[sl];
+            __syncwarp();
+            if (lane == 0) { wc[sl] = old + w; wd.tot[q] += w; }
+            if (wd.kind[q] == Q_PTS) {
+              if (old == wd.minv[q]) {
+                const int nm = wd.nmin[q] - 1;
+                __syncwarp();
+                if (lane == 0) wd.nmin[q] = nm;
+                __syncwarp();
+                if (nm == 0) { recompute(q); bump = true; }
+              }
+            } else if (old == 0) bump = true;  // 0 -> positive can make affinity satisfiable elsewhere
+            __syncwarp();
+          }
+          if (feeds) log_append(lane == 0, x, spec, 1);
+          if (bump) cur_stamp = ++stamp_ctr;
+          ++placed;
+          --n;
+          __syncwarp();
+        };
+        // addNewNodeToSnapshot (:249-265): a sanitized copy of the template joins the list
+        auto add_node = [&]() {
+          const int j = n_new, x = Neff + j;
+          if (lane == 0) {
+#pragma unroll
+            for (int a = 0; a < A; ++a) nfree[(size_t)a * X + x] = tfree[a];
+            nslots[x] = tslots;
+            nports[x] = 0ull;
+            nsched[x] = 0;
+            stamp[x] = 0;
+          }
+          n_new = j + 1;
+          bool bump = false;
+          for (int q = 0; q < nq; ++q) {
+            int32_t* wc = wcnt + (size_t)q * p.dstride;
+            int32_t* wp = wpres + (size_t)q * p.dstride;
+            const int en = wd.elig_new[q], dsw = wd.dsw[q];
+            const int sl = slot_of(q, x);
+            if (wd.host[q]) {  // a brand-new hostname domain
+              if (lane == 0) { wc[sl] = en ? dsw : 0; wp[sl] = en ? 1 : 0; }
+            } else if (en && sl >= 0) {
+              if (lane == 0) { wc[sl] += dsw; wp[sl] += 1; }
+            }
+            __syncwarp();
+            if (en && sl >= 0) {
+              if (lane == 0) wd.tot[q] += dsw;
+              if (wd.kind[q] == Q_PTS) {
+                // a node joining can only HELP other nodes when it lifts the domain count over minDomains
+                // (global minimum stops being treated as 0, filtering.go:55-68) or raises the minimum
+                const int old_nd = wd.ndom[q], old_mn = wd.minv[q];
+                recompute(q);
+                if ((old_nd < wd.mindom[q] && wd.ndom[q] >= wd.mindom[q]) || wd.minv[q] > old_mn) bump = true;
+              } else if (dsw > 0) bump = true;
+            }
+            __syncwarp();
+          }
+          if (bump) cur_stamp = ++stamp_ctr;
+          __syncwarp();
+        };
+
+        // ---- tryToScheduleOnExistingNodes: per pod, first passing added node in cyclic order ----
+        while (n > 0 && n_new > 0) {
+          const int s = last_index >= N ? last_index - N : 0;
+          int found = -1;
+          for (int base = 0; base < n_new && found < 0; base += 32) {
+            const int pos = base + lane;
+            const bool in = pos < n_new;
+            int j = s + pos;
+            if (j >= n_new) j -= n_new;
+            const int x = Neff + (in ? j : 0);
+            bool ok = false;
+            if (in && stamp[x] != cur_stamp) {
+              ok = eval(x) == CAE_R_OK;
+              if (!ok) stamp[x] = cur_stamp;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (m) found = __shfl_sync(0xffffffffu, j, __ffs(m) - 1);
+          }
+          if (found < 0) break;  // first pod that fits nowhere ends this phase for the group (:158)
+          place(Neff + found);
+          last_index = (N + found + 1) % (N + n_new);
+        }
+        // ---- tryToScheduleOnNewNodes ----
+        while (n > 0 && new_nodes_available) {
+          bool found = false;
+          if (n_new > 0) {
+            const int xl = Neff + n_new - 1;
+            const int r = eval(xl);
+            if (r == CAE_R_OK) { place(xl); found = true; }
+            else if (host_spread && r == CAE_R_PTS_SKEW) {
+              // SchedulePodOnAnyNodeMatching(name != lastNodeName) (:190-205): whole list, cyclic from lastIndex
+              ensure_cluster();
+              const int len = N + n_new, lastpos = N + n_new - 1;
+              int hit = -1;
+              if (fb_fail_stamp == cur_stamp) {
+                // everything scanned before still fails; only nodes added since can pass
+                int best = INT_MAX;
+                for (int base = fb_mark; base < n_new - 1; base += 32) {
+                  const int j = base + lane;
+                  int dist = INT_MAX;
+                  if (j < n_new - 1 && eval(Neff + j) == CAE_R_OK) { dist = N + j - last_index; if (dist < 0) dist += len; }
+                  best = min(best, wmin(dist));
+                }
+                if (best != INT_MAX) { hit = last_index + best; if (hit >= len) hit -= len; }
+              } else {
+                for (int base = 0; base < len && hit < 0; base += 32) {
+                  const int pos = base + lane;
+                  int idx = last_index + pos;
+                  if (idx >= len) idx -= len;
+                  bool ok = false;
+                  if (pos < len && idx != lastpos) {
+                    const int x = idx < N ? idx : Neff + (idx - N);
+                    if (!(idx < N && o.node_unschedulable[idx]) && stamp[x] != cur_stamp) {  // plugin_runner.go:92-94
+                      ok = eval(x) == CAE_R_OK;
+                      if (!ok) stamp[x] = cur_stamp;
+                    }
+                  }
+                  const unsigned m = __ballot_sync(0xffffffffu, ok);
+                  if (m) hit = __shfl_sync(0xffffffffu, idx, __ffs(m) - 1);
+                }
+              }
+              if (hit >= 0) {
+                place(hit < N ? hit : Neff + (hit - N));
+                last_index = (hit + 1) % len;
+                found = true;
+              } else { fb_fail_stamp = cur_stamp; fb_mark = n_new; }
+            }
+          }
+          if (!found) {
+            if (n_new > 0 && !nsched[Neff + n_new - 1]) break;  // last node still empty (:212)
+            const bool permit = !(max_nodes < 0 || (max_nodes > 0 && n_new >= max_nodes)) && n_new < p.cap;
+            if (!permit) { new_nodes_available = false; break; }  // (:222)
+            const int stamp_before = cur_stamp;
+            add_node();
+            if (fb_fail_stamp == stamp_before && cur_stamp != stamp_before) fb_fail_stamp = -1;
+            if (eval(Neff + n_new - 1) != CAE_R_OK) break;  // (:238-240)
+            place(Neff + n_new - 1);
+          }
+        }
+      }
+      pods_total += placed;
+      if (lane == 0 && p.sched) p.sched[(size_t)t * p.E + g] = placed;
+    }
+    if (lane == 0) {
+      p.node_count[t] = nodes_with_pods;
+      p.pod_count[t] = pods_total;
+      if (overflow && p.status) atomicExch(p.status, 1);
+    }
+    __syncwarp();
+  }
+}
+
+template <int A>
+static void launch_pack_a(int blocks, cudaStream_t st, const DevObjects& o, const DynTables& d, const PackParams& p) {
+  pack_kernel<A><<<blocks, PACK_WARPS * 32, 0, st>>>(o, d, p);
+}
+
+int launch_pack(Engine* e) {
+  int nt = e->t_end - e->t_begin;
+  if (nt <= 0) return 0;
+  PackParams p{};
+  p.E = e->E; p.T = e->T; p.N = e->N; p.U = e->U; p.t_begin = e->t_begin; p.t_end = e->t_end;
+  p.has_dyn = e->has_dynamic ? 1 : 0;
+  for (int a = 0; a < CAE_MAX_RES; ++a) p.act_dim[a] = e->act_dim[a];
+  p.order = e->d_order; p.order_n = e->d_order_n; p.pre_code = e->d_pre_code; p.spec_sc = e->d_spec_sc; p.spec_dc = e->d_spec_dc;
+  p.tmpl_free = e->d_tmpl_free; p.tmpl_slots = e->d_tmpl_slots; p.max_nodes = e->d_max_nodes;
+  p.pc_of = e->d_pc_of; p.port_conf = e->d_port_conf; p.c_free = e->d_c_free; p.c_slots = e->d_c_slots;
+  p.node_count = e->d_counts2; p.pod_count = e->d_counts2 + e->T; p.sched = e->d_sched;
+  p.work_counter = e->d_work_counter; p.status = e->d_work_counter + 1;
+  // node capacity of a slab: the largest limiter cap, or (unlimited) one node per pod + 1
+  // (every added node but possibly one holds >= 1 pod)
+  const int cap = std::max(1, std::min(e->P + 1, e->pack_cap));
+  p.cap = cap;
+  const int Neff = p.has_dyn ? e->N : 0;
+  const size_t X = (size_t)Neff + cap;
+  int dmax = 1;
+  for (int k = 0; k < e->dyn.K; ++k) dmax = std::max(dmax, e->dyn.Dc[k] + 1 + (e->dyn.is_host[k] ? cap : 0));
+  p.dstride = p.has_dyn ? dmax : 1;
+  p.log_cap = p.has_dyn ? (int)std::min<size_t>(4 * X + 1024, (size_t)1 << 24) : 1;
+  const int A1 = std::max(e->A, 1);
+  size_t per_warp = X * ((size_t)A1 * 8 + 8 + 4 + 4 + 4 + 1) + (size_t)2 * DYN_MAX_Q * p.dstride * 4 + (size_t)p.log_cap * 12;
+  per_warp = (per_warp + 255) & ~(size_t)255;
+  int warps = std::min(nt, e->sm_count * 16);
+  const size_t budget = (size_t)24 << 30;  // keep the slabs within 24 GiB of the 180 GB HBM
+  if (per_warp * warps > budget) warps = (int)std::max<size_t>(1, budget / per_warp);
+  int blocks = (warps + PACK_WARPS - 1) / PACK_WARPS;
+  warps = blocks * PACK_WARPS;
+  size_t need = per_warp * warps;
+  if (need > e->pack_scratch_bytes) {
+    if (e->d_pack_scratch) cudaFree(e->d_pack_scratch);
+    e->d_pack_scratch = nullptr;
+    e->pack_scratch_bytes = 0;
+    CAE_CUDA(cudaMalloc(&e->d_pack_scratch, need));
+    e->pack_scratch_bytes = need;
+    CAE_CUDA(cudaMemsetAsync(e->d_pack_scratch, 0, need, e->stream));  // stamps start at 0
+  } else if (p.has_dyn) {
+    CAE_CUDA(cudaMemsetAsync(e->d_pack_scratch, 0, need, e->stream));  // the slab layout may have moved
+  }
+  p.scratch = static_cast<unsigned char*>(e->d_pack_scratch);
+  p.scratch_per_warp = per_warp;
+  CAE_CUDA(cudaMemsetAsync(e->d_work_counter, 0, sizeof(int32_t) * 2, e->stream));
+  switch (e->A) {
+    case 0: launch_pack_a<0>(blocks, e->stream, e->dobj, e->dyn, p); break;
+    case 1: launch_pack_a<1>(blocks, e->stream, e->dobj, e->dyn, p); break;
+    case 2: launch_pack_a<2>(blocks, e->stream, e->dobj, e->dyn, p); break;
+    case 3: launch_pack_a<3>(blocks, e->stream, e->dobj, e->dyn, p); break;
+    case 4: launch_pack_a<4>(blocks, e->stream, e->dobj, e->dyn, p); break;
+    case 5: launch_pack_a<5>(blocks, e->stream, e->dobj, e->dyn, p); break;
+    case 6: launch_pack_a<6>(blocks, e->stream, e->dobj, e->dyn, p); break;
+    case 7: launch_pack_a<7>(blocks, e->stream, e->dobj, e->dyn, p); break;
+    default: launch_pack_a<8>(blocks, e->stream, e->dobj, e->dyn, p); break;
+  }
+  e->stats.kernel_launches++;
+  CAE_KERNEL_OK();
+  return 0;
+}
+
+}  // namespace cae

@@ -37,7 +37,7 @@ struct DevObjects {
   const int32_t *aff_off, *aterm_selector, *aterm_key, *aterm_ns_off, *aterm_ns, *aterm_ns_selector;
   const int32_t *ps_namespace, *ps_labelset; const int64_t* ps_req;
   const int32_t *ps_tol_list, *ps_naff, *ps_node_name, *ps_port_list, *ps_pts_list, *ps_aff_list, *ps_anti_list;
-  const uint8_t* ps_terminating;
+  const uint8_t* ps_terminating; const uint8_t* ps_hostname_spread;
   const int32_t *node_name, *node_labelset, *node_taint_list; const uint8_t* node_unschedulable;
   const int64_t* node_alloc; const int32_t* node_allowed_pods;
   const int64_t *node_cap_cpu, *node_cap_mem; const uint8_t *node_has_alloc_cpu, *node_has_alloc_mem;

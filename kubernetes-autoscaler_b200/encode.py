@@ -231,10 +231,14 @@ class TableBuilder:
 
     def podspec(self, namespace: int, labelset: int, req: Sequence[int], tol_list: int = 0,
                 naff: int = -1, node_name: int = -1, port_list: int = 0, pts_list: int = 0,
-                aff_list: int = 0, anti_list: int = 0, terminating: bool = False) -> int:
+                aff_list: int = 0, anti_list: int = 0, terminating: bool = False,
+                hostname_spread: Optional[bool] = None) -> int:
         req = tuple(int(x) for x in req) + (0,) * (MAX_RES - len(req))
+        if hostname_spread is None:  # default: derived from the hard constraints
+            hostname_spread = any(self.pts.cols[1][i] == self.hostname_key
+                                  for i in range(self.pts.off[pts_list], self.pts.off[pts_list + 1]))
         key = (namespace, labelset, req, tol_list, naff, node_name, port_list, pts_list, aff_list,
-               anti_list, bool(terminating))
+               anti_list, bool(terminating), bool(hostname_spread))
         i = self.ps_ids.get(key)
         if i is None:
             i = len(self.ps_rows)
@@ -337,7 +341,7 @@ class EncodedObjects:
         a["aterm_ns"] = _i32(b.aterm_ns)
         a["aterm_ns_selector"] = _i32(b.aterm_ns_selector)
         nps = len(b.ps_rows)
-        cols = list(zip(*b.ps_rows)) if nps else [[] for _ in range(11)]
+        cols = list(zip(*b.ps_rows)) if nps else [[] for _ in range(12)]
         a["ps_namespace"] = _i32(cols[0])
         a["ps_labelset"] = _i32(cols[1])
         a["ps_req"] = np.ascontiguousarray(np.asarray(cols[2], dtype=np.int64).reshape(nps, MAX_RES))
@@ -349,6 +353,7 @@ class EncodedObjects:
         a["ps_aff_list"] = _i32(cols[8])
         a["ps_anti_list"] = _i32(cols[9])
         a["ps_terminating"] = np.asarray(cols[10], dtype=np.uint8)
+        a["ps_hostname_spread"] = np.asarray(cols[11], dtype=np.uint8)
         nn = len(b.node_rows)
         ncols = list(zip(*b.node_rows)) if nn else [[] for _ in range(9)]
         a["node_name"] = _i32(ncols[0])
@@ -561,7 +566,8 @@ class Encoder:
 
         sid = b.podspec(ns, self._labelset(pod.labels), self._resource_vec(pod.requests), tols, naff,
                         self.node_names(pod.node_name) if pod.node_name else -1, ports, pts,
-                        aff(pod.pod_affinity), aff(pod.pod_anti_affinity), pod.terminating)
+                        aff(pod.pod_affinity), aff(pod.pod_anti_affinity), pod.terminating,
+                        any(c.topology_key == LABEL_HOSTNAME for c in pod.topology_spread))
         self._podspec_cache[id(pod)] = sid
         return sid
 

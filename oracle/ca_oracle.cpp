@@ -580,12 +580,7 @@ void estimate(Snapshot& s, int tmpl, const std::vector<int>& groups_in, int max_
         int r = s.schedulePod(spec, last_node);
         if (r == CAE_R_OK) { found = true; track(last_node); ++res.sched[g]; }
         /* isPodUsingHostNameTopologyKey && hasTopologyConstraintError (:186, :269-292) */
-        bool host_pts = false;
-        int pl = o->ps_pts_list[spec];
-        /* the reference inspects pod.Spec.TopologySpreadConstraints (ALL constraints incl. ScheduleAnyway);
-         * the encoder only keeps DoNotSchedule ones — a ScheduleAnyway hostname constraint alone cannot
-         * produce ErrReasonConstraintsNotMatch, so the conjunction below is unaffected. */
-        for (int i = o->pts_off[pl]; i < o->pts_off[pl + 1]; ++i) if (o->pts_key[i] == o->hostname_key) host_pts = true;
+        const bool host_pts = o->ps_hostname_spread[spec] != 0;
         if (host_pts && r == CAE_R_PTS_SKEW) {
           int ln = last_node;
           int idx = s.schedulePodOnAnyNodeMatching(spec, [&](const NodeState&, int i) { return i != ln; });

@@ -193,3 +193,129 @@ def test_static_predicates_edge_cases(eng, oracle):
     _check_estimate(eng, oracle, enc, np.full(enc.T, 10))
     want = oracle.feasibility_groups(enc)
     assert len(set(want.ravel().tolist())) >= 7   # the case really exercises many distinct reasons
+
+
+# ---------------------------------------------------------------------------------------------------
+# PodTopologySpread / InterPodAffinity (dyn.cuh, pack.cu dynamic path)
+# ---------------------------------------------------------------------------------------------------
+from kubernetes_autoscaler_b200.objects import (LabelSelector, Namespace, PodAffinityTerm, TopologySpreadConstraint,  # noqa: E402
+                                                WithMaxSkew, WithPodAffinity, WithPodAntiAffinity)
+
+HOST, ZONE = "kubernetes.io/hostname", "topology.kubernetes.io/zone"
+
+
+@pytest.mark.parametrize("cpu,mem,max_skew,key,min_domains,pods,pod_cpu,pod_mem,exp", [
+    (1000, 5000, 2, HOST, 1, 8, 200, 200, (4, 8)),     # binpacking_estimator_test.go:175
+    (1000, 5000, 2, ZONE, 1, 8, 20, 100, (1, 2)),      # :192
+    (1000, 5000, 1, HOST, 3, 12, 20, 100, (3, 12)),    # :209 (oldnode receives the fallback pod and is counted)
+], ids=["hostname-skew2", "zone-skew2", "hostname-skew1-mindomains3"])
+def test_reference_spread_kats_on_gpu(eng, oracle, cpu, mem, max_skew, key, min_domains, pods, pod_cpu, pod_mem, exp):
+    groups = [makePodEquivalenceGroup(_pod(pod_cpu, pod_mem, WithMaxSkew(max_skew, key, min_domains)), pods)]
+    enc = _kat_fixture(cpu, mem, 10, groups)
+    _check_dense(eng, oracle, enc)
+    nc, pc = _check_estimate(eng, oracle, enc, [0])
+    assert (int(nc[0]), int(pc[0])) == exp
+
+
+def test_c3_shaped(eng, oracle):
+    """Config 3 predicates (+ PodTopologySpread hostname/zone, existing cluster with resident pods)."""
+    enc = synth.generate(3, pods=4_000, templates=48, cluster_nodes=60)
+    _check_dense(eng, oracle, enc)
+    _check_estimate(eng, oracle, enc, np.full(enc.T, 1000))
+    _check_estimate(eng, oracle, enc, np.full(enc.T, 12))
+    _check_estimate(eng, oracle, enc, np.zeros(enc.T))
+
+
+def test_c4_shaped(eng, oracle):
+    """Config 4 predicates (+ InterPodAffinity: self anti-affinity on hostname, affinity to another group on zone)."""
+    enc = synth.generate(4, pods=4_000, templates=40, cluster_nodes=50)
+    _check_dense(eng, oracle, enc)
+    _check_estimate(eng, oracle, enc, np.full(enc.T, 1000))
+    _check_estimate(eng, oracle, enc, np.full(enc.T, 7))
+
+
+def _znode(name, zone, cpu=4000, mem=8 << 30, pods=20, labels=None, taints=None):
+    n = BuildTestNode(name, cpu, mem)
+    n.labels = {HOST: name, ZONE: zone}
+    n.labels.update(labels or {})
+    n.allocatable["pods"] = pods
+    n.taints = list(taints or [])
+    return n
+
+
+def test_spread_and_affinity_edge_cases(eng, oracle):
+    """Cross-group selectors, two constraints per pod, minDomains, inclusion policies, nil / empty
+    selectors, missing topology labels, affinity escape hatch, anti-affinity held by resident pods,
+    namespace / namespaceSelector rules, terminating pods."""
+    sel = lambda **kw: LabelSelector(match_labels=dict(kw))  # noqa: E731
+    web = lambda i, *o: BuildTestPod("web%d" % i, 300, 1 << 20, WithLabels({"app": "web", "tier": "fe"}), *o)  # noqa: E731
+
+    def tsc(skew, key, selector, **kw):
+        return TopologySpreadConstraint(max_skew=skew, topology_key=key, label_selector=selector, **kw)
+
+    res_web = BuildTestPod("r-web", 100, 1 << 20, WithLabels({"app": "web", "tier": "fe"}))
+    res_db = BuildTestPod("r-db", 100, 1 << 20, WithLabels({"app": "db"}))
+    res_db.pod_anti_affinity = [PodAffinityTerm(sel(app="cache"), ZONE)]            # existing anti-affinity vs cache pods
+    res_term = BuildTestPod("r-term", 100, 1 << 20, WithLabels({"app": "web", "tier": "fe"}))
+    res_term.terminating = True
+    res_other_ns = BuildTestPod("r-ns", 100, 1 << 20, WithNamespace("other"), WithLabels({"app": "web", "tier": "fe"}))
+    cluster = [
+        NodeInfo(_znode("c-a1", "za"), [res_web, res_web, res_term]),
+        NodeInfo(_znode("c-a2", "za"), [res_db]),
+        NodeInfo(_znode("c-b1", "zb"), [res_web, res_other_ns]),
+        NodeInfo(_znode("c-c1", "zc", labels={"pool": "x"}, taints=[Taint("dedicated", "x", "NoSchedule")]), []),
+        NodeInfo(Node_nolabel()),
+    ]
+    templates = [NodeInfo(_znode("t-a", "za")), NodeInfo(_znode("t-b", "zb", cpu=2000)), NodeInfo(_znode("t-d", "zd")),
+                 NodeInfo(_znode("t-x", "zc", labels={"pool": "x"}, taints=[Taint("dedicated", "x", "NoSchedule")])),
+                 NodeInfo(Node_nolabel("t-nolabel"))]
+    P = []
+    P.append(web(0))                                                                  # plain, but counted by others' selectors
+    p = web(1); p.topology_spread = [tsc(1, ZONE, sel(app="web"))]; P.append(p)
+    p = web(2); p.topology_spread = [tsc(2, ZONE, sel(app="web")), tsc(1, HOST, sel(tier="fe"))]; P.append(p)
+    p = web(3); p.topology_spread = [tsc(1, ZONE, sel(app="web"), min_domains=5)]; P.append(p)
+    p = web(4); p.topology_spread = [tsc(1, HOST, sel(app="web"), min_domains=2)]; P.append(p)
+    p = web(5); p.topology_spread = [tsc(1, ZONE, None)]; P.append(p)                # nil selector: matches nothing
+    p = web(6); p.topology_spread = [tsc(1, ZONE, LabelSelector())]; P.append(p)     # {} selector: counts 0, self matches
+    p = web(7); p.topology_spread = [tsc(1, ZONE, sel(app="web"), node_taints_policy="Honor")]; P.append(p)
+    p = web(8); p.node_selector = {"pool": "x"}; p.tolerations = [Toleration("dedicated", "Exists", "", "")]
+    p.topology_spread = [tsc(1, ZONE, sel(app="web"))]; P.append(p)                  # NodeAffinityPolicy Honor (default)
+    p = web(9); p.node_selector = {"pool": "x"}; p.tolerations = [Toleration("dedicated", "Exists", "", "")]
+    p.topology_spread = [tsc(1, ZONE, sel(app="web"), node_affinity_policy="Ignore")]; P.append(p)
+    p = web(10); p.topology_spread = [tsc(1, "rack", sel(app="web"))]; P.append(p)   # key no node carries
+    p = web(11); p.topology_spread = [tsc(3, ZONE, sel(app="web"), when_unsatisfiable="ScheduleAnyway"),
+                                      tsc(1, HOST, sel(app="web"), when_unsatisfiable="ScheduleAnyway")]; P.append(p)
+    cache = BuildTestPod("cache", 200, 1 << 20, WithLabels({"app": "cache"})); P.append(cache)   # blocked in zone za by r-db
+    p = BuildTestPod("selfaff", 200, 1 << 20, WithLabels({"app": "selfaff"}))
+    p.pod_affinity = [PodAffinityTerm(sel(app="selfaff"), ZONE)]; P.append(p)        # first-pod escape hatch
+    p = BuildTestPod("affweb", 200, 1 << 20, WithLabels({"app": "affweb"}))
+    p.pod_affinity = [PodAffinityTerm(sel(app="web"), ZONE)]; P.append(p)            # must land where web pods are
+    p = BuildTestPod("aff2", 200, 1 << 20, WithLabels({"app": "aff2"}))
+    p.pod_affinity = [PodAffinityTerm(sel(app="web"), ZONE), PodAffinityTerm(sel(tier="fe"), HOST)]; P.append(p)
+    p = BuildTestPod("affnone", 200, 1 << 20, WithLabels({"app": "affnone"}))
+    p.pod_affinity = [PodAffinityTerm(sel(app="nobody"), ZONE)]; P.append(p)         # nobody matches, pod does not match itself
+    p = BuildTestPod("anti-host", 200, 1 << 20, WithLabels({"app": "anti-host"}))
+    p.pod_anti_affinity = [PodAffinityTerm(sel(app="anti-host"), HOST)]; P.append(p)  # one per node
+    p = BuildTestPod("anti-web", 200, 1 << 20, WithLabels({"app": "anti-web"}))
+    p.pod_anti_affinity = [PodAffinityTerm(sel(app="web"), ZONE)]; P.append(p)        # zones holding web pods are closed
+    p = BuildTestPod("anti-ns", 200, 1 << 20, WithLabels({"app": "anti-ns"}))
+    p.pod_anti_affinity = [PodAffinityTerm(sel(app="web"), ZONE, namespaces=["other"])]; P.append(p)
+    p = BuildTestPod("anti-nssel", 200, 1 << 20, WithLabels({"app": "anti-nssel"}))
+    p.pod_anti_affinity = [PodAffinityTerm(sel(app="web"), ZONE, namespace_selector=sel(team="a"))]; P.append(p)
+    p = BuildTestPod("anti-allns", 200, 1 << 20, WithLabels({"app": "anti-allns"}))
+    p.pod_anti_affinity = [PodAffinityTerm(sel(app="web"), ZONE, namespace_selector=LabelSelector())]; P.append(p)
+    groups = [makePodEquivalenceGroup(q, n) for q, n in zip(P, [4, 5, 6, 3, 7, 3, 4, 5, 3, 3, 2, 3, 3, 4, 3, 3, 2, 6, 3, 3, 3, 3])]
+    assert len(groups) == len(P)
+    for nss in ([], [Namespace("other", {"team": "a"}), Namespace("default", {})]):
+        enc = encode(cluster, templates, groups, namespaces=nss)
+        _check_dense(eng, oracle, enc)
+        _check_estimate(eng, oracle, enc, np.full(enc.T, 20))
+        _check_estimate(eng, oracle, enc, np.full(enc.T, 3))
+        want = oracle.feasibility_groups(enc)
+        assert {8, 9, 10, 11}.issubset(set(want.ravel().tolist()))   # PTS missing label / skew, IPA affinity / anti-affinity
+
+
+def Node_nolabel(name="c-nolabel"):
+    n = BuildTestNode(name, 4000, 8 << 30)
+    n.allocatable["pods"] = 20
+    return n
