@@ -261,8 +261,16 @@ def main():
         return
 
     # ---- roofline of the dominant kernel (feasibility_kernel) -----------------------------------------
-    A = max(1, len(set(np.nonzero(enc.arrays["ps_req"][np.unique(enc.arrays["pend_spec"])].max(axis=0) > 0)[0].tolist())))
-    alg_bytes = Pl * (8 * A + 8) + T * (8 * A) + Pl * T // 8 + 4 * T   # pod planes + template planes + bit matrix + counts
+    # algorithmic bytes of feasibility_kernel: per pod W packed-rank words + 2 class ids,
+    # per template W words, the bit matrix, the fit histogram
+    req = enc.arrays["ps_req"][np.unique(enc.arrays["pend_spec"])]
+    bits = 0
+    for a in range(req.shape[1]):
+        dv = len(np.unique(req[:, a][req[:, a] > 0]))
+        if dv:
+            bits += int(dv).bit_length() + 1
+    Wd = max(1, (bits + 31) // 32)
+    alg_bytes = Pl * (4 * Wd + 8) + T * 4 * Wd + Pl * T // 8 + 4 * T
     peak, peak_src = _peak_hbm()
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

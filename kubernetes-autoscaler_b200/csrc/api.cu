@@ -286,6 +286,37 @@ static int do_load(Engine* e, const cae_objects* o) {
     if (used) e->act_dim[e->A++] = r;
   }
   const int A1 = std::max(e->A, 1);
+  // order-preserving rank encoding of the request / free-capacity operands (feas.cu)
+  std::vector<std::vector<int64_t>> rvals(e->A);
+  for (int a = 0; a < e->A; ++a) {
+    for (int s = 0; s < S; ++s) if (spec_pending[s] && o->ps_req[(size_t)s * R + e->act_dim[a]] > 0) rvals[a].push_back(o->ps_req[(size_t)s * R + e->act_dim[a]]);
+    std::sort(rvals[a].begin(), rvals[a].end());
+    rvals[a].erase(std::unique(rvals[a].begin(), rvals[a].end()), rvals[a].end());
+  }
+  int f_word[CAE_MAX_RES], f_shift[CAE_MAX_RES], f_bits[CAE_MAX_RES];
+  e->W = 0;
+  for (int w = 0; w < FEAS_MAX_W; ++w) e->feas_guard[w] = 0;
+  { int w = 0, shift = 0;
+    for (int a = 0; a < e->A; ++a) {
+      int bits = 1;
+      while ((1ll << bits) <= (long long)rvals[a].size()) ++bits;   // ranks 0..D need `bits` bits
+      bits += 1;                                                     // + guard bit
+      if (shift + bits > 32) { ++w; shift = 0; }
+      if (w >= FEAS_MAX_W || bits > 32) { set_error("resource request cardinality too large for the rank encoding"); return 1; }
+      f_word[a] = w; f_shift[a] = shift; f_bits[a] = bits;
+      e->feas_guard[w] |= 1u << (shift + bits - 1);
+      shift += bits;
+      e->W = w + 1;
+    } }
+  std::vector<uint32_t> spec_w((size_t)S * FEAS_MAX_W, 0), tmpl_w((size_t)std::max(e->W, 1) * std::max(T, 1), 0);
+  for (int s = 0; s < S; ++s) {
+    if (!spec_pending[s]) continue;
+    for (int a = 0; a < e->A; ++a) {
+      int64_t v = o->ps_req[(size_t)s * R + e->act_dim[a]];
+      uint32_t rank = v > 0 ? (uint32_t)(std::lower_bound(rvals[a].begin(), rvals[a].end(), v) - rvals[a].begin()) + 1 : 0;
+      spec_w[(size_t)s * FEAS_MAX_W + f_word[a]] |= rank << f_shift[a];
+    }
+  }
   std::vector<int64_t> free_all((size_t)R * T), free_act((size_t)A1 * T), cfree((size_t)A1 * std::max(N, 1));
   std::vector<int32_t> slots(T), cslots(std::max(N, 1));
   for (int row = 0; row < NT; ++row) {
@@ -298,6 +329,11 @@ static int do_load(Engine* e, const cae_objects* o) {
       for (int r = 0; r < R; ++r) free_all[(size_t)r * T + t] = o->node_alloc[(size_t)row * R + r] - reqd[r];
       for (int a = 0; a < e->A; ++a) free_act[(size_t)a * T + t] = free_all[(size_t)e->act_dim[a] * T + t];
       slots[t] = o->node_allowed_pods[row] - npods;
+      for (int a = 0; a < e->A; ++a) {
+        int64_t f = free_act[(size_t)a * T + t];
+        uint32_t rank = (uint32_t)(std::upper_bound(rvals[a].begin(), rvals[a].end(), f) - rvals[a].begin());
+        tmpl_w[(size_t)f_word[a] * T + t] |= (rank | (1u << (f_bits[a] - 1))) << f_shift[a];
+      }
     } else if (e->has_dynamic) {
       for (int a = 0; a < e->A; ++a) cfree[(size_t)a * N + row] = o->node_alloc[(size_t)row * R + e->act_dim[a]] - reqd[e->act_dim[a]];
       cslots[row] = o->node_allowed_pods[row] - npods;
@@ -305,12 +341,12 @@ static int do_load(Engine* e, const cae_objects* o) {
   }
   if (upload_mut(e, sclass, &e->d_sclass) || upload_mut(e, spec_sc, &e->d_spec_sc) || upload_mut(e, slots, &e->d_tmpl_slots) ||
       upload_mut(e, free_all, &e->d_tmpl_free_all) || upload_mut(e, free_act, &e->d_tmpl_free) || upload_mut(e, cfree, &e->d_c_free) ||
-      upload_mut(e, cslots, &e->d_c_slots) || upload_mut(e, pc_of, &e->d_pc_of) || upload_mut(e, spec_dc, &e->d_spec_dc))
+      upload_mut(e, cslots, &e->d_c_slots) || upload_mut(e, spec_w, &e->d_spec_w) || upload_mut(e, tmpl_w, &e->d_tmpl_w) || upload_mut(e, pc_of, &e->d_pc_of) || upload_mut(e, spec_dc, &e->d_spec_dc))
     return -1;
 
   if (dev_alloc(e, &e->d_pre_code, (size_t)e->SC * e->U) || dev_alloc(e, &e->d_pre_ok, (size_t)e->SC * std::max(e->Tw, 1)) ||
       dev_alloc(e, &e->d_post_code, (size_t)e->DC * std::max(T, 1), true) || dev_alloc(e, &e->d_post_ok, (size_t)e->DC * std::max(e->Tw, 1)) ||
-      dev_alloc(e, &e->d_pod_req, (size_t)A1 * std::max(e->Pl, 1)) || dev_alloc(e, &e->d_pod_sc, (size_t)std::max(e->Pl, 1)) ||
+      dev_alloc(e, &e->d_pod_w, (size_t)std::max(e->W, 1) * std::max(e->Pl, 1)) || dev_alloc(e, &e->d_pod_sc, (size_t)std::max(e->Pl, 1)) ||
       dev_alloc(e, &e->d_pod_dc, (size_t)std::max(e->Pl, 1)) || dev_alloc(e, &e->d_fit_bits, (size_t)std::max(T, 1) * std::max(e->Plw, 1)) ||
       dev_alloc(e, &e->d_fit_count, (size_t)std::max(T, 1), true) || dev_alloc(e, &e->d_group_reason, (size_t)std::max(T, 1) * std::max(e->E, 1)) ||
       dev_alloc(e, &e->d_counts2, (size_t)2 * std::max(T, 1), true) || dev_alloc(e, &e->d_sched, (size_t)std::max(T, 1) * std::max(e->E, 1), true) ||

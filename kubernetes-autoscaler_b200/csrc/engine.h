@@ -12,6 +12,8 @@
 
 namespace cae {
 
+constexpr int FEAS_MAX_W = 4;
+
 void set_error(const std::string& msg);
 
 #define CAE_CUDA(expr)                                                                        \
@@ -84,7 +86,11 @@ struct Engine {
   int32_t* d_spec_dc = nullptr;           // [num_podspecs] dynamic class (0 = none)
   uint8_t* d_post_code = nullptr;         // [DC][T] PTS / IPA reason on the empty template (0 = ok)
   uint32_t* d_post_ok = nullptr;          // [DC][Tw]
-  int64_t* d_pod_req = nullptr;           // [A][P] request planes of the pending pods; <=0 stored as INT64_MIN
+  int W = 0;                              // 32-bit words of the packed rank encoding (feas.cu)
+  uint32_t feas_guard[4] = {0, 0, 0, 0};  // guard-bit mask per word
+  uint32_t* d_spec_w = nullptr;           // [num_podspecs][FEAS_MAX_W] packed request ranks
+  uint32_t* d_pod_w = nullptr;            // [W][Pl] per pending pod
+  uint32_t* d_tmpl_w = nullptr;           // [W][T] packed free-capacity ranks + guard bits
   int32_t* d_pod_sc = nullptr;            // [P]
   int32_t* d_pod_dc = nullptr;            // [P]
   int64_t* d_tmpl_free = nullptr;         // [A][T] allocatable - DaemonSet requested

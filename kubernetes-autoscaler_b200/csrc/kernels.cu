@@ -2,11 +2,9 @@
 //
 //   class_matrix_kernel   (static class x universe node) -> reason/flag byte     [tables.cuh static_code]
 //   pack_ok_bits_kernel   byte matrix -> per-class template bit words
-//   expand_pods_kernel    podspec table -> per-pod SoA planes resident in HBM
-//   feasibility_kernel    K1: dense pods x templates Filter pass, warp-ballot bit matrix + counts
+//   (K1, the dense pods x templates pass, lives in feas.cu; K3, the pack, in pack.cu)
 //   group_reason_kernel   exemplar x template reasons (what SchedulablePodGroups asks)
 //   order_kernel          K0: DecreasingPodOrderer per template (float64 score, stable bitonic sort)
-//   pack_kernel           K3: BinpackingNodeEstimator.Estimate, one warp per template
 //   waste_kernel          K4: least-waste score per option
 //
 // Integer / bitset work only: no tensor cores.  Grid sizes are multiples of the SM
@@ -55,141 +53,6 @@ __global__ void port_conflict_kernel(DevObjects o, int num_port_lists, const int
     for (int q = 0; q < num_port_lists; ++q)
       if (pc_of[q] >= 0 && port_lists_conflict(o, pl, q)) m |= 1ull << pc_of[q];
   port_conf[pl] = m;
-}
-
-// per-pod SoA planes from the podspec table: the dense pass reads one row per pending pod
-__global__ void expand_pods_kernel(const int32_t* __restrict__ pend_spec, int p_begin, int Pl,
-                                   const int64_t* __restrict__ ps_req, const int32_t* __restrict__ spec_sc,
-                                   const int32_t* __restrict__ spec_dc, int A, const int* __restrict__ act_dim_dev,
-                                   int64_t* __restrict__ pod_req, int32_t* __restrict__ pod_sc,
-                                   int32_t* __restrict__ pod_dc) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= Pl) return;
-  int spec = pend_spec[p_begin + p];
-  for (int a = 0; a < A; ++a) {
-    int64_t v = ps_req[(size_t)spec * R + act_dim_dev[a]];
-    pod_req[(size_t)a * Pl + p] = v > 0 ? v : LLONG_MIN;  // fit.go:670-704: a resource is only checked when requested > 0
-  }
-  pod_sc[p] = spec_sc[spec];
-  pod_dc[p] = spec_dc[spec];
-}
-
-// ------------------------------------------------------------------------------------------------
-// K1: dense feasibility.  thread = pod (row in registers), template rows staged in smem and
-// broadcast, 32 templates per class-word, warp ballot = one output word (template-major bit matrix).
-// ------------------------------------------------------------------------------------------------
-constexpr int K1_THREADS = 256;
-constexpr int K1_TCHUNK = 128;  // templates per CTA
-constexpr int K1_WARPS = K1_THREADS / 32;
-constexpr int K1_PAD = K1_TCHUNK + 4;
-
-template <int A, bool REASONS>
-__global__ void __launch_bounds__(K1_THREADS)
-feasibility_kernel(int Pl, int Plw, int T, int Tw, int N, int U,
-                   const int64_t* __restrict__ pod_req, const int32_t* __restrict__ pod_sc,
-                   const int32_t* __restrict__ pod_dc, const int64_t* __restrict__ tmpl_free,
-                   const int32_t* __restrict__ tmpl_slots,
-                   const uint32_t* __restrict__ pre_ok, const uint32_t* __restrict__ post_ok,
-                   const uint8_t* __restrict__ pre_code, const uint8_t* __restrict__ post_code,
-                   uint32_t* __restrict__ fit_bits, int32_t* __restrict__ fit_count,
-                   uint8_t* __restrict__ reasons) {
-  __shared__ int64_t s_free[A > 0 ? A : 1][K1_TCHUNK];
-  __shared__ uint32_t s_out[K1_WARPS][K1_PAD];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int p = blockIdx.x * K1_THREADS + tid;
-  const int t0 = blockIdx.y * K1_TCHUNK;
-  const int tn = min(K1_TCHUNK, T - t0);
-
-  for (int i = tid; i < A * K1_TCHUNK; i += K1_THREADS) {
-    int a = i / K1_TCHUNK, j = i % K1_TCHUNK;
-    s_free[a][j] = (j < tn) ? tmpl_free[(size_t)a * T + t0 + j] : LLONG_MIN;
-  }
-  const bool valid = p < Pl;
-  int64_t req[A > 0 ? A : 1];
-#pragma unroll
-  for (int a = 0; a < A; ++a) req[a] = valid ? pod_req[(size_t)a * Pl + p] : LLONG_MAX;
-  const int sc = valid ? pod_sc[p] : 0;
-  const int dc = valid ? pod_dc[p] : 0;
-  __syncthreads();
-
-  for (int tw = 0; tw < K1_TCHUNK / 32; ++tw) {
-    const int wglob = t0 / 32 + tw;
-    if (wglob >= Tw) {
-      s_out[warp][tw * 32 + lane] = 0;
-      continue;
-    }
-    uint32_t w = valid ? (pre_ok[(size_t)sc * Tw + wglob] & post_ok[(size_t)dc * Tw + wglob]) : 0u;
-    uint32_t mine = 0;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int tl = tw * 32 + j;
-      bool fail = false;
-#pragma unroll
-      for (int a = 0; a < A; ++a) fail |= req[a] > s_free[a][tl];
-      const bool fit = ((w >> j) & 1u) && !fail;
-      const uint32_t b = __ballot_sync(0xffffffffu, fit);
-      if (lane == j) mine = b;
-      if (REASONS) {
-        const int t = t0 + tl;
-        if (valid && t < T) {
-          // first failing plugin in Filter order: static plugins, NodeResourcesFit, then PTS / IPA
-          uint8_t r = pre_code[(size_t)sc * U + N + t] & 0x0F;
-          if (r == 0) r = (fail || tmpl_slots[t] < 1) ? CAE_R_FIT : post_code[(size_t)dc * T + t];
-          reasons[(size_t)t * Pl + p] = r;
-        }
-      }
-    }
-    s_out[warp][tw * 32 + lane] = mine;  // word for template t0 + tw*32 + lane, pods of this warp
-  }
-  __syncthreads();
-  // flush: 8 consecutive words (one 32 B sector) per template row; popcount -> per-template counts
-  const int pw0 = blockIdx.x * K1_WARPS;
-  for (int i = tid; i < K1_TCHUNK * K1_WARPS; i += K1_THREADS) {
-    const int tl = i / K1_WARPS, wv = i % K1_WARPS;
-    const int t = t0 + tl;
-    uint32_t word = (t < T) ? s_out[wv][tl] : 0u;
-    int c = __popc(word);
-    c += __shfl_xor_sync(0xffffffffu, c, 1);
-    c += __shfl_xor_sync(0xffffffffu, c, 2);
-    c += __shfl_xor_sync(0xffffffffu, c, 4);
-    if (t < T) {
-      if (pw0 + wv < Plw && fit_bits) fit_bits[(size_t)t * Plw + pw0 + wv] = word;
-      if (wv == 0 && c) atomicAdd(&fit_count[t], c);
-    }
-  }
-}
-
-template <int A>
-static int launch_feas_a(Engine* e, bool want_reasons) {
-  dim3 grid((e->Pl + K1_THREADS - 1) / K1_THREADS, (e->T + K1_TCHUNK - 1) / K1_TCHUNK);
-  if (grid.x == 0 || grid.y == 0) return 0;
-  if (want_reasons)
-    feasibility_kernel<A, true><<<grid, K1_THREADS, 0, e->stream>>>(
-        e->Pl, e->Plw, e->T, e->Tw, e->N, e->U, e->d_pod_req, e->d_pod_sc, e->d_pod_dc, e->d_tmpl_free,
-        e->d_tmpl_slots, e->d_pre_ok, e->d_post_ok, e->d_pre_code, e->d_post_code, e->d_fit_bits, e->d_fit_count, e->d_reasons);
-  else
-    feasibility_kernel<A, false><<<grid, K1_THREADS, 0, e->stream>>>(
-        e->Pl, e->Plw, e->T, e->Tw, e->N, e->U, e->d_pod_req, e->d_pod_sc, e->d_pod_dc, e->d_tmpl_free,
-        e->d_tmpl_slots, e->d_pre_ok, e->d_post_ok, e->d_pre_code, e->d_post_code, e->d_fit_bits, e->d_fit_count, e->d_reasons);
-  e->stats.kernel_launches++;
-  return 0;
-}
-
-int launch_feasibility(Engine* e, bool want_reasons) {
-  CAE_CUDA(cudaMemsetAsync(e->d_fit_count, 0, sizeof(int32_t) * e->T, e->stream));
-  switch (e->A) {
-    case 0: launch_feas_a<0>(e, want_reasons); break;
-    case 1: launch_feas_a<1>(e, want_reasons); break;
-    case 2: launch_feas_a<2>(e, want_reasons); break;
-    case 3: launch_feas_a<3>(e, want_reasons); break;
-    case 4: launch_feas_a<4>(e, want_reasons); break;
-    case 5: launch_feas_a<5>(e, want_reasons); break;
-    case 6: launch_feas_a<6>(e, want_reasons); break;
-    case 7: launch_feas_a<7>(e, want_reasons); break;
-    default: launch_feas_a<8>(e, want_reasons); break;
-  }
-  CAE_KERNEL_OK();
-  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -257,16 +120,6 @@ int launch_post_bits(Engine* e) {
 
 int launch_port_conflicts(Engine* e, int num_port_lists) {
   port_conflict_kernel<<<(num_port_lists + 63) / 64, 64, 0, e->stream>>>(e->dobj, num_port_lists, e->d_pc_of, e->d_port_conf);
-  e->stats.kernel_launches++;
-  CAE_KERNEL_OK();
-  return 0;
-}
-
-int launch_expand_pods(Engine* e) {
-  if (e->Pl == 0) return 0;
-  expand_pods_kernel<<<(e->Pl + 255) / 256, 256, 0, e->stream>>>(e->dobj.pend_spec, e->p_begin, e->Pl, e->dobj.ps_req,
-                                                                   e->d_spec_sc, e->d_spec_dc, e->A, e->d_act_dim,
-                                                                   e->d_pod_req, e->d_pod_sc, e->d_pod_dc);
   e->stats.kernel_launches++;
   CAE_KERNEL_OK();
   return 0;

@@ -46,6 +46,22 @@ class PinnedArray:
             pass
 
 
+def shard_pods(P: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Block partition of the pending pods for the dense pass; shard starts are multiples of 32 so the
+    template-major bit rows of the ranks concatenate word by word (must match do_load in csrc/api.cu)."""
+    b = (P * rank // world_size) // 32 * 32
+    e = P * (rank + 1) // world_size
+    if rank + 1 < world_size:
+        e = e // 32 * 32
+    return b, e
+
+
+def shard_templates(T: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Block partition of the templates for the pack: rows of other ranks stay zero, so a sum
+    all-reduce of node_count|pod_count assembles the result."""
+    return T * rank // world_size, T * (rank + 1) // world_size
+
+
 class Engine:
     def __init__(self, device: int = 0, rank: int = 0, world_size: int = 1, want_reasons: bool = False) -> None:
         self.lib = capi.load_engine_lib()
@@ -97,16 +113,10 @@ class Engine:
 
     # ---- shards -------------------------------------------------------------------------------
     def pod_shard(self, P: int) -> Tuple[int, int]:
-        W, r = self.world_size, self.rank
-        b = (P * r // W) // 32 * 32
-        e = P * (r + 1) // W
-        if r + 1 < W:
-            e = e // 32 * 32
-        return b, e
+        return shard_pods(P, self.rank, self.world_size)
 
     def template_shard(self, T: int) -> Tuple[int, int]:
-        W, r = self.world_size, self.rank
-        return T * r // W, T * (r + 1) // W
+        return shard_templates(T, self.rank, self.world_size)
 
     # ---- API ------------------------------------------------------------------------------------
     def load(self, enc: EncodedObjects) -> None:
