@@ -80,6 +80,15 @@ def _worker_run(job):
     return ev, time.perf_counter() - t0
 
 
+def _worker_decide(job):
+    tb, te, cap = job
+    enc = _W["enc"]
+    caps = np.full(enc.T, cap, np.int32)
+    t0 = time.perf_counter()
+    _W["oracle"].estimate_all(enc, caps, t_range=(tb, te))
+    return time.perf_counter() - t0
+
+
 def _worker_pid(_):
     time.sleep(0.02)
     return os.getpid()
@@ -112,6 +121,8 @@ def main():
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--pods", type=int, default=None)
     ap.add_argument("--templates", type=int, default=None)
+    ap.add_argument("--decision", action="store_true", help="reference arm: time full scale-up decisions (oracle) instead")
+    ap.add_argument("--no-decision", action="store_true", help="engine arm: skip the secondary decision-latency figure")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -136,6 +147,18 @@ def main():
         P = P1
         # bounded sample per step: all pods x a template slice (~0.2 s of work per core)
         t_slice = min(T, 8 * cores)
+        if args.decision:
+            # metric 2: SchedulablePodGroups + Estimate per template, one template per job
+            with mp.get_context("fork").Pool(cores, initializer=_worker_init, initargs=(args.config, P1, T)) as pool:
+                _wait_workers(pool, cores)
+                k = min(T, 2 * cores)
+                t0 = time.perf_counter()
+                per = pool.map(_worker_decide, [(t, t + 1, 1000) for t in range(k)], chunksize=1)
+                wall = time.perf_counter() - t0
+            print(json.dumps({"impl": "reference", "decision": True, "templates_timed": k, "wall_s": wall,
+                              "cpu_seconds_per_template": float(np.mean(per)), "cores": cores,
+                              "extrapolated_s_all_templates": wall * T / k, "kind": "port"}))
+            return
         with mp.get_context("fork").Pool(cores, initializer=_worker_init, initargs=(args.config, P1, T)) as pool:
             _wait_workers(pool, cores)
             for _ in range(2):
@@ -289,6 +312,32 @@ def main():
     except Exception as ex:  # the bench line must still be printed
         cpu["sample"] = "failed: %r" % (ex,)
 
+    # ---- metric 2: scale-up decision latency @ 100k pods x 5k templates (C3), one GPU ---------------------
+    decision = None
+    if world == 1 and not args.no_decision:
+        try:
+            enc3 = synth.generate(3)
+            caps = np.full(enc3.T, 1000, np.int32)
+            ms = []
+            for i in range(4):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                eng.load(enc3)                                                 # intern + H2D + class / counter tables
+                nc, pc, _, _ = eng.estimate_all(caps, want_sched=False, copy=False)  # exemplar feasibility, order, pack
+                mask, _ = eng.expander_best([0, 1, 2], nc, pc)                 # least-waste, most-pods, least-nodes
+                if i:
+                    ms.append(1e3 * (time.perf_counter() - t0))
+            st = eng.stats()
+            decision = {"workload": synth.CONFIGS[3].name + ", node cap 1000 per template", "ms": float(np.median(ms)),
+                        "estimate_device_ms": st.estimate_ms, "nodes_total": int(nc.sum()), "pods_scheduled_total": int(pc.sum()),
+                        "options_surviving_chain": int(mask.sum()), "cpu_baseline": None}
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--decision", "--config", "3"],
+                                 capture_output=True, text=True, timeout=900,
+                                 env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+            decision["cpu_baseline"] = json.loads(out.stdout.strip().splitlines()[-1])
+        except Exception as ex:
+            decision = {"error": repr(ex)}
+
     print(json.dumps({
         "metric": metric, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
@@ -298,7 +347,7 @@ def main():
         "kernel_ms": kern_ms, "clocks": _clocks_summary(samples),
         "e2e": {"value": (P1 * world) * T / (e2e_step * 1e-3), "unit": "evals/s", "ms_per_step": e2e_step,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}))
+        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "decision_latency": decision}))
     if dist is not None:
         dist.destroy_process_group()
 

@@ -297,7 +297,8 @@ int32_t cae_estimate_all(cae_engine* e, const int32_t* max_nodes, int32_t* node_
 enum cae_expander { CAE_EXP_LEAST_WASTE = 0, CAE_EXP_MOST_PODS = 1, CAE_EXP_LEAST_NODES = 2 };
 int32_t cae_expander_best(cae_engine* e, const int32_t* chain, int32_t chain_len,
                           const int32_t* node_count, const int32_t* pod_count,
-                          const int32_t* sched_count, /* [T][E] */
+                          const int32_t* sched_count, /* [T][E]; NULL = use the device-resident result of
+                                                         the last cae_estimate_all (single shard) */
                           uint8_t* best_mask /* [T] 1 = in the surviving option set */,
                           double* waste_score /* [T], may be NULL */);
 

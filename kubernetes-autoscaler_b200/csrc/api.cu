@@ -188,7 +188,7 @@ static int build_dynamic(Engine* e, const cae_objects* o, const std::vector<uint
       dev_alloc(e, &d.dc_aff_self, (size_t)d.DC) || dev_alloc(e, &d.dc_active, (size_t)d.DC) || dev_alloc(e, &d.elig, Q * e->U) ||
       dev_alloc(e, &d.base_cnt, pool, true) || dev_alloc(e, &d.base_pres, pool, true) || dev_alloc(e, &d.base_tot, Q, true) ||
       dev_alloc(e, &d.ds_w, Q * std::max(T, 1)) || dev_alloc(e, &d.st_min1, Q) || dev_alloc(e, &d.st_arg1, Q) ||
-      dev_alloc(e, &d.st_min2, Q) || dev_alloc(e, &d.st_ndom, Q) || dev_alloc(e, &d.q_nfeed, Q, true) ||
+      dev_alloc(e, &d.st_min2, Q) || dev_alloc(e, &d.st_ndom, Q) || dev_alloc(e, &d.st_nmin, Q) || dev_alloc(e, &d.q_nfeed, Q, true) ||
       dev_alloc(e, &d.group_feeds, (size_t)std::max(e->E, 1), true))
     return -1;
   e->h_dc_of_spec_valid = true;
@@ -538,24 +538,36 @@ int32_t cae_expander_best(cae_engine* h, const int32_t* chain, int32_t chain_len
   cudaSetDevice(e->cfg.device);
   const int T = e->T, E = e->E;
   if (T == 0) return 0;
-  // scores on the device from the caller's (all-reduced) option table
+  // scores on the device: from the caller's (all-reduced) option table, or — sched_count == NULL —
+  // straight from the device-resident result of the last cae_estimate_all (single-shard fast path)
   int32_t *d_nc = nullptr, *d_sched = nullptr;
   double* d_waste = nullptr;
-  CAE_CUDA(cudaMalloc(&d_nc, sizeof(int32_t) * T));
-  CAE_CUDA(cudaMalloc(&d_sched, sizeof(int32_t) * (size_t)T * std::max(E, 1)));
-  CAE_CUDA(cudaMalloc(&d_waste, sizeof(double) * T));
-  CAE_CUDA(cudaMemcpyAsync(d_nc, node_count, sizeof(int32_t) * T, cudaMemcpyHostToDevice, e->stream));
-  if (E) CAE_CUDA(cudaMemcpyAsync(d_sched, sched_count, sizeof(int32_t) * (size_t)T * E, cudaMemcpyHostToDevice, e->stream));
-  cudaEventRecord(e->ev0, e->stream);
-  if (cae::launch_expander(e, chain, chain_len, d_nc, nullptr, d_sched, nullptr, d_waste)) return -1;
-  cudaEventRecord(e->ev1, e->stream);
   std::vector<double> waste(T);
-  CAE_CUDA(cudaMemcpyAsync(waste.data(), d_waste, sizeof(double) * T, cudaMemcpyDeviceToHost, e->stream));
-  CAE_CUDA(cudaStreamSynchronize(e->stream));
+  if (sched_count == nullptr) {
+    void* pw = nullptr;
+    if (e->scratch.alloc(&pw, nullptr, sizeof(double) * T)) return -1;
+    d_waste = static_cast<double*>(pw);
+    cudaEventRecord(e->ev0, e->stream);
+    if (cae::launch_expander(e, chain, chain_len, e->d_counts2, nullptr, e->d_sched, nullptr, d_waste)) return -1;
+    cudaEventRecord(e->ev1, e->stream);
+    CAE_CUDA(cudaMemcpyAsync(waste.data(), d_waste, sizeof(double) * T, cudaMemcpyDeviceToHost, e->stream));
+    CAE_CUDA(cudaStreamSynchronize(e->stream));
+  } else {
+    CAE_CUDA(cudaMalloc(&d_nc, sizeof(int32_t) * T));
+    CAE_CUDA(cudaMalloc(&d_sched, sizeof(int32_t) * (size_t)T * std::max(E, 1)));
+    CAE_CUDA(cudaMalloc(&d_waste, sizeof(double) * T));
+    CAE_CUDA(cudaMemcpyAsync(d_nc, node_count, sizeof(int32_t) * T, cudaMemcpyHostToDevice, e->stream));
+    if (E) CAE_CUDA(cudaMemcpyAsync(d_sched, sched_count, sizeof(int32_t) * (size_t)T * E, cudaMemcpyHostToDevice, e->stream));
+    cudaEventRecord(e->ev0, e->stream);
+    if (cae::launch_expander(e, chain, chain_len, d_nc, nullptr, d_sched, nullptr, d_waste)) return -1;
+    cudaEventRecord(e->ev1, e->stream);
+    CAE_CUDA(cudaMemcpyAsync(waste.data(), d_waste, sizeof(double) * T, cudaMemcpyDeviceToHost, e->stream));
+    CAE_CUDA(cudaStreamSynchronize(e->stream));
+    cudaFree(d_nc); cudaFree(d_sched); cudaFree(d_waste);
+  }
   float ms = 0;
   cudaEventElapsedTime(&ms, e->ev0, e->ev1);
   e->stats.expander_ms = ms;
-  cudaFree(d_nc); cudaFree(d_sched); cudaFree(d_waste);
   if (waste_score) std::copy(waste.begin(), waste.end(), waste_score);
   // The filter chain itself is a sequential scan over <= T options in option order
   // (expander/factory/chain.go:36-45) — it keeps the reference's order-dependent quirks

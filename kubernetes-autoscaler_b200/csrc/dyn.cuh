@@ -57,6 +57,7 @@ struct DynTables {
   int32_t* st_arg1 = nullptr;       // [Q] a domain attaining it
   int32_t* st_min2 = nullptr;       // [Q] min over the other present domains
   int32_t* st_ndom = nullptr;       // [Q] present cluster domains
+  int32_t* st_nmin = nullptr;       // [Q] present cluster domains attaining st_min1
   int32_t* q_nfeed = nullptr;       // [Q] pending groups whose pods have non-zero weight
   uint8_t* group_feeds = nullptr;   // [E] pods of the group count for a counter of ANOTHER group
 };

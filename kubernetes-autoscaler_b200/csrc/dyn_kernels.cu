@@ -134,7 +134,9 @@ __global__ void dyn_stats_kernel(DevObjects o, DynTables d) {
     if (c < m1) { m2 = m1; m1 = c; a1 = i; }
     else if (c < m2) m2 = c;
   }
-  d.st_min1[q] = m1; d.st_arg1[q] = a1; d.st_min2[q] = m2; d.st_ndom[q] = nd;
+  int nm = 0;
+  for (int i = 0; i < n; ++i) if (d.base_pres[off + i] > 0 && d.base_cnt[off + i] == m1) ++nm;
+  d.st_min1[q] = m1; d.st_arg1[q] = a1; d.st_min2[q] = m2; d.st_ndom[q] = nd; d.st_nmin[q] = nm;
 }
 
 __global__ void dyn_feed_kernel(DevObjects o, DynTables d, int E, const int32_t* __restrict__ spec_dc,

@@ -115,6 +115,7 @@ struct Engine {
   // pack scratch
   void* d_pack_scratch = nullptr;
   size_t pack_scratch_bytes = 0;
+  size_t pack_layout_sig = 0;
   int32_t* d_work_counter = nullptr;
   // host copies needed by host-side steps
   std::vector<int32_t> h_group_off, h_pend_spec;

@@ -66,7 +66,7 @@ struct WarpDyn {
   int nq;
   int qid[DYN_MAX_Q], kind[DYN_MAX_Q], k[DYN_MAX_Q], host[DYN_MAX_Q], Dc[DYN_MAX_Q], tslot[DYN_MAX_Q];
   int wown[DYN_MAX_Q], self[DYN_MAX_Q], maxskew[DYN_MAX_Q], mindom[DYN_MAX_Q], elig_new[DYN_MAX_Q], dsw[DYN_MAX_Q];
-  int minv[DYN_MAX_Q], nmin[DYN_MAX_Q], ndom[DYN_MAX_Q], tot[DYN_MAX_Q];
+  int minv[DYN_MAX_Q], nmin[DYN_MAX_Q], ndom[DYN_MAX_Q], tot[DYN_MAX_Q], boff[DYN_MAX_Q];
   int aff_self;
 };
 
@@ -82,16 +82,18 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
   const int N = p.N, NT = p.N + p.T;
   const int Neff = p.has_dyn ? N : 0;  // cluster nodes carry run state only when a fallback can reach them
   const int X = Neff + p.cap;
-  int64_t* nfree = reinterpret_cast<int64_t*>(slab);                                  // [A][X]
+  int32_t* hdr = reinterpret_cast<int32_t*>(slab);  // stamp / version counters survive across launches
+  int64_t* nfree = reinterpret_cast<int64_t*>(slab + 16);                             // [A][X]
   unsigned long long* nports = reinterpret_cast<unsigned long long*>(nfree + (size_t)(A > 0 ? A : 1) * X);  // [X]
   int32_t* nslots = reinterpret_cast<int32_t*>(nports + X);                           // [X]
   int32_t* kbuf = nslots + X;                                                         // [X] capacities of the current pass
   int32_t* stamp = kbuf + X;                                                          // [X] "failed at stamp"
   int32_t* wcnt = stamp + X;                                                          // [DYN_MAX_Q][dstride]
   int32_t* wpres = wcnt + (size_t)DYN_MAX_Q * p.dstride;                              // [DYN_MAX_Q][dstride]
-  int32_t* logbuf = wpres + (size_t)DYN_MAX_Q * p.dstride;                            // [log_cap][3]
+  int32_t* wver = wpres + (size_t)DYN_MAX_Q * p.dstride;                              // [DYN_MAX_Q][dstride] slot version
+  int32_t* logbuf = wver + (size_t)DYN_MAX_Q * p.dstride;                             // [log_cap][3]
   uint8_t* nsched = reinterpret_cast<uint8_t*>(logbuf + (size_t)p.log_cap * 3);       // [X]
-  int stamp_ctr = 1;
+  int stamp_ctr = hdr[0] + 1, gver_ctr = hdr[1] + 1;
 
   for (;;) {
     int t = 0;
@@ -283,6 +285,8 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
         // ======================= dynamic group: per-pod loop on incremental counters ===============
         const bool host_spread = o.ps_hostname_spread[spec] != 0;
         int cur_stamp = ++stamp_ctr;
+        const int gver = ++gver_ctr;      // version of this group's working counters (lazy copy-on-write)
+        const int n_new_start = n_new;
         int fb_fail_stamp = -1, fb_mark = 0;
         // ---- describe the group's counters ----
         __syncwarp();
@@ -300,6 +304,8 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
             wd.elig_new[nq] = d.elig[(size_t)q * p.U + col_new];
             wd.dsw[nq] = d.ds_w[(size_t)q * p.T + t];
             wd.tot[nq] = d.base_tot[q];
+            wd.boff[nq] = d.q_base_off[q];
+            wd.minv[nq] = d.st_min1[q]; wd.nmin[nq] = d.st_nmin[q]; wd.ndom[nq] = d.st_ndom[q];
             ++nq;
           }
           wd.nq = nq;
@@ -307,62 +313,95 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
         }
         __syncwarp();
         const int nq = wd.nq;
-        // ---- seed the working counters: cluster base + nodes added so far ----
-        bool need_log = false;
-        for (int q = 0; q < nq; ++q) {
-          const int qid = wd.qid[q], off = d.q_base_off[qid], Dc = wd.Dc[q];
-          int32_t* wc = wcnt + (size_t)q * p.dstride;
-          int32_t* wp = wpres + (size_t)q * p.dstride;
-          for (int i = lane; i < Dc; i += 32) { wc[i] = d.base_cnt[off + i]; wp[i] = d.base_pres[off + i]; }
-          const int extra = 1 + (wd.host[q] ? n_new : 0);
-          const int en = wd.elig_new[q], dsw = wd.dsw[q];
-          for (int i = lane; i < extra; i += 32) {
-            int c = 0, pr = 0;
-            if (i >= 1 && en) { c = dsw; pr = 1; }  // fresh hostname domain of an added node
-            wc[Dc + i] = c; wp[Dc + i] = pr;
-          }
-          __syncwarp();
-          if (lane == 0 && en && n_new > 0) {
-            if (wd.host[q]) wd.tot[q] += n_new * dsw;
-            else if (wd.tslot[q] >= 0) { wc[wd.tslot[q]] += n_new * dsw; wp[wd.tslot[q]] += n_new; wd.tot[q] += n_new * dsw; }
-          }
-          if (d.q_nfeed[qid] - (wd.wown[q] > 0 ? 1 : 0) > 0) need_log = true;
-        }
-        __syncwarp();
-        if (need_log && log_n > 0) {  // pods other groups placed earlier in this run
-          for (int q = 0; q < nq; ++q) {
-            const int qid = wd.qid[q];
-            int32_t* wc = wcnt + (size_t)q * p.dstride;
-            int add = 0;
-            for (int i = lane; i < min(log_n, p.log_cap); i += 32) {
-              const int x = logbuf[i * 3], w = d.wmat[(size_t)qid * d.S + logbuf[i * 3 + 1]];
-              if (w == 0 || !elig_of(q, x)) continue;
-              const int sl = slot_of(q, x);
-              if (sl < 0) continue;
-              atomicAdd(&wc[sl], w * logbuf[i * 3 + 2]);
-              add += w * logbuf[i * 3 + 2];
-            }
-            add = wsum(add);
-            if (lane == 0) wd.tot[q] += add;
-          }
-          __syncwarp();
-        }
+        // Working counters are copy-on-write over the cluster base counts: a slot is valid only when its
+        // version equals this group's, otherwise it reads as its default (base count for cluster domains,
+        // DaemonSet weight for the fresh hostname domain of an added node, 0 for a template-only value).
+        auto rd_cnt = [&](int q, int sl) -> int {
+          const size_t o2 = (size_t)q * p.dstride + sl;
+          if (wver[o2] == gver) return wcnt[o2];
+          const int Dc = wd.Dc[q];
+          return sl < Dc ? d.base_cnt[wd.boff[q] + sl] : (sl == Dc ? 0 : (wd.elig_new[q] ? wd.dsw[q] : 0));
+        };
+        auto rd_pres = [&](int q, int sl) -> int {
+          const size_t o2 = (size_t)q * p.dstride + sl;
+          if (wver[o2] == gver) return wpres[o2];
+          const int Dc = wd.Dc[q];
+          return sl < Dc ? d.base_pres[wd.boff[q] + sl] : (sl == Dc ? 0 : (wd.elig_new[q] ? 1 : 0));
+        };
+        auto wr = [&](int q, int sl, int c, int pr) {  // single lane
+          const size_t o2 = (size_t)q * p.dstride + sl;
+          wcnt[o2] = c; wpres[o2] = pr; wver[o2] = gver;
+        };
         auto recompute = [&](int q) {  // min / #domains over the present domains of a spread counter
-          const int32_t* wc = wcnt + (size_t)q * p.dstride;
-          const int32_t* wp = wpres + (size_t)q * p.dstride;
           const int len = wd.Dc[q] + 1 + (wd.host[q] ? n_new : 0);
           int mn = INT_MAX, nd = 0;
-          for (int i = lane; i < len; i += 32) if (wp[i] > 0) { mn = min(mn, wc[i]); ++nd; }
+          for (int i = lane; i < len; i += 32) if (rd_pres(q, i) > 0) { mn = min(mn, rd_cnt(q, i)); ++nd; }
           mn = wmin(mn);
           nd = wsum(nd);
           int nm = 0;
-          for (int i = lane; i < len; i += 32) if (wp[i] > 0 && wc[i] == mn) ++nm;
+          for (int i = lane; i < len; i += 32) if (rd_pres(q, i) > 0 && rd_cnt(q, i) == mn) ++nm;
           nm = wsum(nm);
           __syncwarp();
           if (lane == 0) { wd.minv[q] = mn; wd.nmin[q] = nm; wd.ndom[q] = nd; }
           __syncwarp();
         };
-        for (int q = 0; q < nq; ++q) if (wd.kind[q] == Q_PTS) recompute(q);
+        // ---- seed: nodes added so far (O(1) per counter), then the run's placement log if other groups feed us ----
+        bool need_log = false;
+        for (int q = 0; q < nq; ++q) {
+          bool full = false;
+          if (wd.elig_new[q] && n_new > 0) {
+            const int dsw = wd.dsw[q];
+            if (wd.host[q]) {  // n_new fresh hostname domains, each holding the DaemonSet weight
+              if (lane == 0) {
+                wd.tot[q] += n_new * dsw;
+                if (wd.kind[q] == Q_PTS) {
+                  wd.ndom[q] += n_new;
+                  if (dsw < wd.minv[q]) { wd.minv[q] = dsw; wd.nmin[q] = n_new; }
+                  else if (dsw == wd.minv[q]) wd.nmin[q] += n_new;
+                }
+              }
+            } else if (wd.tslot[q] >= 0) {  // all added nodes share the template's value of this key
+              const int sl = wd.tslot[q];
+              const int c0 = rd_cnt(q, sl), p0 = rd_pres(q, sl), c1 = c0 + n_new * dsw;
+              __syncwarp();
+              if (lane == 0) {
+                wr(q, sl, c1, p0 + n_new);
+                wd.tot[q] += n_new * dsw;
+                if (wd.kind[q] == Q_PTS && p0 == 0) {
+                  wd.ndom[q] += 1;
+                  if (c1 < wd.minv[q]) { wd.minv[q] = c1; wd.nmin[q] = 1; }
+                  else if (c1 == wd.minv[q]) wd.nmin[q] += 1;
+                }
+              }
+              if (wd.kind[q] == Q_PTS && p0 > 0 && dsw > 0) full = true;
+            }
+          }
+          __syncwarp();
+          if (d.q_nfeed[wd.qid[q]] - (wd.wown[q] > 0 ? 1 : 0) > 0) need_log = true;
+          if (full) recompute(q);
+        }
+        __syncwarp();
+        if (need_log && log_n > 0) {  // pods other groups placed earlier in this run (rare: serial on lane 0)
+          for (int q = 0; q < nq; ++q) {
+            const int qid = wd.qid[q];
+            bool touched = false;
+            if (lane == 0) {
+              for (int i = 0; i < min(log_n, p.log_cap); ++i) {
+                const int x = logbuf[i * 3], w = d.wmat[(size_t)qid * d.S + logbuf[i * 3 + 1]];
+                if (w == 0 || !elig_of(q, x)) continue;
+                const int sl = slot_of(q, x);
+                if (sl < 0) continue;
+                wr(q, sl, rd_cnt(q, sl) + w * logbuf[i * 3 + 2], rd_pres(q, sl));
+                wd.tot[q] += w * logbuf[i * 3 + 2];
+                touched = true;
+              }
+            }
+            touched = __shfl_sync(0xffffffffu, touched, 0);
+            __syncwarp();
+            if (touched && wd.kind[q] == Q_PTS) recompute(q);
+          }
+          __syncwarp();
+        }
 
         auto ensure_cluster = [&]() {  // run state of the cluster nodes, needed once a fallback can place onto them
           if (cl_init) return;
@@ -372,7 +411,6 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
             nslots[x] = p.c_slots[x];
             nports[x] = 0ull;
             nsched[x] = 0;
-            stamp[x] = 0;
           }
           cl_init = true;
           __syncwarp();
@@ -392,7 +430,7 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
           for (int q = 0; q < nq; ++q) {
             const int kind = wd.kind[q];
             const int sl = slot_of(q, x);
-            const int c = sl >= 0 ? wcnt[(size_t)q * p.dstride + sl] : 0;
+            const int c = sl >= 0 ? rd_cnt(q, sl) : 0;
             if (kind == Q_PTS) {  // podtopologyspread/filtering.go:314-359
               if (sl < 0) return CAE_R_PTS_MISSING_LABEL;
               const long long minm = wd.ndom[q] < wd.mindom[q] ? 0 : wd.minv[q];
@@ -431,10 +469,9 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
             if (w == 0 || !elig_of(q, x)) continue;
             const int sl = slot_of(q, x);
             if (sl < 0) continue;
-            int32_t* wc = wcnt + (size_t)q * p.dstride;
-            const int old = wc[sl];
+            const int old = rd_cnt(q, sl), pr = rd_pres(q, sl);
             __syncwarp();
-            if (lane == 0) { wc[sl] = old + w; wd.tot[q] += w; }
+            if (lane == 0) { wr(q, sl, old + w, pr); wd.tot[q] += w; }
             if (wd.kind[q] == Q_PTS) {
               if (old == wd.minv[q]) {
                 const int nm = wd.nmin[q] - 1;
@@ -466,31 +503,51 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
           n_new = j + 1;
           bool bump = false;
           for (int q = 0; q < nq; ++q) {
-            int32_t* wc = wcnt + (size_t)q * p.dstride;
-            int32_t* wp = wpres + (size_t)q * p.dstride;
             const int en = wd.elig_new[q], dsw = wd.dsw[q];
             const int sl = slot_of(q, x);
-            if (wd.host[q]) {  // a brand-new hostname domain
-              if (lane == 0) { wc[sl] = en ? dsw : 0; wp[sl] = en ? 1 : 0; }
+            const bool pts = wd.kind[q] == Q_PTS;
+            if (wd.host[q]) {  // a brand-new hostname domain (its default already reads dsw / present)
+              if (en) {
+                const int old_nd = wd.ndom[q];
+                __syncwarp();
+                if (lane == 0) {
+                  wd.tot[q] += dsw;
+                  if (pts) {
+                    wd.ndom[q] = old_nd + 1;
+                    if (dsw < wd.minv[q]) { wd.minv[q] = dsw; wd.nmin[q] = 1; }
+                    else if (dsw == wd.minv[q]) wd.nmin[q] += 1;
+                  }
+                }
+                __syncwarp();
+                // a node joining can only HELP other nodes by lifting the domain count over minDomains
+                // (the global minimum stops being treated as 0, filtering.go:55-68)
+                if (pts && old_nd < wd.mindom[q] && wd.ndom[q] >= wd.mindom[q]) bump = true;
+                if (!pts && dsw > 0) bump = true;
+              }
             } else if (en && sl >= 0) {
-              if (lane == 0) { wc[sl] += dsw; wp[sl] += 1; }
-            }
-            __syncwarp();
-            if (en && sl >= 0) {
-              if (lane == 0) wd.tot[q] += dsw;
-              if (wd.kind[q] == Q_PTS) {
-                // a node joining can only HELP other nodes when it lifts the domain count over minDomains
-                // (global minimum stops being treated as 0, filtering.go:55-68) or raises the minimum
-                const int old_nd = wd.ndom[q], old_mn = wd.minv[q];
-                recompute(q);
-                if ((old_nd < wd.mindom[q] && wd.ndom[q] >= wd.mindom[q]) || wd.minv[q] > old_mn) bump = true;
-              } else if (dsw > 0) bump = true;
+              const int c0 = rd_cnt(q, sl), p0 = rd_pres(q, sl);
+              const int old_nd = wd.ndom[q], old_mn = wd.minv[q];
+              __syncwarp();
+              if (lane == 0) {
+                wr(q, sl, c0 + dsw, p0 + 1);
+                wd.tot[q] += dsw;
+                if (pts && p0 == 0) {
+                  wd.ndom[q] = old_nd + 1;
+                  if (c0 + dsw < wd.minv[q]) { wd.minv[q] = c0 + dsw; wd.nmin[q] = 1; }
+                  else if (c0 + dsw == wd.minv[q]) wd.nmin[q] += 1;
+                }
+              }
+              __syncwarp();
+              if (pts && p0 > 0 && dsw > 0) recompute(q);
+              if (pts && ((old_nd < wd.mindom[q] && wd.ndom[q] >= wd.mindom[q]) || wd.minv[q] > old_mn)) bump = true;
+              if (!pts && dsw > 0) bump = true;
             }
             __syncwarp();
           }
           if (bump) cur_stamp = ++stamp_ctr;
           __syncwarp();
         };
+        (void)n_new_start;
 
         // ---- tryToScheduleOnExistingNodes: per pod, first passing added node in cyclic order ----
         while (n > 0 && n_new > 0) {
@@ -576,6 +633,7 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
       if (lane == 0 && p.sched) p.sched[(size_t)t * p.E + g] = placed;
     }
     if (lane == 0) {
+      hdr[0] = stamp_ctr; hdr[1] = gver_ctr;
       p.node_count[t] = nodes_with_pods;
       p.pod_count[t] = pods_total;
       if (overflow && p.status) atomicExch(p.status, 1);
@@ -612,7 +670,7 @@ int launch_pack(Engine* e) {
   p.dstride = p.has_dyn ? dmax : 1;
   p.log_cap = p.has_dyn ? (int)std::min<size_t>(4 * X + 1024, (size_t)1 << 24) : 1;
   const int A1 = std::max(e->A, 1);
-  size_t per_warp = X * ((size_t)A1 * 8 + 8 + 4 + 4 + 4 + 1) + (size_t)2 * DYN_MAX_Q * p.dstride * 4 + (size_t)p.log_cap * 12;
+  size_t per_warp = 16 + X * ((size_t)A1 * 8 + 8 + 4 + 4 + 4 + 1) + (size_t)3 * DYN_MAX_Q * p.dstride * 4 + (size_t)p.log_cap * 12;
   per_warp = (per_warp + 255) & ~(size_t)255;
   int warps = std::min(nt, e->sm_count * 16);
   const size_t budget = (size_t)24 << 30;  // keep the slabs within 24 GiB of the 180 GB HBM
@@ -620,15 +678,18 @@ int launch_pack(Engine* e) {
   int blocks = (warps + PACK_WARPS - 1) / PACK_WARPS;
   warps = blocks * PACK_WARPS;
   size_t need = per_warp * warps;
+  const size_t sig = per_warp * 1000003u + X * 10007u + (size_t)p.dstride * 101u + (size_t)p.log_cap * 7u + (size_t)A1;
   if (need > e->pack_scratch_bytes) {
     if (e->d_pack_scratch) cudaFree(e->d_pack_scratch);
     e->d_pack_scratch = nullptr;
     e->pack_scratch_bytes = 0;
     CAE_CUDA(cudaMalloc(&e->d_pack_scratch, need));
     e->pack_scratch_bytes = need;
-    CAE_CUDA(cudaMemsetAsync(e->d_pack_scratch, 0, need, e->stream));  // stamps start at 0
-  } else if (p.has_dyn) {
-    CAE_CUDA(cudaMemsetAsync(e->d_pack_scratch, 0, need, e->stream));  // the slab layout may have moved
+    e->pack_layout_sig = 0;
+  }
+  if (sig != e->pack_layout_sig) {  // stamps / versions are only meaningful within one slab layout
+    CAE_CUDA(cudaMemsetAsync(e->d_pack_scratch, 0, need, e->stream));
+    e->pack_layout_sig = sig;
   }
   p.scratch = static_cast<unsigned char*>(e->d_pack_scratch);
   p.scratch_per_warp = per_warp;

@@ -144,29 +144,34 @@ class Engine:
         self._check(self.lib.cae_feasibility_groups(self.h, out.ctypes.data_as(C.c_void_p)))
         return out
 
-    def estimate_all(self, max_nodes: Optional[Sequence[int]] = None):
+    def estimate_all(self, max_nodes: Optional[Sequence[int]] = None, want_sched: bool = True, copy: bool = True):
         """Returns node_count[T], pod_count[T], sched_count[T][E], order[T][E] (rows outside this
-        rank's template shard are zero / -1)."""
+        rank's template shard are zero / -1).  Outputs land in pinned buffers; copy=False returns
+        views that the next call overwrites; want_sched=False skips the two [T][E] matrices."""
         enc = self.enc
         T, E = enc.T, enc.E
         mn = None if max_nodes is None else np.ascontiguousarray(max_nodes, np.int32)
-        node_count = np.zeros(T, np.int32)
-        pod_count = np.zeros(T, np.int32)
-        sched = np.zeros((T, E), np.int32)
-        order = np.full((T, E), -1, np.int32)
+        node_count = self._pin("node_count", (T,), np.int32)
+        pod_count = self._pin("pod_count", (T,), np.int32)
+        sched = self._pin("sched", (T, E), np.int32) if want_sched else None
+        order = self._pin("order", (T, E), np.int32) if want_sched else None
         vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
         self._check(self.lib.cae_estimate_all(self.h, vp(mn), vp(node_count), vp(pod_count), vp(sched), vp(order)))
+        if copy:
+            return (node_count.copy(), pod_count.copy(), None if sched is None else sched.copy(),
+                    None if order is None else order.copy())
         return node_count, pod_count, sched, order
 
-    def expander_best(self, chain: Sequence[int], node_count, pod_count, sched):
+    def expander_best(self, chain: Sequence[int], node_count, pod_count, sched=None):
+        """sched=None scores the device-resident result of the last estimate_all (single shard)."""
         enc = self.enc
         ch = np.asarray(chain, np.int32)
         nc = np.ascontiguousarray(node_count, np.int32)
         pc = np.ascontiguousarray(pod_count, np.int32)
-        sc = np.ascontiguousarray(sched, np.int32)
+        sc = None if sched is None else np.ascontiguousarray(sched, np.int32)
         mask = np.zeros(enc.T, np.uint8)
         waste = np.zeros(enc.T, np.float64)
-        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
         self._check(self.lib.cae_expander_best(self.h, vp(ch), len(ch), vp(nc), vp(pc), vp(sc), vp(mask), vp(waste)))
         return mask, waste
 

@@ -38,9 +38,9 @@ def main():
         t0 = time.perf_counter()
         eng.load(enc)
         t1 = time.perf_counter()
-        nc, pc, sched, order = eng.estimate_all(caps)
+        nc, pc, sched, order = eng.estimate_all(caps, copy=False)
         t2 = time.perf_counter()
-        mask, waste = eng.expander_best([0, 1, 2], nc, pc, sched)
+        mask, waste = eng.expander_best([0, 1, 2], nc, pc)
         t3 = time.perf_counter()
         st = eng.stats()
         rows.append({"load_ms": 1e3 * (t1 - t0), "estimate_wall_ms": 1e3 * (t2 - t1), "estimate_dev_ms": st.estimate_ms,

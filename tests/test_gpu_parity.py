@@ -49,6 +49,8 @@ def _check_estimate(eng, oracle, enc, caps):
         omask, owaste = oracle.expander(enc, chain, nc, pc, sched)
         assert np.array_equal(mask, omask), chain
         assert np.array_equal(waste, owaste)  # float64, bit-identical
+        mask2, waste2 = eng.expander_best(chain, nc, pc)   # device-resident result of the estimate just run
+        assert np.array_equal(mask2, omask) and np.array_equal(waste2, owaste)
     return nc, pc
 
 
