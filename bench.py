@@ -216,10 +216,15 @@ def main():
             __cuda_array_interface__ = {"shape": (T,), "typestr": "<i4", "data": (ptr, False), "version": 3}
         count_t = torch.as_tensor(_Wrap(), device="cuda")
 
+    ar0 = torch.cuda.Event(enable_timing=True)
+    ar1 = torch.cuda.Event(enable_timing=True)
+
     def step_resident():
         eng.lib.cae_feasibility(eng.h, None, None, None)       # kernel only; results stay in HBM
         if count_t is not None:
+            ar0.record()
             dist.all_reduce(count_t)                           # int32[T] histogram over NVLink
+            ar1.record()
 
     for _ in range(args.warmup):
         flush.zero_()
@@ -231,7 +236,7 @@ def main():
     th = threading.Thread(target=_clock_sampler, args=(stop, samples, local_rank), daemon=True)
     th.start()
     launches0 = eng.stats().kernel_launches
-    dev_ms, wall_ms = [], []
+    dev_ms, wall_ms, ar_ms = [], [], []
     for _ in range(args.steps):
         flush.zero_()                                          # L2 flush between timed iterations (untimed)
         torch.cuda.synchronize()
@@ -242,10 +247,14 @@ def main():
         torch.cuda.synchronize()
         wall_ms.append(1e3 * (time.perf_counter() - t0))
         dev_ms.append(eng.stats().feasibility_ms)
+        if count_t is not None:
+            ar_ms.append(ar0.elapsed_time(ar1))
     launches = eng.stats().kernel_launches - launches0
     kern_ms = float(np.mean(dev_ms))
-    # N>1: step time incl. the allreduce, max over ranks; N=1: device time of the pass
-    step_ms = float(np.mean(wall_ms)) if world > 1 else kern_ms
+    # device time of a step: the pass (CUDA events on the engine's stream) + for N>1 the NCCL all-reduce of
+    # the histogram (CUDA events on torch's stream), max over ranks
+    allreduce_ms = float(np.mean(ar_ms)) if ar_ms else 0.0
+    step_ms = kern_ms + allreduce_ms
     if dist is not None:
         tt = torch.tensor([step_ms, kern_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -344,7 +353,7 @@ def main():
         "vs_baseline": None, "dtype": "int64", "data": "synthetic",
         "config": {"workload": workload, "global_pods": P1 * world, "templates": T, "parallelism": "pods sharded x%d" % world,
                    "l2": "flushed between timed iterations (512 MiB memset)"},
-        "kernel_ms": kern_ms, "clocks": _clocks_summary(samples),
+        "kernel_ms": kern_ms, "allreduce_ms": allreduce_ms, "wall_ms_per_step": float(np.mean(wall_ms)), "clocks": _clocks_summary(samples),
         "e2e": {"value": (P1 * world) * T / (e2e_step * 1e-3), "unit": "evals/s", "ms_per_step": e2e_step,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "decision_latency": decision}))

@@ -339,6 +339,26 @@ static int do_load(Engine* e, const cae_objects* o) {
       cslots[row] = o->node_allowed_pods[row] - npods;
     }
   }
+  // bit-sliced free-capacity ranks for the dense pass (feas.cu): slice b, word tw holds bit b of the rank
+  // of templates tw*32 .. tw*32+31; slices run MSB-first inside a field, fields concatenated
+  e->feas_B = 0;
+  e->feas_fstart = 0;
+  for (int a = 0; a < e->A; ++a) {
+    const int nb = f_bits[a] - 1;
+    for (int i = nb - 1; i >= 0; --i) {
+      if (e->feas_B >= 32) { set_error("resource request cardinality too large for the bit-sliced encoding"); return 1; }
+      e->feas_sword[e->feas_B] = (uint8_t)f_word[a];
+      e->feas_sshift[e->feas_B] = (uint8_t)(f_shift[a] + i);
+      if (i == nb - 1) e->feas_fstart |= 1u << e->feas_B;
+      ++e->feas_B;
+    }
+  }
+  const int Bpad = std::max(4, (e->feas_B + 3) / 4 * 4);
+  std::vector<uint32_t> tslice((size_t)Bpad * std::max(e->Tw, 1), 0);
+  for (int b = 0; b < e->feas_B; ++b)
+    for (int t = 0; t < T; ++t)
+      tslice[(size_t)b * e->Tw + t / 32] |= ((tmpl_w[(size_t)e->feas_sword[b] * T + t] >> e->feas_sshift[b]) & 1u) << (t % 32);
+  if (upload_mut(e, tslice, &e->d_tslice)) return -1;
   if (upload_mut(e, sclass, &e->d_sclass) || upload_mut(e, spec_sc, &e->d_spec_sc) || upload_mut(e, slots, &e->d_tmpl_slots) ||
       upload_mut(e, free_all, &e->d_tmpl_free_all) || upload_mut(e, free_act, &e->d_tmpl_free) || upload_mut(e, cfree, &e->d_c_free) ||
       upload_mut(e, cslots, &e->d_c_slots) || upload_mut(e, spec_w, &e->d_spec_w) || upload_mut(e, tmpl_w, &e->d_tmpl_w) || upload_mut(e, pc_of, &e->d_pc_of) || upload_mut(e, spec_dc, &e->d_spec_dc))

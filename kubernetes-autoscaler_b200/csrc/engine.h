@@ -91,6 +91,10 @@ struct Engine {
   uint32_t* d_spec_w = nullptr;           // [num_podspecs][FEAS_MAX_W] packed request ranks
   uint32_t* d_pod_w = nullptr;            // [W][Pl] per pending pod
   uint32_t* d_tmpl_w = nullptr;           // [W][T] packed free-capacity ranks + guard bits
+  int feas_B = 0;                         // bit slices of the free-capacity ranks (all fields)
+  uint32_t feas_fstart = 0;               // bit b set: slice b is the most significant bit of a field
+  uint8_t feas_sword[32] = {0}, feas_sshift[32] = {0};  // where bit b sits in the packed pod words
+  uint32_t* d_tslice = nullptr;           // [ceil4(B)][Tw] bit-sliced template ranks
   int32_t* d_pod_sc = nullptr;            // [P]
   int32_t* d_pod_dc = nullptr;            // [P]
   int64_t* d_tmpl_free = nullptr;         // [A][T] allocatable - DaemonSet requested

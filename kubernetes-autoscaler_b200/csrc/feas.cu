@@ -7,12 +7,12 @@
 //                    (0 when the pod does not request it: such a resource is never checked, fit.go:670-704)
 //     rank_free(f) = number of distinct request values <= f
 //     request > free  <=>  rank_req > rank_free            (exact, both directions)
-// and the ranks of all resources are packed into W 32-bit words with one guard bit per field, so one
-// subtraction per word compares every resource at once (a cleared guard bit = a borrow = "insufficient").
-// Per 32 templates a lane assembles its pod's row of verdict bits, ANDs the class words of the
-// size-independent plugins (pre_ok / post_ok), and a 5-stage shuffle transpose of the warp's 32x32 bit
-// block yields the template-major words of the output bit matrix.  Output is flushed in full 32 B
-// sectors with a popcount per template for the fit histogram.
+// The template ranks are stored BIT-SLICED: slice b, word tw holds bit b of the ranks of templates
+// tw*32 .. tw*32+31.  A lane compares its pod's rank against 32 templates at once with the classic
+// MSB-first bit-serial comparator (gt |= eq & r & ~f; eq &= ~(r ^ f)), ~2.5 logic ops per slice per
+// 32 evaluations, then ANDs the class words of the size-independent plugins (pre_ok / post_ok).
+// A 5-stage shuffle transpose of the warp's 32x32 verdict block yields the template-major words of
+// the output bit matrix; they are flushed in full 32 B sectors and pop-counted into the fit histogram.
 #include <climits>
 
 #include "engine.h"
@@ -41,11 +41,16 @@ int launch_expand_pods(Engine* e) {
 }
 
 constexpr int K1_THREADS = 256;
-constexpr int K1_TCHUNK = 128;  // templates per CTA
+constexpr int K1_TW = 16;                 // template words (x32 templates) per CTA
+constexpr int K1_TCHUNK = K1_TW * 32;
 constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int K1_PAD = K1_TCHUNK + 4;
 
-struct FeasGuards { uint32_t g[FEAS_MAX_W]; };
+struct FeasLayout {
+  uint32_t fstart;           // bit b: slice b starts a field
+  int nb;                    // real slices (the rest is zero padding)
+  uint8_t sword[32], sshift[32];
+};
 
 // lane i holds row i of a 32x32 bit matrix; afterwards lane j holds column j (bit i = M[i][j])
 __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
@@ -58,104 +63,125 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
   return x;
 }
 
-template <int W, bool REASONS>
+template <int B, bool REASONS>
 __global__ void __launch_bounds__(K1_THREADS)
-feasibility_kernel(int Pl, int Plw, int T, int Tw, int N, int U, FeasGuards guards,
+feasibility_kernel(int Pl, int Plw, int T, int Tw, int N, int U, int W, FeasLayout lay,
                    const uint32_t* __restrict__ pod_w, const int32_t* __restrict__ pod_sc,
-                   const int32_t* __restrict__ pod_dc, const uint32_t* __restrict__ tmpl_w,
+                   const int32_t* __restrict__ pod_dc, const uint32_t* __restrict__ tslice,
                    const int32_t* __restrict__ tmpl_slots,
                    const uint32_t* __restrict__ pre_ok, const uint32_t* __restrict__ post_ok,
                    const uint8_t* __restrict__ pre_code, const uint8_t* __restrict__ post_code,
                    uint32_t* __restrict__ fit_bits, int32_t* __restrict__ fit_count,
                    uint8_t* __restrict__ reasons) {
-  __shared__ __align__(16) uint32_t s_tw[W > 0 ? W : 1][K1_TCHUNK];
+  __shared__ uint32_t s_sl[B > 0 ? B : 1][K1_TW];
   __shared__ uint32_t s_out[K1_WARPS][K1_PAD];
+  __shared__ int32_t s_cnt[K1_TCHUNK];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int p = blockIdx.x * K1_THREADS + tid;
-  const int t0 = blockIdx.y * K1_TCHUNK;
-  const int tn = min(K1_TCHUNK, T - t0);
+  const int tw0 = blockIdx.y * K1_TW;
+  const int t0 = tw0 * 32;
 
-  for (int i = tid; i < W * K1_TCHUNK; i += K1_THREADS) {
-    const int w = i / K1_TCHUNK, j = i % K1_TCHUNK;
-    s_tw[w][j] = (j < tn) ? tmpl_w[(size_t)w * T + t0 + j] : 0u;  // guard bits clear: every pod "fails" on padding
+  for (int i = tid; i < B * K1_TW; i += K1_THREADS) {
+    const int b = i / K1_TW, w = i % K1_TW;
+    s_sl[b][w] = (tw0 + w < Tw) ? tslice[(size_t)b * Tw + tw0 + w] : 0u;
   }
+  for (int i = tid; i < K1_TCHUNK; i += K1_THREADS) s_cnt[i] = 0;
   const bool valid = p < Pl;
-  uint32_t pw[W > 0 ? W : 1];
+  // the pod's rank bits as all-ones / all-zeros masks, one register per slice
+  uint32_t r[B > 0 ? B : 1];
+  {
+    uint32_t pw[FEAS_MAX_W];
 #pragma unroll
-  for (int w = 0; w < W; ++w) pw[w] = valid ? pod_w[(size_t)w * Pl + p] : 0u;
+    for (int w = 0; w < FEAS_MAX_W; ++w) pw[w] = (valid && w < W) ? pod_w[(size_t)w * Pl + p] : 0u;
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      const uint32_t word = lay.sword[b] == 0 ? pw[0] : lay.sword[b] == 1 ? pw[1] : lay.sword[b] == 2 ? pw[2] : pw[3];
+      r[b] = b < lay.nb ? 0u - ((word >> lay.sshift[b]) & 1u) : 0u;
+    }
+  }
   const int sc = valid ? pod_sc[p] : 0;
   const int dc = valid ? pod_dc[p] : 0;
   __syncthreads();
 
 #pragma unroll 1
-  for (int tw = 0; tw < K1_TCHUNK / 32; ++tw) {
-    const int wglob = t0 / 32 + tw;
+  for (int tw = 0; tw < K1_TW; ++tw) {
+    const int wglob = tw0 + tw;
     uint32_t row = 0;
     if (wglob < Tw) {
+      // bit-serial "rank_req > rank_free" for 32 templates at once; fields concatenated, MSB first
+      uint32_t gt = 0, eq = 0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int tl = tw * 32 + j;
-        uint32_t bad = 0;
-#pragma unroll
-        for (int w = 0; w < W; ++w) bad |= ~(s_tw[w][tl] - pw[w]) & guards.g[w];  // a cleared guard bit = insufficient
-        if (bad == 0) row |= 1u << j;
-        if (REASONS) {
-          const int t = t0 + tl;
-          if (valid && t < T) {
+      for (int b = 0; b < B; ++b) {
+        const uint32_t f = s_sl[b][tw];
+        if ((lay.fstart >> b) & 1u) eq = 0xffffffffu;  // uniform: a new field starts
+        gt |= eq & r[b] & ~f;
+        eq &= ~(r[b] ^ f);
+      }
+      row = valid ? (~gt & pre_ok[(size_t)sc * Tw + wglob] & post_ok[(size_t)dc * Tw + wglob]) : 0u;
+      if (REASONS) {
+        if (valid) {
+          for (int j = 0; j < 32; ++j) {
+            const int t = wglob * 32 + j;
+            if (t >= T) break;
             // first failing plugin in Filter order: static plugins, NodeResourcesFit, then PTS / IPA
-            uint8_t r = pre_code[(size_t)sc * U + N + t] & 0x0F;
-            if (r == 0) r = (bad != 0 || tmpl_slots[t] < 1) ? CAE_R_FIT : post_code[(size_t)dc * T + t];
-            reasons[(size_t)t * Pl + p] = r;
+            uint8_t rs = pre_code[(size_t)sc * U + N + t] & 0x0F;
+            if (rs == 0) rs = (((gt >> j) & 1u) || tmpl_slots[t] < 1) ? CAE_R_FIT : post_code[(size_t)dc * T + t];
+            reasons[(size_t)t * Pl + p] = rs;
           }
         }
       }
-      row &= valid ? (pre_ok[(size_t)sc * Tw + wglob] & post_ok[(size_t)dc * Tw + wglob]) : 0u;
     }
-    s_out[warp][tw * 32 + lane] = warp_transpose32(row, lane);  // word of template t0 + tw*32 + lane over this warp's pods
+    const uint32_t col = warp_transpose32(row, lane);  // word of template t0 + tw*32 + lane over this warp's pods
+    s_out[warp][tw * 32 + lane] = col;
+    if (col) atomicAdd(&s_cnt[tw * 32 + lane], __popc(col));
   }
   __syncthreads();
-  // flush: 8 consecutive words (one 32 B sector) per template row; popcount -> per-template counts
+  // flush: 8 consecutive words (one 32 B sector) per template row
   const int pw0 = blockIdx.x * K1_WARPS;
   for (int i = tid; i < K1_TCHUNK * K1_WARPS; i += K1_THREADS) {
     const int tl = i / K1_WARPS, wv = i % K1_WARPS;
     const int t = t0 + tl;
-    const uint32_t word = (t < T) ? s_out[wv][tl] : 0u;
-    int c = __popc(word);
-    c += __shfl_xor_sync(0xffffffffu, c, 1);
-    c += __shfl_xor_sync(0xffffffffu, c, 2);
-    c += __shfl_xor_sync(0xffffffffu, c, 4);
-    if (t < T) {
-      if (pw0 + wv < Plw && fit_bits) fit_bits[(size_t)t * Plw + pw0 + wv] = word;
-      if (wv == 0 && c) atomicAdd(&fit_count[t], c);
-    }
+    if (t < T && pw0 + wv < Plw && fit_bits) fit_bits[(size_t)t * Plw + pw0 + wv] = s_out[wv][tl];
+  }
+  for (int i = tid; i < K1_TCHUNK; i += K1_THREADS) {
+    const int c = s_cnt[i];
+    if (c && t0 + i < T) atomicAdd(&fit_count[t0 + i], c);
   }
 }
 
-template <int W>
-static void launch_feas_w(Engine* e, bool want_reasons) {
-  dim3 grid((e->Pl + K1_THREADS - 1) / K1_THREADS, (e->T + K1_TCHUNK - 1) / K1_TCHUNK);
+template <int B>
+static void launch_feas_b(Engine* e, bool want_reasons) {
+  dim3 grid((e->Pl + K1_THREADS - 1) / K1_THREADS, (e->Tw + K1_TW - 1) / K1_TW);
   if (grid.x == 0 || grid.y == 0) return;
-  FeasGuards g;
-  for (int w = 0; w < FEAS_MAX_W; ++w) g.g[w] = e->feas_guard[w];
+  FeasLayout lay;
+  lay.fstart = e->feas_fstart;
+  lay.nb = e->feas_B;
+  for (int b = 0; b < 32; ++b) { lay.sword[b] = e->feas_sword[b]; lay.sshift[b] = e->feas_sshift[b]; }
   if (want_reasons)
-    feasibility_kernel<W, true><<<grid, K1_THREADS, 0, e->stream>>>(
-        e->Pl, e->Plw, e->T, e->Tw, e->N, e->U, g, e->d_pod_w, e->d_pod_sc, e->d_pod_dc, e->d_tmpl_w, e->d_tmpl_slots,
+    feasibility_kernel<B, true><<<grid, K1_THREADS, 0, e->stream>>>(
+        e->Pl, e->Plw, e->T, e->Tw, e->N, e->U, e->W, lay, e->d_pod_w, e->d_pod_sc, e->d_pod_dc, e->d_tslice, e->d_tmpl_slots,
         e->d_pre_ok, e->d_post_ok, e->d_pre_code, e->d_post_code, e->d_fit_bits, e->d_fit_count, e->d_reasons);
   else
-    feasibility_kernel<W, false><<<grid, K1_THREADS, 0, e->stream>>>(
-        e->Pl, e->Plw, e->T, e->Tw, e->N, e->U, g, e->d_pod_w, e->d_pod_sc, e->d_pod_dc, e->d_tmpl_w, e->d_tmpl_slots,
+    feasibility_kernel<B, false><<<grid, K1_THREADS, 0, e->stream>>>(
+        e->Pl, e->Plw, e->T, e->Tw, e->N, e->U, e->W, lay, e->d_pod_w, e->d_pod_sc, e->d_pod_dc, e->d_tslice, e->d_tmpl_slots,
         e->d_pre_ok, e->d_post_ok, e->d_pre_code, e->d_post_code, e->d_fit_bits, e->d_fit_count, e->d_reasons);
   e->stats.kernel_launches++;
 }
 
 int launch_feasibility(Engine* e, bool want_reasons) {
   CAE_CUDA(cudaMemsetAsync(e->d_fit_count, 0, sizeof(int32_t) * e->T, e->stream));
-  switch (e->W) {
-    case 0: launch_feas_w<0>(e, want_reasons); break;
-    case 1: launch_feas_w<1>(e, want_reasons); break;
-    case 2: launch_feas_w<2>(e, want_reasons); break;
-    case 3: launch_feas_w<3>(e, want_reasons); break;
-    default: launch_feas_w<4>(e, want_reasons); break;
+  // slices beyond feas_B are all-zero with r = 0: they change nothing (padding to a multiple of 4)
+  const int Bp = e->feas_B == 0 ? 0 : (e->feas_B + 3) / 4 * 4;
+  switch (Bp) {
+    case 0: launch_feas_b<0>(e, want_reasons); break;
+    case 4: launch_feas_b<4>(e, want_reasons); break;
+    case 8: launch_feas_b<8>(e, want_reasons); break;
+    case 12: launch_feas_b<12>(e, want_reasons); break;
+    case 16: launch_feas_b<16>(e, want_reasons); break;
+    case 20: launch_feas_b<20>(e, want_reasons); break;
+    case 24: launch_feas_b<24>(e, want_reasons); break;
+    case 28: launch_feas_b<28>(e, want_reasons); break;
+    default: launch_feas_b<32>(e, want_reasons); break;
   }
   CAE_KERNEL_OK();
   return 0;
