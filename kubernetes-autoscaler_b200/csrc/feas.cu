@@ -41,9 +41,10 @@ int launch_expand_pods(Engine* e) {
 }
 
 constexpr int K1_THREADS = 256;
-constexpr int K1_SUB = 4;                 // template words (x32 templates) staged per flush
+constexpr int K1_TW = 16;                 // template words (x32 templates) per CTA
+constexpr int K1_TCHUNK = K1_TW * 32;
 constexpr int K1_WARPS = K1_THREADS / 32;
-constexpr int K1_PAD = K1_SUB * 32 + 4;
+constexpr int K1_PAD = K1_TCHUNK + 4;
 
 struct FeasLayout {
   uint32_t fstart;           // bit b: slice b starts a field
@@ -62,11 +63,8 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
   return x;
 }
 
-// Persistent CTAs: the (pod block of 256, template word) units are linearised pod-block-major and split
-// into equal contiguous ranges, so every CTA does the same amount of work (no tail wave) and reloads its
-// pods' rank masks at most twice.
 template <int B, bool REASONS>
-__global__ void __launch_bounds__(K1_THREADS, 5)
+__global__ void __launch_bounds__(K1_THREADS)
 feasibility_kernel(int Pl, int Plw, int T, int Tw, int N, int U, int W, FeasLayout lay,
                    const uint32_t* __restrict__ pod_w, const int32_t* __restrict__ pod_sc,
                    const int32_t* __restrict__ pod_dc, const uint32_t* __restrict__ tslice,
@@ -75,53 +73,51 @@ feasibility_kernel(int Pl, int Plw, int T, int Tw, int N, int U, int W, FeasLayo
                    const uint8_t* __restrict__ pre_code, const uint8_t* __restrict__ post_code,
                    uint32_t* __restrict__ fit_bits, int32_t* __restrict__ fit_count,
                    uint8_t* __restrict__ reasons) {
-  __shared__ uint32_t s_sl[B > 0 ? B : 1][K1_SUB];
+  __shared__ uint32_t s_sl[B > 0 ? B : 1][K1_TW];
   __shared__ uint32_t s_out[K1_WARPS][K1_PAD];
+  __shared__ int32_t s_cnt[K1_TCHUNK];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nblocks = (Pl + K1_THREADS - 1) / K1_THREADS;
-  const long long units = (long long)nblocks * Tw;
-  const long long u0 = units * blockIdx.x / gridDim.x, u1 = units * (blockIdx.x + 1) / gridDim.x;
-  int pb_cur = -1, p = 0, sc = 0, dc = 0;
-  bool valid = false;
-  uint32_t r[B > 0 ? B : 1];  // the pod's rank bits as all-ones / all-zeros masks, one register per slice
-#pragma unroll
-  for (int b = 0; b < B; ++b) r[b] = 0;
+  const int p = blockIdx.x * K1_THREADS + tid;
+  const int tw0 = blockIdx.y * K1_TW;
+  const int t0 = tw0 * 32;
 
-  for (long long u = u0; u < u1;) {
-    const int pb = (int)(u / Tw), tw0 = (int)(u % Tw);
-    const int nsub = (int)min((long long)min(K1_SUB, Tw - tw0), u1 - u);
-    if (pb != pb_cur) {
-      pb_cur = pb;
-      p = pb * K1_THREADS + tid;
-      valid = p < Pl;
-      uint32_t pw[FEAS_MAX_W];
+  for (int i = tid; i < B * K1_TW; i += K1_THREADS) {
+    const int b = i / K1_TW, w = i % K1_TW;
+    s_sl[b][w] = (tw0 + w < Tw) ? tslice[(size_t)b * Tw + tw0 + w] : 0u;
+  }
+  for (int i = tid; i < K1_TCHUNK; i += K1_THREADS) s_cnt[i] = 0;
+  const bool valid = p < Pl;
+  // the pod's rank bits as all-ones / all-zeros masks, one register per slice
+  uint32_t r[B > 0 ? B : 1];
+  {
+    uint32_t pw[FEAS_MAX_W];
 #pragma unroll
-      for (int w = 0; w < FEAS_MAX_W; ++w) pw[w] = (valid && w < W) ? pod_w[(size_t)w * Pl + p] : 0u;
+    for (int w = 0; w < FEAS_MAX_W; ++w) pw[w] = (valid && w < W) ? pod_w[(size_t)w * Pl + p] : 0u;
 #pragma unroll
-      for (int b = 0; b < B; ++b) {
-        const uint32_t word = lay.sword[b] == 0 ? pw[0] : lay.sword[b] == 1 ? pw[1] : lay.sword[b] == 2 ? pw[2] : pw[3];
-        r[b] = b < lay.nb ? 0u - ((word >> lay.sshift[b]) & 1u) : 0u;
-      }
-      sc = valid ? pod_sc[p] : 0;
-      dc = valid ? pod_dc[p] : 0;
+    for (int b = 0; b < B; ++b) {
+      const uint32_t word = lay.sword[b] == 0 ? pw[0] : lay.sword[b] == 1 ? pw[1] : lay.sword[b] == 2 ? pw[2] : pw[3];
+      r[b] = b < lay.nb ? 0u - ((word >> lay.sshift[b]) & 1u) : 0u;
     }
-    if (tid < B * K1_SUB) {
-      const int b = tid / K1_SUB, k = tid % K1_SUB;
-      s_sl[b][k] = k < nsub ? tslice[(size_t)b * Tw + tw0 + k] : 0u;
-    }
-    __syncthreads();
-    for (int k = 0; k < nsub; ++k) {
-      const int wglob = tw0 + k;
+  }
+  const int sc = valid ? pod_sc[p] : 0;
+  const int dc = valid ? pod_dc[p] : 0;
+  __syncthreads();
+
+#pragma unroll 1
+  for (int tw = 0; tw < K1_TW; ++tw) {
+    const int wglob = tw0 + tw;
+    uint32_t row = 0;
+    if (wglob < Tw) {
       // bit-serial "rank_req > rank_free" for 32 templates at once; fields concatenated, MSB first
       uint32_t gt = 0, eq = 0;
 #pragma unroll
       for (int b = 0; b < B; ++b) {
-        const uint32_t f = s_sl[b][k];
+        const uint32_t f = s_sl[b][tw];
         if ((lay.fstart >> b) & 1u) eq = 0xffffffffu;  // uniform: a new field starts
         gt |= eq & r[b] & ~f;
         eq &= ~(r[b] ^ f);
       }
-      const uint32_t row = valid ? (~gt & pre_ok[(size_t)sc * Tw + wglob] & post_ok[(size_t)dc * Tw + wglob]) : 0u;
+      row = valid ? (~gt & pre_ok[(size_t)sc * Tw + wglob] & post_ok[(size_t)dc * Tw + wglob]) : 0u;
       if (REASONS) {
         if (valid) {
           for (int j = 0; j < 32; ++j) {
@@ -134,36 +130,29 @@ feasibility_kernel(int Pl, int Plw, int T, int Tw, int N, int U, int W, FeasLayo
           }
         }
       }
-      s_out[warp][k * 32 + lane] = warp_transpose32(row, lane);  // word of template (tw0+k)*32 + lane, this warp's pods
     }
-    __syncthreads();
-    // flush: 8 consecutive words (one 32 B sector) per template row + the fit histogram
-    const int pw0 = pb * K1_WARPS;
-    for (int i = tid; i < nsub * 32 * K1_WARPS; i += K1_THREADS) {
-      const int tl = i / K1_WARPS, wv = i % K1_WARPS;
-      const int t = tw0 * 32 + tl;
-      const uint32_t word = s_out[wv][tl];
-      int c = __popc(word);
-      c += __shfl_xor_sync(0xffffffffu, c, 1);
-      c += __shfl_xor_sync(0xffffffffu, c, 2);
-      c += __shfl_xor_sync(0xffffffffu, c, 4);
-      if (t < T) {
-        if (pw0 + wv < Plw && fit_bits) fit_bits[(size_t)t * Plw + pw0 + wv] = word;
-        if (wv == 0 && c) atomicAdd(&fit_count[t], c);
-      }
-    }
-    __syncthreads();
-    u += nsub;
+    const uint32_t col = warp_transpose32(row, lane);  // word of template t0 + tw*32 + lane over this warp's pods
+    s_out[warp][tw * 32 + lane] = col;
+    if (col) atomicAdd(&s_cnt[tw * 32 + lane], __popc(col));
+  }
+  __syncthreads();
+  // flush: 8 consecutive words (one 32 B sector) per template row
+  const int pw0 = blockIdx.x * K1_WARPS;
+  for (int i = tid; i < K1_TCHUNK * K1_WARPS; i += K1_THREADS) {
+    const int tl = i / K1_WARPS, wv = i % K1_WARPS;
+    const int t = t0 + tl;
+    if (t < T && pw0 + wv < Plw && fit_bits) fit_bits[(size_t)t * Plw + pw0 + wv] = s_out[wv][tl];
+  }
+  for (int i = tid; i < K1_TCHUNK; i += K1_THREADS) {
+    const int c = s_cnt[i];
+    if (c && t0 + i < T) atomicAdd(&fit_count[t0 + i], c);
   }
 }
 
 template <int B>
 static void launch_feas_b(Engine* e, bool want_reasons) {
-  const long long units = (long long)((e->Pl + K1_THREADS - 1) / K1_THREADS) * e->Tw;
-  if (units == 0) return;
-  int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, feasibility_kernel<B, false>, K1_THREADS, 0);
-  const int grid = (int)std::min<long long>(units, (long long)e->sm_count * std::max(occ, 1));
+  dim3 grid((e->Pl + K1_THREADS - 1) / K1_THREADS, (e->Tw + K1_TW - 1) / K1_TW);
+  if (grid.x == 0 || grid.y == 0) return;
   FeasLayout lay;
   lay.fstart = e->feas_fstart;
   lay.nb = e->feas_B;
