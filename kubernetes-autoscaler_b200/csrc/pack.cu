@@ -26,6 +26,7 @@ namespace cae {
 
 struct PackParams {
   int E, T, N, U, t_begin, t_end, cap, has_dyn, dstride, log_cap;
+  size_t sufmin_off;
   const int32_t *order, *order_n;
   const uint8_t* pre_code;
   const int32_t *spec_sc, *spec_dc;
@@ -92,7 +93,9 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
   int32_t* wpres = wcnt + (size_t)DYN_MAX_Q * p.dstride;                              // [DYN_MAX_Q][dstride]
   int32_t* wver = wpres + (size_t)DYN_MAX_Q * p.dstride;                              // [DYN_MAX_Q][dstride] slot version
   int32_t* logbuf = wver + (size_t)DYN_MAX_Q * p.dstride;                             // [log_cap][3]
-  uint8_t* nsched = reinterpret_cast<uint8_t*>(logbuf + (size_t)p.log_cap * 3);       // [X]
+  int32_t* live = logbuf + (size_t)p.log_cap * 3;                                     // [cap] added nodes that can still host SOME remaining group, ascending
+  int64_t* sufmin = reinterpret_cast<int64_t*>(slab + p.sufmin_off);                  // [A][E+1] min positive request over the groups still to come
+  uint8_t* nsched = reinterpret_cast<uint8_t*>(sufmin + (size_t)(A > 0 ? A : 1) * (p.E + 1));  // [X]
   int stamp_ctr = hdr[0] + 1, gver_ctr = hdr[1] + 1;
 
   for (;;) {
@@ -110,6 +113,49 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
     int n_new = 0, nodes_with_pods = 0, pods_total = 0, last_index = 0, log_n = 0;
     bool new_nodes_available = true, cl_init = false, overflow = false;
     const int n_groups = p.order_n[t];
+    int n_live = 0;
+    bool want_compact = false;
+    // A node is DEAD once no group still to come can fit: no pod slot left, or some resource that every
+    // remaining group requests is below the smallest such request.  free only shrinks and the suffix
+    // minimum only grows, so dead nodes stay dead and are dropped from the scan list.
+    {
+      const int chunk = (n_groups + 31) / 32;
+      const int g0 = min(lane * chunk, n_groups), g1 = min(g0 + chunk, n_groups);
+      int64_t cm[A > 0 ? A : 1];
+#pragma unroll
+      for (int a = 0; a < A; ++a) cm[a] = LLONG_MAX;
+      for (int gi = g1 - 1; gi >= g0; --gi) {
+        const int sp2 = o.pend_spec[o.group_off[p.order[(size_t)t * p.E + gi]]];
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+          const int64_t q = o.ps_req[(size_t)sp2 * R + p.act_dim[a]];
+          cm[a] = min(cm[a], q > 0 ? q : 0);
+        }
+      }
+      // exclusive suffix scan of the chunk minima over lanes
+      int64_t tail[A > 0 ? A : 1];
+#pragma unroll
+      for (int a = 0; a < A; ++a) {
+        int64_t v = cm[a];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const int64_t w2 = __shfl_down_sync(0xffffffffu, v, off);
+          if (lane + off < 32) v = min(v, w2);
+        }
+        tail[a] = __shfl_down_sync(0xffffffffu, v, 1);
+        if (lane == 31) tail[a] = LLONG_MAX;
+      }
+      for (int gi = g1 - 1; gi >= g0; --gi) {
+        const int sp2 = o.pend_spec[o.group_off[p.order[(size_t)t * p.E + gi]]];
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+          const int64_t q = o.ps_req[(size_t)sp2 * R + p.act_dim[a]];
+          tail[a] = min(tail[a], q > 0 ? q : 0);
+          sufmin[(size_t)a * (p.E + 1) + gi] = tail[a];
+        }
+      }
+      __syncwarp();
+    }
 
     // ---- shared helpers -----------------------------------------------------------------------
     auto slot_of = [&](int q, int x) -> int {
@@ -149,33 +195,65 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
       const unsigned long long pbit = has_ports ? (1ull << p.pc_of[plist]) : 0ull;
       const bool feeds = p.has_dyn && d.group_feeds[g];
       int placed = 0;
+      int64_t sm[A > 0 ? A : 1];
+#pragma unroll
+      for (int a = 0; a < A; ++a) sm[a] = sufmin[(size_t)a * (p.E + 1) + gi];
+      auto is_dead = [&](int x) -> bool {
+        bool dead = nslots[x] <= 0;
+#pragma unroll
+        for (int a = 0; a < A; ++a) dead |= (sm[a] > 0 && nfree[(size_t)a * X + x] < sm[a]);
+        return dead;
+      };
+      if (want_compact) {  // stable in-place compaction of the scan list
+        int out = 0;
+        for (int base = 0; base < n_live; base += 32) {
+          const int pos = base + lane;
+          const int j = pos < n_live ? live[pos] : 0;
+          const bool keep = pos < n_live && !is_dead(Neff + j);
+          const unsigned m = __ballot_sync(0xffffffffu, keep);
+          __syncwarp();
+          if (keep) live[out + __popc(m & ((1u << lane) - 1))] = j;
+          out += __popc(m);
+          __syncwarp();
+        }
+        n_live = out;
+        want_compact = false;
+      }
 
       if (dc == 0) {
         // ======================= plain group: closed form =======================================
-        if (n_new > 0 && static_new) {
+        if (n_live > 0 && static_new) {
           const int list_len = N + n_new;
           const int s = last_index >= N ? last_index - N : 0;  // first added node in cyclic scan order
           long long total = 0;
-          int kmax = 0;
-          for (int j = lane; j < n_new; j += 32) {
+          int kmax = 0, sp = 0, ndead = 0;
+          for (int pos = lane; pos < n_live; pos += 32) {
+            const int j = live[pos];
             const int x = Neff + j;
+            sp += j < s;
             int k = min(nslots[x], n);
             if (k > 0 && (nports[x] & pconf)) k = 0;
+            bool dead = nslots[x] <= 0;
 #pragma unroll
             for (int a = 0; a < A; ++a) {
+              const int64_t f = nfree[(size_t)a * X + x];
+              dead |= (sm[a] > 0 && f < sm[a]);
               if (req[a] > 0 && k > 0) {
-                const int64_t f = nfree[(size_t)a * X + x];
                 if (f < req[a]) k = 0;
                 else if (f < (int64_t)k * req[a]) k = (int)(f / req[a]);
               }
             }
             if (has_ports) k = min(k, 1);
-            kbuf[x] = k;
+            kbuf[pos] = k;
             total += k;
             kmax = max(kmax, k);
+            ndead += dead;
           }
           total = wsum_ll(total);
           kmax = wmax(kmax);
+          sp = wsum(sp);        // live nodes before the cyclic start
+          ndead = wsum(ndead);
+          if (ndead * 4 >= n_live) want_compact = true;
           __syncwarp();
           if (total > 0) {
             int L, rem;
@@ -185,23 +263,23 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
               while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
                 long long f = 0;
-                for (int j = lane; j < n_new; j += 32) f += min(kbuf[Neff + j], mid);
+                for (int pos = lane; pos < n_live; pos += 32) f += min(kbuf[pos], mid);
                 f = wsum_ll(f);
                 if (f <= n) lo = mid; else hi = mid;
               }
               L = lo;
               long long f = 0;
-              for (int j = lane; j < n_new; j += 32) f += min(kbuf[Neff + j], L);
+              for (int pos = lane; pos < n_live; pos += 32) f += min(kbuf[pos], L);
               rem = (int)(n - wsum_ll(f));
             }
             int seen = 0, last_pos = -1, newly = 0, got = 0;
-            for (int base = 0; base < n_new; base += 32) {
-              const int pos = base + lane;
-              const bool in = pos < n_new;
-              int j = s + pos;
-              if (j >= n_new) j -= n_new;
-              const int x = Neff + (in ? j : 0);
-              const int k = in ? kbuf[x] : 0;
+            for (int base = 0; base < n_live; base += 32) {
+              const int i = base + lane;
+              const bool in = i < n_live;
+              int pos = sp + i;
+              if (pos >= n_live) pos -= n_live;
+              const int x = Neff + (in ? live[pos] : 0);
+              const int k = in ? kbuf[pos] : 0;
               const bool extra_c = in && k > L;
               const unsigned m = __ballot_sync(0xffffffffu, extra_c);
               const int rank = seen + __popc(m & ((1u << lane) - 1));
@@ -215,7 +293,7 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
                 if (!nsched[x]) { nsched[x] = 1; newly++; }
                 got += mj;
                 // the pod placed last sits at the furthest position served in the final lap
-                if (rem > 0 ? (extra_c && rank < rem) : (k >= L)) last_pos = pos;
+                if (rem > 0 ? (extra_c && rank < rem) : (k >= L)) last_pos = i;
               }
               if (feeds) log_append(mj > 0, x, spec, mj);
             }
@@ -226,9 +304,9 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
             nodes_with_pods += newly;
             n -= got;
             if (last_pos >= 0) {
-              int jl = s + last_pos;
-              if (jl >= n_new) jl -= n_new;
-              last_index = (N + jl + 1) % list_len;
+              int pl = sp + last_pos;
+              if (pl >= n_live) pl -= n_live;
+              last_index = (N + live[pl] + 1) % list_len;
             }
             __syncwarp();
           }
@@ -273,11 +351,13 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
                 nports[x] = mj > 0 ? pbit : 0ull;
                 nsched[x] = mj > 0;
                 stamp[x] = 0;
+                live[n_live + i] = n_new + i;
               }
               if (feeds) log_append(in && mj > 0, x, spec, mj);
             }
             if (k_new > 0) { nodes_with_pods += add; placed += fill; n -= fill; }
             n_new += add;
+            n_live += add;
             __syncwarp();
           }
         }
@@ -499,8 +579,10 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
             nports[x] = 0ull;
             nsched[x] = 0;
             stamp[x] = 0;
+            live[n_live] = j;
           }
           n_new = j + 1;
+          n_live += 1;
           bool bump = false;
           for (int q = 0; q < nq; ++q) {
             const int en = wd.elig_new[q], dsw = wd.dsw[q];
@@ -550,15 +632,18 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
         (void)n_new_start;
 
         // ---- tryToScheduleOnExistingNodes: per pod, first passing added node in cyclic order ----
-        while (n > 0 && n_new > 0) {
+        while (n > 0 && n_live > 0) {
           const int s = last_index >= N ? last_index - N : 0;
+          int sp = 0;  // lower_bound(live, s): the scan list is ascending
+          { int lo = 0, hi = n_live; while (lo < hi) { const int mid = (lo + hi) >> 1; if (live[mid] < s) lo = mid + 1; else hi = mid; } sp = lo; }
           int found = -1;
-          for (int base = 0; base < n_new && found < 0; base += 32) {
-            const int pos = base + lane;
-            const bool in = pos < n_new;
-            int j = s + pos;
-            if (j >= n_new) j -= n_new;
-            const int x = Neff + (in ? j : 0);
+          for (int base = 0; base < n_live && found < 0; base += 32) {
+            const int i = base + lane;
+            const bool in = i < n_live;
+            int pos = sp + i;
+            if (pos >= n_live) pos -= n_live;
+            const int j = in ? live[pos] : 0;
+            const int x = Neff + j;
             bool ok = false;
             if (in && stamp[x] != cur_stamp) {
               ok = eval(x) == CAE_R_OK;
@@ -670,7 +755,10 @@ int launch_pack(Engine* e) {
   p.dstride = p.has_dyn ? dmax : 1;
   p.log_cap = p.has_dyn ? (int)std::min<size_t>(4 * X + 1024, (size_t)1 << 24) : 1;
   const int A1 = std::max(e->A, 1);
-  size_t per_warp = 16 + X * ((size_t)A1 * 8 + 8 + 4 + 4 + 4 + 1) + (size_t)3 * DYN_MAX_Q * p.dstride * 4 + (size_t)p.log_cap * 12;
+  size_t per_warp = 16 + X * ((size_t)A1 * 8 + 8 + 4 + 4 + 4) + (size_t)3 * DYN_MAX_Q * p.dstride * 4 + (size_t)p.log_cap * 12 + (size_t)cap * 4;
+  per_warp = (per_warp + 7) & ~(size_t)7;
+  p.sufmin_off = per_warp;
+  per_warp += (size_t)A1 * (e->E + 1) * 8 + X;
   per_warp = (per_warp + 255) & ~(size_t)255;
   int warps = std::min(nt, e->sm_count * 16);
   const size_t budget = (size_t)24 << 30;  // keep the slabs within 24 GiB of the 180 GB HBM
