@@ -25,8 +25,8 @@
 namespace cae {
 
 struct PackParams {
-  int E, T, N, U, t_begin, t_end, cap, has_dyn, dstride, log_cap;
-  size_t sufmin_off;
+  int E, T, N, U, t_begin, t_end, cap, has_dyn, dstride, log_cap, nblk;
+  size_t bmax_off;
   const int32_t *order, *order_n;
   const uint8_t* pre_code;
   const int32_t *spec_sc, *spec_dc;
@@ -93,9 +93,11 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
   int32_t* wpres = wcnt + (size_t)DYN_MAX_Q * p.dstride;                              // [DYN_MAX_Q][dstride]
   int32_t* wver = wpres + (size_t)DYN_MAX_Q * p.dstride;                              // [DYN_MAX_Q][dstride] slot version
   int32_t* logbuf = wver + (size_t)DYN_MAX_Q * p.dstride;                             // [log_cap][3]
-  int32_t* live = logbuf + (size_t)p.log_cap * 3;                                     // [cap] added nodes that can still host SOME remaining group, ascending
-  int64_t* sufmin = reinterpret_cast<int64_t*>(slab + p.sufmin_off);                  // [A][E+1] min positive request over the groups still to come
-  uint8_t* nsched = reinterpret_cast<uint8_t*>(sufmin + (size_t)(A > 0 ? A : 1) * (p.E + 1));  // [X]
+  int32_t* bslots = logbuf + (size_t)p.log_cap * 3;                                   // [nblk] upper bound of the pod slots in a 32-node block
+  int32_t* cmw = bslots + p.nblk;                                                     // [nblk/32+2] candidate-block masks of the current group
+  int32_t* kcap = kbuf + Neff;                                                        // capacities of the added nodes for the current group
+  int64_t* bmax = reinterpret_cast<int64_t*>(slab + p.bmax_off);                      // [A][nblk] upper bound of the free capacity in a block
+  uint8_t* nsched = reinterpret_cast<uint8_t*>(bmax + (size_t)(A > 0 ? A : 1) * p.nblk);  // [X]
   int stamp_ctr = hdr[0] + 1, gver_ctr = hdr[1] + 1;
 
   for (;;) {
@@ -113,49 +115,6 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
     int n_new = 0, nodes_with_pods = 0, pods_total = 0, last_index = 0, log_n = 0;
     bool new_nodes_available = true, cl_init = false, overflow = false;
     const int n_groups = p.order_n[t];
-    int n_live = 0;
-    bool want_compact = false;
-    // A node is DEAD once no group still to come can fit: no pod slot left, or some resource that every
-    // remaining group requests is below the smallest such request.  free only shrinks and the suffix
-    // minimum only grows, so dead nodes stay dead and are dropped from the scan list.
-    {
-      const int chunk = (n_groups + 31) / 32;
-      const int g0 = min(lane * chunk, n_groups), g1 = min(g0 + chunk, n_groups);
-      int64_t cm[A > 0 ? A : 1];
-#pragma unroll
-      for (int a = 0; a < A; ++a) cm[a] = LLONG_MAX;
-      for (int gi = g1 - 1; gi >= g0; --gi) {
-        const int sp2 = o.pend_spec[o.group_off[p.order[(size_t)t * p.E + gi]]];
-#pragma unroll
-        for (int a = 0; a < A; ++a) {
-          const int64_t q = o.ps_req[(size_t)sp2 * R + p.act_dim[a]];
-          cm[a] = min(cm[a], q > 0 ? q : 0);
-        }
-      }
-      // exclusive suffix scan of the chunk minima over lanes
-      int64_t tail[A > 0 ? A : 1];
-#pragma unroll
-      for (int a = 0; a < A; ++a) {
-        int64_t v = cm[a];
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-          const int64_t w2 = __shfl_down_sync(0xffffffffu, v, off);
-          if (lane + off < 32) v = min(v, w2);
-        }
-        tail[a] = __shfl_down_sync(0xffffffffu, v, 1);
-        if (lane == 31) tail[a] = LLONG_MAX;
-      }
-      for (int gi = g1 - 1; gi >= g0; --gi) {
-        const int sp2 = o.pend_spec[o.group_off[p.order[(size_t)t * p.E + gi]]];
-#pragma unroll
-        for (int a = 0; a < A; ++a) {
-          const int64_t q = o.ps_req[(size_t)sp2 * R + p.act_dim[a]];
-          tail[a] = min(tail[a], q > 0 ? q : 0);
-          sufmin[(size_t)a * (p.E + 1) + gi] = tail[a];
-        }
-      }
-      __syncwarp();
-    }
 
     // ---- shared helpers -----------------------------------------------------------------------
     auto slot_of = [&](int q, int x) -> int {
@@ -178,6 +137,24 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
       if (log_n > p.log_cap) overflow = true;
     };
 
+    // Per 32-node block of added nodes: upper bounds of the free capacity / pod slots.  free only shrinks, so a
+    // stale bound stays valid; blocks whose bound is below the request are skipped without touching their nodes.
+    auto refresh_block = [&](int b) {  // exact maxima of block b (all lanes)
+      const int j = b * 32 + lane;
+      const bool in = j < n_new;
+      const int x = Neff + (in ? j : 0);
+      int ms = in ? nslots[x] : INT_MIN;
+      ms = wmax(ms);
+#pragma unroll
+      for (int a = 0; a < A; ++a) {
+        long long v = in ? nfree[(size_t)a * X + x] : LLONG_MIN;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, off));
+        if (lane == 0) bmax[(size_t)a * p.nblk + b] = v;
+      }
+      if (lane == 0) bslots[b] = ms;
+    };
+
     for (int gi = 0; gi < n_groups; ++gi) {
       const int g = p.order[(size_t)t * p.E + gi];
       const int pb = o.group_off[g];
@@ -195,91 +172,91 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
       const unsigned long long pbit = has_ports ? (1ull << p.pc_of[plist]) : 0ull;
       const bool feeds = p.has_dyn && d.group_feeds[g];
       int placed = 0;
-      int64_t sm[A > 0 ? A : 1];
-#pragma unroll
-      for (int a = 0; a < A; ++a) sm[a] = sufmin[(size_t)a * (p.E + 1) + gi];
-      auto is_dead = [&](int x) -> bool {
-        bool dead = nslots[x] <= 0;
-#pragma unroll
-        for (int a = 0; a < A; ++a) dead |= (sm[a] > 0 && nfree[(size_t)a * X + x] < sm[a]);
-        return dead;
-      };
-      if (want_compact) {  // stable in-place compaction of the scan list
-        int out = 0;
-        for (int base = 0; base < n_live; base += 32) {
-          const int pos = base + lane;
-          const int j = pos < n_live ? live[pos] : 0;
-          const bool keep = pos < n_live && !is_dead(Neff + j);
-          const unsigned m = __ballot_sync(0xffffffffu, keep);
-          __syncwarp();
-          if (keep) live[out + __popc(m & ((1u << lane) - 1))] = j;
-          out += __popc(m);
-          __syncwarp();
-        }
-        n_live = out;
-        want_compact = false;
-      }
 
       if (dc == 0) {
         // ======================= plain group: closed form =======================================
-        if (n_live > 0 && static_new) {
+        if (n_new > 0 && static_new) {
           const int list_len = N + n_new;
           const int s = last_index >= N ? last_index - N : 0;  // first added node in cyclic scan order
-          long long total = 0;
-          int kmax = 0, sp = 0, ndead = 0;
-          for (int pos = lane; pos < n_live; pos += 32) {
-            const int j = live[pos];
-            const int x = Neff + j;
-            sp += j < s;
-            int k = min(nslots[x], n);
-            if (k > 0 && (nports[x] & pconf)) k = 0;
-            bool dead = nslots[x] <= 0;
+          const int nb = (n_new + 31) >> 5;
+          // candidate blocks: lanes test 32 block summaries at once
+          auto block_may_fit = [&](int b2) -> bool {
+            bool ok = bslots[b2] >= 1;
 #pragma unroll
-            for (int a = 0; a < A; ++a) {
-              const int64_t f = nfree[(size_t)a * X + x];
-              dead |= (sm[a] > 0 && f < sm[a]);
-              if (req[a] > 0 && k > 0) {
-                if (f < req[a]) k = 0;
-                else if (f < (int64_t)k * req[a]) k = (int)(f / req[a]);
+            for (int a = 0; a < A; ++a) ok &= !(req[a] > 0 && bmax[(size_t)a * p.nblk + b2] < req[a]);
+            return ok;
+          };
+          long long total = 0;
+          int kmax = 0;
+          for (int cb = 0; cb < nb; cb += 32) {
+            const int b2 = cb + lane;
+            unsigned cm = __ballot_sync(0xffffffffu, b2 < nb && block_may_fit(b2));
+            if (lane == 0) cmw[cb >> 5] = (int)cm;
+            while (cm) {
+              const int bb = cb + __ffs(cm) - 1;
+              cm &= cm - 1;
+              const int j = bb * 32 + lane;
+              if (j < n_new) {
+                const int x = Neff + j;
+                int k = min(nslots[x], n);
+                if (k > 0 && (nports[x] & pconf)) k = 0;
+#pragma unroll
+                for (int a = 0; a < A; ++a) {
+                  if (req[a] > 0 && k > 0) {
+                    const int64_t f = nfree[(size_t)a * X + x];
+                    if (f < req[a]) k = 0;
+                    else if (f < (int64_t)k * req[a]) k = (int)(f / req[a]);
+                  }
+                }
+                if (has_ports) k = min(k, 1);
+                kcap[j] = k;
+                total += k;
+                kmax = max(kmax, k);
               }
             }
-            if (has_ports) k = min(k, 1);
-            kbuf[pos] = k;
-            total += k;
-            kmax = max(kmax, k);
-            ndead += dead;
           }
           total = wsum_ll(total);
           kmax = wmax(kmax);
-          sp = wsum(sp);        // live nodes before the cyclic start
-          ndead = wsum(ndead);
-          if (ndead * 4 >= n_live) want_compact = true;
           __syncwarp();
           if (total > 0) {
+            auto sum_min = [&](int lim) -> long long {  // sum over candidate blocks of min(k_j, lim)
+              long long f = 0;
+              for (int cb = 0; cb < nb; cb += 32) {
+                unsigned cm = (unsigned)cmw[cb >> 5];
+                while (cm) {
+                  const int bb = cb + __ffs(cm) - 1;
+                  cm &= cm - 1;
+                  const int j = bb * 32 + lane;
+                  if (j < n_new) f += min(kcap[j], lim);
+                }
+              }
+              return wsum_ll(f);
+            };
             int L, rem;
             if (total <= n) { L = kmax; rem = 0; }
             else {
               int lo = 0, hi = kmax;  // f(lo) <= n < f(hi), f(L) = sum min(k_j, L)
               while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
-                long long f = 0;
-                for (int pos = lane; pos < n_live; pos += 32) f += min(kbuf[pos], mid);
-                f = wsum_ll(f);
-                if (f <= n) lo = mid; else hi = mid;
+                if (sum_min(mid) <= n) lo = mid; else hi = mid;
               }
               L = lo;
-              long long f = 0;
-              for (int pos = lane; pos < n_live; pos += 32) f += min(kbuf[pos], L);
-              rem = (int)(n - wsum_ll(f));
+              rem = (int)(n - sum_min(L));
             }
-            int seen = 0, last_pos = -1, newly = 0, got = 0;
-            for (int base = 0; base < n_live; base += 32) {
-              const int i = base + lane;
-              const bool in = i < n_live;
-              int pos = sp + i;
-              if (pos >= n_live) pos -= n_live;
-              const int x = Neff + (in ? live[pos] : 0);
-              const int k = in ? kbuf[pos] : 0;
+            // cyclic walk from node s over the candidate blocks: block(s) is visited twice (its tail first, its head last)
+            int seen = 0, last_dist = -1, newly = 0, got = 0;
+            const int bs = s >> 5;
+            for (int step = 0; step <= nb; ++step) {
+              int bb = bs + step;
+              if (bb >= nb) bb -= nb;
+              if (step == nb) bb = bs;
+              const unsigned cw = (unsigned)cmw[bb >> 5];
+              if (!((cw >> (bb & 31)) & 1u)) continue;
+              const int j = bb * 32 + lane;
+              bool in = j < n_new;
+              if (bb == bs) in = in && (step == 0 ? j >= s : (step == nb && j < s));
+              const int x = Neff + (j < n_new ? j : 0);
+              const int k = in ? kcap[j] : 0;
               const bool extra_c = in && k > L;
               const unsigned m = __ballot_sync(0xffffffffu, extra_c);
               const int rank = seen + __popc(m & ((1u << lane) - 1));
@@ -293,20 +270,22 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
                 if (!nsched[x]) { nsched[x] = 1; newly++; }
                 got += mj;
                 // the pod placed last sits at the furthest position served in the final lap
-                if (rem > 0 ? (extra_c && rank < rem) : (k >= L)) last_pos = i;
+                if (rem > 0 ? (extra_c && rank < rem) : (k >= L)) { int dd = j - s; if (dd < 0) dd += n_new; last_dist = dd; }
               }
               if (feeds) log_append(mj > 0, x, spec, mj);
+              __syncwarp();
+              refresh_block(bb);  // tighten the bounds of a block we touched
             }
             got = wsum(got);
             newly = wsum(newly);
-            last_pos = wmax(last_pos);
+            last_dist = wmax(last_dist);
             placed += got;
             nodes_with_pods += newly;
             n -= got;
-            if (last_pos >= 0) {
-              int pl = sp + last_pos;
-              if (pl >= n_live) pl -= n_live;
-              last_index = (N + live[pl] + 1) % list_len;
+            if (last_dist >= 0) {
+              int jl = s + last_dist;
+              if (jl >= n_new) jl -= n_new;
+              last_index = (N + jl + 1) % list_len;
             }
             __syncwarp();
           }
@@ -351,13 +330,14 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
                 nports[x] = mj > 0 ? pbit : 0ull;
                 nsched[x] = mj > 0;
                 stamp[x] = 0;
-                live[n_live + i] = n_new + i;
               }
               if (feeds) log_append(in && mj > 0, x, spec, mj);
             }
             if (k_new > 0) { nodes_with_pods += add; placed += fill; n -= fill; }
+            const int b_first = n_new >> 5;
             n_new += add;
-            n_live += add;
+            __syncwarp();
+            if (add > 0) for (int b2 = b_first; b2 <= (n_new - 1) >> 5; ++b2) refresh_block(b2);
             __syncwarp();
           }
         }
@@ -579,10 +559,16 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
             nports[x] = 0ull;
             nsched[x] = 0;
             stamp[x] = 0;
-            live[n_live] = j;
+            const int b2 = j >> 5;
+            const bool first = (j & 31) == 0;
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+              const int64_t old = bmax[(size_t)a * p.nblk + b2];
+              bmax[(size_t)a * p.nblk + b2] = (first || tfree[a] > old) ? tfree[a] : old;
+            }
+            bslots[b2] = first ? tslots : max(bslots[b2], tslots);
           }
           n_new = j + 1;
-          n_live += 1;
           bool bump = false;
           for (int q = 0; q < nq; ++q) {
             const int en = wd.elig_new[q], dsw = wd.dsw[q];
@@ -632,18 +618,23 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
         (void)n_new_start;
 
         // ---- tryToScheduleOnExistingNodes: per pod, first passing added node in cyclic order ----
-        while (n > 0 && n_live > 0) {
+        while (n > 0 && n_new > 0) {
           const int s = last_index >= N ? last_index - N : 0;
-          int sp = 0;  // lower_bound(live, s): the scan list is ascending
-          { int lo = 0, hi = n_live; while (lo < hi) { const int mid = (lo + hi) >> 1; if (live[mid] < s) lo = mid + 1; else hi = mid; } sp = lo; }
+          const int nb = (n_new + 31) >> 5, bs = s >> 5;
           int found = -1;
-          for (int base = 0; base < n_live && found < 0; base += 32) {
-            const int i = base + lane;
-            const bool in = i < n_live;
-            int pos = sp + i;
-            if (pos >= n_live) pos -= n_live;
-            const int j = in ? live[pos] : 0;
-            const int x = Neff + j;
+          // cyclic order from node s, block by block; block(s) is visited twice (tail first, head last)
+          for (int step = 0; step <= nb && found < 0; ++step) {
+            int bb = bs + step;
+            if (bb >= nb) bb -= nb;
+            if (step == nb) bb = bs;
+            bool may = bslots[bb] >= 1;  // block bounds: nothing in this block can take the pod (uniform)
+#pragma unroll
+            for (int a = 0; a < A; ++a) may &= !(req[a] > 0 && bmax[(size_t)a * p.nblk + bb] < req[a]);
+            if (!may) continue;
+            const int j = bb * 32 + lane;
+            bool in = j < n_new;
+            if (bb == bs) in = in && (step == 0 ? j >= s : (step == nb && j < s));
+            const int x = Neff + (j < n_new ? j : 0);
             bool ok = false;
             if (in && stamp[x] != cur_stamp) {
               ok = eval(x) == CAE_R_OK;
@@ -755,10 +746,11 @@ int launch_pack(Engine* e) {
   p.dstride = p.has_dyn ? dmax : 1;
   p.log_cap = p.has_dyn ? (int)std::min<size_t>(4 * X + 1024, (size_t)1 << 24) : 1;
   const int A1 = std::max(e->A, 1);
-  size_t per_warp = 16 + X * ((size_t)A1 * 8 + 8 + 4 + 4 + 4) + (size_t)3 * DYN_MAX_Q * p.dstride * 4 + (size_t)p.log_cap * 12 + (size_t)cap * 4;
+  p.nblk = (cap + 31) / 32 + 1;
+  size_t per_warp = 16 + X * ((size_t)A1 * 8 + 8 + 4 + 4 + 4) + (size_t)3 * DYN_MAX_Q * p.dstride * 4 + (size_t)p.log_cap * 12 + (size_t)(p.nblk + p.nblk / 32 + 2) * 4;
   per_warp = (per_warp + 7) & ~(size_t)7;
-  p.sufmin_off = per_warp;
-  per_warp += (size_t)A1 * (e->E + 1) * 8 + X;
+  p.bmax_off = per_warp;
+  per_warp += (size_t)A1 * p.nblk * 8 + X;
   per_warp = (per_warp + 255) & ~(size_t)255;
   int warps = std::min(nt, e->sm_count * 16);
   const size_t budget = (size_t)24 << 30;  // keep the slabs within 24 GiB of the 180 GB HBM
