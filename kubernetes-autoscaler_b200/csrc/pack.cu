@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
               const int bb = cb + __ffs(cm) - 1;
               cm &= cm - 1;
               const int j = bb * 32 + lane;
+              int kblk = 0;
               if (j < n_new) {
                 const int x = Neff + j;
                 int k = min(nslots[x], n);
@@ -212,6 +213,13 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
                 kcap[j] = k;
                 total += k;
                 kmax = max(kmax, k);
+                kblk = k;
+              }
+              // a candidate block that cannot take a single pod had a stale bound: tighten it so that the
+              // following groups skip it without touching its nodes
+              if (__ballot_sync(0xffffffffu, kblk > 0) == 0u) {
+                refresh_block(bb);
+                if (lane == 0) cmw[cb >> 5] &= ~(1 << (bb - cb));
               }
             }
           }
@@ -273,8 +281,6 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
                 if (rem > 0 ? (extra_c && rank < rem) : (k >= L)) { int dd = j - s; if (dd < 0) dd += n_new; last_dist = dd; }
               }
               if (feeds) log_append(mj > 0, x, spec, mj);
-              __syncwarp();
-              refresh_block(bb);  // tighten the bounds of a block we touched
             }
             got = wsum(got);
             newly = wsum(newly);
@@ -337,7 +343,18 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
             const int b_first = n_new >> 5;
             n_new += add;
             __syncwarp();
-            if (add > 0) for (int b2 = b_first; b2 <= (n_new - 1) >> 5; ++b2) refresh_block(b2);
+            if (add > 0) {  // loose but valid bounds for the blocks that received nodes; tightened lazily
+              for (int b2 = b_first + lane; b2 <= (n_new - 1) >> 5; b2 += 32) {
+                const bool fresh_blk = b2 > b_first || (b_first << 5) == n_new - add;
+#pragma unroll
+                for (int a = 0; a < A; ++a) {
+                  const int64_t old = fresh_blk ? LLONG_MIN : bmax[(size_t)a * p.nblk + b2];
+                  bmax[(size_t)a * p.nblk + b2] = tfree[a] > old ? tfree[a] : old;
+                }
+                const int olds = fresh_blk ? INT_MIN : bslots[b2];
+                bslots[b2] = tslots > olds ? tslots : olds;
+              }
+            }
             __syncwarp();
           }
         }
