@@ -1,0 +1,146 @@
+"""Randomised parity: small random snapshots built through the string-world object model (random
+tolerations, selectors, host ports, spread constraints, pod (anti)affinity, resident pods, caps)
+must give bit-identical dense reasons, Estimate() results and expander sets on the engine and the
+CPU oracle.  Seeds are fixed: a failure reproduces."""
+import random
+
+import numpy as np
+import pytest
+
+from kubernetes_autoscaler_b200.encode import encode
+from kubernetes_autoscaler_b200.objects import (BuildTestNode, BuildTestPod, HostPort, LabelSelector, Namespace, NodeInfo,
+                                                NodeSelectorTerm, PodAffinityTerm, Requirement, Taint, Toleration,
+                                                TopologySpreadConstraint, makePodEquivalenceGroup)
+
+pytestmark = pytest.mark.gpu
+HOST, ZONE = "kubernetes.io/hostname", "topology.kubernetes.io/zone"
+APPS = ["a", "b", "c", "d"]
+ZONES = ["z1", "z2", "z3"]
+POOLS = ["p1", "p2"]
+NSS = ["default", "other"]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import __graft_entry__ as g
+    g.build()
+    from kubernetes_autoscaler_b200.engine import Engine
+    e = Engine(device=0, want_reasons=True)
+    yield e
+    e.close()
+
+
+def _rand_selector(rng):
+    kind = rng.random()
+    if kind < 0.08:
+        return None
+    if kind < 0.16:
+        return LabelSelector()
+    if kind < 0.75:
+        return LabelSelector(match_labels={"app": rng.choice(APPS)})
+    op = rng.choice(["In", "NotIn", "Exists", "DoesNotExist"])
+    vals = rng.sample(APPS, rng.randint(1, 2)) if op in ("In", "NotIn") else []
+    return LabelSelector(match_expressions=[Requirement("app", op, vals)])
+
+
+def _rand_node(rng, name, template):
+    n = BuildTestNode(name, rng.choice([1000, 2000, 4000, 8000]), rng.choice([2, 4, 8, 16]) << 30)
+    n.allocatable["pods"] = rng.choice([3, 5, 8, 110])
+    n.labels = {HOST: name}
+    if rng.random() < 0.9:
+        n.labels[ZONE] = rng.choice(ZONES)
+    if rng.random() < 0.7:
+        n.labels["pool"] = rng.choice(POOLS)
+    if rng.random() < 0.3:
+        n.labels["gen"] = str(rng.randint(1, 9))
+    if rng.random() < 0.25:
+        n.taints.append(Taint("dedicated", rng.choice(["x", "y"]), rng.choice(["NoSchedule", "NoExecute", "PreferNoSchedule"])))
+    if rng.random() < 0.1:
+        n.unschedulable = not template
+    if rng.random() < 0.2:
+        n.allocatable["nvidia.com/gpu"] = rng.choice([1, 4])
+        n.capacity["nvidia.com/gpu"] = n.allocatable["nvidia.com/gpu"]
+    return n
+
+
+def _rand_pod(rng, name):
+    p = BuildTestPod(name, rng.choice([0, 100, 250, 500, 1000, 3000]), rng.choice([0, 1 << 28, 1 << 30, 3 << 30]))
+    p.namespace = rng.choice(NSS)
+    p.labels = {"app": rng.choice(APPS)}
+    if rng.random() < 0.3:
+        p.labels["tier"] = rng.choice(["fe", "be"])
+    if rng.random() < 0.15:
+        p.requests["nvidia.com/gpu"] = rng.choice([1, 2])
+    if rng.random() < 0.3:
+        p.tolerations.append(Toleration("dedicated", rng.choice(["Equal", "Exists"]), rng.choice(["x", "y"]),
+                                        rng.choice(["", "NoSchedule", "NoExecute"])))
+    if rng.random() < 0.05:
+        p.tolerations.append(Toleration("", "Exists", "", ""))
+    if rng.random() < 0.2:
+        p.node_selector = {"pool": rng.choice(POOLS)}
+    if rng.random() < 0.15:
+        op = rng.choice(["In", "NotIn", "Exists", "Gt", "Lt"])
+        key = "gen" if op in ("Gt", "Lt") else rng.choice(["pool", ZONE])
+        vals = {"In": [rng.choice(POOLS + ZONES)], "NotIn": [rng.choice(POOLS + ZONES)], "Exists": [], "Gt": ["4"], "Lt": ["6"]}[op]
+        p.node_affinity_terms = [NodeSelectorTerm([Requirement(key, op, vals)])]
+    if rng.random() < 0.15:
+        p.host_ports = [HostPort(rng.choice([80, 443]), rng.choice(["TCP", "UDP"]), rng.choice(["", "10.0.0.1"]))]
+    if rng.random() < 0.35:
+        for _ in range(rng.randint(1, 2)):
+            p.topology_spread.append(TopologySpreadConstraint(
+                max_skew=rng.randint(1, 3), topology_key=rng.choice([HOST, ZONE, ZONE, "pool"]),
+                label_selector=_rand_selector(rng), min_domains=rng.choice([None, 1, 2, 4]),
+                when_unsatisfiable=rng.choice(["DoNotSchedule", "DoNotSchedule", "ScheduleAnyway"]),
+                node_affinity_policy=rng.choice([None, "Honor", "Ignore"]), node_taints_policy=rng.choice([None, "Honor", "Ignore"])))
+    def term():
+        return PodAffinityTerm(_rand_selector(rng), rng.choice([HOST, ZONE, "pool"]),
+                               namespaces=rng.choice([[], [], ["other"], ["default", "other"]]),
+                               namespace_selector=rng.choice([None, None, LabelSelector(), LabelSelector(match_labels={"team": "a"})]))
+    if rng.random() < 0.2:
+        p.pod_affinity = [term() for _ in range(rng.randint(1, 2))]
+    if rng.random() < 0.25:
+        p.pod_anti_affinity = [term() for _ in range(rng.randint(1, 2))]
+    return p
+
+
+def _scenario(seed):
+    rng = random.Random(seed)
+    residents = [_rand_pod(rng, "r%d" % i) for i in range(6)]
+    for r in residents:
+        r.requests = {"cpu": 100, "memory": 1 << 26}
+        r.host_ports = []
+        if rng.random() < 0.1:
+            r.terminating = True
+    cluster = [NodeInfo(_rand_node(rng, "c%d" % i, False), [rng.choice(residents) for _ in range(rng.randint(0, 3))])
+               for i in range(rng.randint(0, 6))]
+    ds = BuildTestPod("ds", 50, 1 << 24)
+    ds.labels = {"app": rng.choice(APPS)}
+    ds.tolerations = [Toleration("", "Exists", "", "")]
+    templates = [NodeInfo(_rand_node(rng, "t%d" % i, True), [ds] if rng.random() < 0.5 else []) for i in range(rng.randint(1, 5))]
+    groups = [makePodEquivalenceGroup(_rand_pod(rng, "p%d" % i), rng.randint(1, 9)) for i in range(rng.randint(1, 8))]
+    namespaces = [Namespace("other", {"team": "a"})] if rng.random() < 0.5 else []
+    caps = [rng.choice([0, 0, 1, 2, 5, -1]) for _ in templates]
+    return cluster, templates, groups, namespaces, caps
+
+
+@pytest.mark.parametrize("block", range(8))
+def test_random_scenarios(eng, oracle, block):
+    from kubernetes_autoscaler_b200.engine import unpack_bits
+    for seed in range(block * 25, block * 25 + 25):
+        cluster, templates, groups, namespaces, caps = _scenario(1000 + seed)
+        enc = encode(cluster, templates, groups, namespaces=namespaces)
+        eng.load(enc)
+        bits, reasons, count = eng.feasibility()
+        want, _ = oracle.feasibility_dense(enc)
+        assert np.array_equal(reasons, want), "seed %d dense reasons" % seed
+        assert np.array_equal(unpack_bits(bits, enc.P), want == 0), "seed %d" % seed
+        assert np.array_equal(count, (want == 0).sum(axis=1)), "seed %d" % seed
+        caps_a = np.asarray(caps, np.int32)
+        nc, pc, sched, order = eng.estimate_all(caps_a)
+        onc, opc, osched, oorder, _ = oracle.estimate_all(enc, caps_a)
+        assert np.array_equal(nc, onc), "seed %d node counts %s vs %s" % (seed, nc, onc)
+        assert np.array_equal(pc, opc), "seed %d pod counts" % seed
+        assert np.array_equal(sched, osched) and np.array_equal(order, oorder), "seed %d sched/order" % seed
+        mask, waste = eng.expander_best([0, 1, 2], nc, pc)
+        omask, owaste = oracle.expander(enc, [0, 1, 2], nc, pc, sched)
+        assert np.array_equal(mask, omask) and np.array_equal(waste, owaste), "seed %d expander" % seed
