@@ -123,6 +123,8 @@ def main():
     ap.add_argument("--templates", type=int, default=None)
     ap.add_argument("--decision", action="store_true", help="reference arm: time full scale-up decisions (oracle) instead")
     ap.add_argument("--no-decision", action="store_true", help="engine arm: skip the secondary decision-latency figure")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="N>1: how the int32[T] fit histogram is reduced: fused P2P atomics in the kernel's last block, or NCCL")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -209,7 +211,18 @@ def main():
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     count_t = None
-    if world > 1:
+    fused = False
+    if world > 1 and args.collective == "peer":
+        try:
+            handles = [None] * world
+            dist.all_gather_object(handles, eng.peer_handle())
+            eng.peer_attach(handles)
+            dist.barrier()
+            fused = True
+        except Exception as ex:   # no P2P between these devices: fall back to the NCCL all-reduce
+            if rank == 0:
+                print("peer exchange unavailable (%r); using NCCL" % (ex,), file=sys.stderr)
+    if world > 1 and not fused:
         ptr, nbytes = eng.device_buffer(0)
 
         class _Wrap:
@@ -353,7 +366,8 @@ def main():
         "vs_baseline": None, "dtype": "int64", "data": "synthetic",
         "config": {"workload": workload, "global_pods": P1 * world, "templates": T, "parallelism": "pods sharded x%d" % world,
                    "l2": "flushed between timed iterations (512 MiB memset)"},
-        "kernel_ms": kern_ms, "allreduce_ms": allreduce_ms, "wall_ms_per_step": float(np.mean(wall_ms)), "clocks": _clocks_summary(samples),
+        "kernel_ms": kern_ms, "allreduce_ms": allreduce_ms,
+        "collective": ("none" if world == 1 else ("fused P2P atomics over NVLink (peer memory)" if fused else "NCCL all_reduce int32[T]")), "wall_ms_per_step": float(np.mean(wall_ms)), "clocks": _clocks_summary(samples),
         "e2e": {"value": (P1 * world) * T / (e2e_step * 1e-3), "unit": "evals/s", "ms_per_step": e2e_step,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "decision_latency": decision}))

@@ -144,6 +144,10 @@ def load_engine_lib() -> C.CDLL:
     lib.cae_expander_best.restype = C.c_int32
     lib.cae_get_stats.argtypes = [C.c_void_p, P(cae_stats)]
     lib.cae_get_stats.restype = C.c_int32
+    lib.cae_peer_handle.argtypes = [C.c_void_p, C.c_void_p]
+    lib.cae_peer_handle.restype = C.c_int32
+    lib.cae_peer_attach.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    lib.cae_peer_attach.restype = C.c_int32
     lib.cae_device_buffer.argtypes = [C.c_void_p, C.c_int32, P(C.c_size_t)]
     lib.cae_device_buffer.restype = C.c_void_p
     _engine_lib = lib

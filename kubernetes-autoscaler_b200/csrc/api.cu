@@ -484,6 +484,9 @@ int32_t cae_feasibility(cae_engine* h, uint32_t* fit_bits, uint8_t* reasons, int
     e->stats.d2h_bytes += sizeof(int32_t) * e->T;
   }
   cudaEventRecord(c1, e->stream);
+  int32_t peer_status = 0;
+  if (e->peer_world > 1)
+    CAE_CUDA(cudaMemcpyAsync(&peer_status, e->d_xbuf + (size_t)2 * Engine::PEER_CAP + 9, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
   CAE_CUDA(cudaStreamSynchronize(e->stream));
   float ms = 0;
   cudaEventElapsedTime(&ms, e->ev0, e->ev1);
@@ -492,6 +495,7 @@ int32_t cae_feasibility(cae_engine* h, uint32_t* fit_bits, uint8_t* reasons, int
   e->stats.d2h_ms = ms;
   cudaEventDestroy(c0); cudaEventDestroy(c1);
   e->stats.evals = (int64_t)e->Pl * e->T;
+  if (peer_status) { cae::set_error("peer exchange timed out: a rank did not contribute its histogram"); return -1; }
   return 0;
 }
 
@@ -639,6 +643,44 @@ void* cae_device_buffer(cae_engine* h, int32_t which, size_t* bytes) {
   if (which == 0) { if (bytes) *bytes = sizeof(int32_t) * e->T; return e->d_fit_count; }
   if (which == 1) { if (bytes) *bytes = sizeof(int32_t) * 2 * e->T; return e->d_counts2; }
   return nullptr;
+}
+
+static int ensure_xbuf(Engine* e) {
+  if (e->d_xbuf) return 0;
+  const size_t n = (size_t)2 * Engine::PEER_CAP + 16;
+  CAE_CUDA(cudaMalloc(&e->d_xbuf, n * sizeof(int32_t)));
+  CAE_CUDA(cudaMemset(e->d_xbuf, 0, n * sizeof(int32_t)));
+  return 0;
+}
+
+int32_t cae_peer_handle(cae_engine* h, void* handle) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (!e || !handle) return -2;
+  cudaSetDevice(e->cfg.device);
+  if (ensure_xbuf(e)) return -1;
+  static_assert(sizeof(cudaIpcMemHandle_t) == CAE_PEER_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t hd;
+  CAE_CUDA(cudaIpcGetMemHandle(&hd, e->d_xbuf));
+  memcpy(handle, &hd, sizeof(hd));
+  return 0;
+}
+
+int32_t cae_peer_attach(cae_engine* h, const void* handles, int32_t world) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (!e || !handles) return -2;
+  if (world < 1 || world > Engine::PEER_MAX || world != e->cfg.world_size) { cae::set_error("cae_peer_attach: bad world size"); return -2; }
+  cudaSetDevice(e->cfg.device);
+  if (ensure_xbuf(e)) return -1;
+  for (int r = 0; r < world; ++r) {
+    if (r == e->cfg.rank) { e->peer_base[r] = e->d_xbuf; continue; }
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, static_cast<const char*>(handles) + (size_t)r * CAE_PEER_HANDLE_BYTES, sizeof(hd));
+    void* p = nullptr;
+    CAE_CUDA(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    e->peer_base[r] = static_cast<int32_t*>(p);
+  }
+  e->peer_world = world;
+  return 0;
 }
 
 void* cae_host_alloc(size_t bytes) {

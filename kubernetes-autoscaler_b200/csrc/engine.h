@@ -120,6 +120,13 @@ struct Engine {
   void* d_pack_scratch = nullptr;
   size_t pack_scratch_bytes = 0;
   size_t pack_layout_sig = 0;
+  // fused histogram exchange over peer memory (feas.cu)
+  static constexpr int PEER_MAX = 8, PEER_CAP = 1 << 16;
+  int32_t* d_xbuf = nullptr;              // [2][PEER_CAP] accumulators + [2] arrival counters (+ done counter)
+  int peer_world = 0;
+  int32_t* peer_base[PEER_MAX] = {nullptr};
+  int64_t peer_uses[2] = {0, 0};
+  int64_t peer_step = 0;
   int32_t* d_work_counter = nullptr;
   // host copies needed by host-side steps
   std::vector<int32_t> h_group_off, h_pend_spec;

@@ -46,6 +46,37 @@ constexpr int K1_TCHUNK = K1_TW * 32;
 constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int K1_PAD = K1_TCHUNK + 4;
 
+// Fused exchange of the fit histogram over peer memory (see cae_peer_attach in include/caengine.h)
+struct PeerPush {
+  int world;                 // 0 = disabled
+  int32_t* accum[8];         // every rank's accumulator slot for this step (P2P-mapped)
+  int32_t* arrive[8];        // every rank's arrival counter of that slot
+  int32_t* done_ctr;         // local: thread blocks finished
+};
+
+// Publishes the all-reduced histogram once every rank's contribution has arrived, and clears the slot.
+__global__ void peer_wait_kernel(int32_t* __restrict__ accum, volatile int32_t* arrive, int target, int T,
+                                 int32_t* __restrict__ fit_count, int32_t* __restrict__ status) {
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    int ok = 1;
+    while (*arrive < target) {
+      if (clock64() - t0 > 4000000000ll) { ok = 0; break; }  // ~2 s: a peer died; fail instead of hanging the GPU
+      __nanosleep(200);
+    }
+    __threadfence_system();
+    s_ok = ok;
+    if (!ok) atomicExch(status, 1);
+  }
+  __syncthreads();
+  if (!s_ok) return;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    fit_count[t] = __ldcg(&accum[t]);
+    accum[t] = 0;
+  }
+}
+
 struct FeasLayout {
   uint32_t fstart;           // bit b: slice b starts a field
   int nb;                    // real slices (the rest is zero padding)
@@ -72,7 +103,7 @@ feasibility_kernel(int Pl, int Plw, int T, int Tw, int N, int U, int W, FeasLayo
                    const uint32_t* __restrict__ pre_ok, const uint32_t* __restrict__ post_ok,
                    const uint8_t* __restrict__ pre_code, const uint8_t* __restrict__ post_code,
                    uint32_t* __restrict__ fit_bits, int32_t* __restrict__ fit_count,
-                   uint8_t* __restrict__ reasons) {
+                   uint8_t* __restrict__ reasons, PeerPush pp) {
   __shared__ uint32_t s_sl[B > 0 ? B : 1][K1_TW];
   __shared__ uint32_t s_out[K1_WARPS][K1_PAD];
   __shared__ int32_t s_cnt[K1_TCHUNK];
@@ -147,6 +178,29 @@ feasibility_kernel(int Pl, int Plw, int T, int Tw, int N, int U, int W, FeasLayo
     const int c = s_cnt[i];
     if (c && t0 + i < T) atomicAdd(&fit_count[t0 + i], c);
   }
+  if (pp.world) {
+    // the LAST thread block to finish owns the complete local histogram: it adds it into every rank's
+    // exchange buffer over NVLink (system-scope atomics on peer memory), then signals arrival
+    __shared__ int s_last;
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      s_last = atomicAdd(pp.done_ctr, 1) == (int)(gridDim.x * gridDim.y) - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      for (int t = tid; t < T; t += K1_THREADS) {
+        const int v = __ldcg(&fit_count[t]);
+        if (v)
+          for (int r = 0; r < pp.world; ++r) atomicAdd_system(pp.accum[r] + t, v);
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (tid < pp.world) atomicAdd_system(pp.arrive[tid], 1);
+      if (tid == 0) *pp.done_ctr = 0;
+    }
+  }
 }
 
 template <int B>
@@ -157,15 +211,35 @@ static void launch_feas_b(Engine* e, bool want_reasons) {
   lay.fstart = e->feas_fstart;
   lay.nb = e->feas_B;
   for (int b = 0; b < 32; ++b) { lay.sword[b] = e->feas_sword[b]; lay.sshift[b] = e->feas_sshift[b]; }
+  PeerPush pp{};
+  if (e->peer_world > 1 && e->T <= Engine::PEER_CAP) {
+    const int slot = (int)(e->peer_step & 1);
+    pp.world = e->peer_world;
+    for (int r = 0; r < e->peer_world; ++r) {
+      pp.accum[r] = e->peer_base[r] + (size_t)slot * Engine::PEER_CAP;
+      pp.arrive[r] = e->peer_base[r] + (size_t)2 * Engine::PEER_CAP + slot;
+    }
+    pp.done_ctr = e->d_xbuf + (size_t)2 * Engine::PEER_CAP + 8;
+  }
   if (want_reasons)
     feasibility_kernel<B, true><<<grid, K1_THREADS, 0, e->stream>>>(
         e->Pl, e->Plw, e->T, e->Tw, e->N, e->U, e->W, lay, e->d_pod_w, e->d_pod_sc, e->d_pod_dc, e->d_tslice, e->d_tmpl_slots,
-        e->d_pre_ok, e->d_post_ok, e->d_pre_code, e->d_post_code, e->d_fit_bits, e->d_fit_count, e->d_reasons);
+        e->d_pre_ok, e->d_post_ok, e->d_pre_code, e->d_post_code, e->d_fit_bits, e->d_fit_count, e->d_reasons, pp);
   else
     feasibility_kernel<B, false><<<grid, K1_THREADS, 0, e->stream>>>(
         e->Pl, e->Plw, e->T, e->Tw, e->N, e->U, e->W, lay, e->d_pod_w, e->d_pod_sc, e->d_pod_dc, e->d_tslice, e->d_tmpl_slots,
-        e->d_pre_ok, e->d_post_ok, e->d_pre_code, e->d_post_code, e->d_fit_bits, e->d_fit_count, e->d_reasons);
+        e->d_pre_ok, e->d_post_ok, e->d_pre_code, e->d_post_code, e->d_fit_bits, e->d_fit_count, e->d_reasons, pp);
   e->stats.kernel_launches++;
+  if (pp.world) {
+    const int slot = (int)(e->peer_step & 1);
+    e->peer_uses[slot] += 1;
+    e->peer_step += 1;
+    peer_wait_kernel<<<1, 256, 0, e->stream>>>(e->d_xbuf + (size_t)slot * Engine::PEER_CAP,
+                                               e->d_xbuf + (size_t)2 * Engine::PEER_CAP + slot,
+                                               (int)(e->peer_uses[slot] * e->peer_world), e->T, e->d_fit_count,
+                                               e->d_xbuf + (size_t)2 * Engine::PEER_CAP + 9);
+    e->stats.kernel_launches++;
+  }
 }
 
 int launch_feasibility(Engine* e, bool want_reasons) {

@@ -175,6 +175,17 @@ class Engine:
         self._check(self.lib.cae_expander_best(self.h, vp(ch), len(ch), vp(nc), vp(pc), vp(sc), vp(mask), vp(waste)))
         return mask, waste
 
+    # ---- fused histogram exchange over peer memory (multi-GPU dense pass) -------------------------
+    def peer_handle(self) -> bytes:
+        buf = C.create_string_buffer(capi.CONST["CAE_PEER_HANDLE_BYTES"])
+        self._check(self.lib.cae_peer_handle(self.h, buf))
+        return buf.raw
+
+    def peer_attach(self, handles: Sequence[bytes]) -> None:
+        blob = b"".join(handles)
+        assert len(blob) == capi.CONST["CAE_PEER_HANDLE_BYTES"] * self.world_size
+        self._check(self.lib.cae_peer_attach(self.h, C.create_string_buffer(blob, len(blob)), self.world_size))
+
     def stats(self) -> capi.cae_stats:
         s = capi.cae_stats()
         self._check(self.lib.cae_get_stats(self.h, C.byref(s)))
