@@ -166,7 +166,7 @@ static int build_dynamic(Engine* e, const cae_objects* o, const std::vector<uint
       for (int t = o->aff_off[fl]; t < o->aff_off[fl + 1]; ++t) add_q(Q_AFF, kidx(o->aterm_key[t]), t);
       for (int t = o->aff_off[al]; t < o->aff_off[al + 1]; ++t) add_q(Q_ANTI, kidx(o->aterm_key[t]), t);
       for (int key2 : exist_keys) add_q(Q_EXIST, kidx(key2), -1);
-      if ((int)q_kind.size() - dc_q_off.back() > DYN_MAX_Q) { set_error("a pod needs more than 8 topology counters"); return 1; }
+      if ((int)q_kind.size() - dc_q_off.back() > DYN_MAX_Q) { set_error("a pod needs more than 12 topology counters"); return 1; }
       dc_q_off.push_back((int)q_kind.size());
     }
     spec_dc[s] = it->second;

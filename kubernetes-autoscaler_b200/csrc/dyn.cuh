@@ -20,7 +20,7 @@
 namespace cae {
 
 constexpr int DYN_MAX_KEYS = 8;
-constexpr int DYN_MAX_Q = 8;  // counters per dynamic class
+constexpr int DYN_MAX_Q = 12;  // counters per dynamic class
 enum { Q_PTS = 0, Q_AFF = 1, Q_ANTI = 2, Q_EXIST = 3 };
 
 struct DynTables {
