@@ -318,8 +318,15 @@ def main():
     alg_bytes = Pl * (4 * Wd + 8) + T * 4 * Wd + Pl * T // 8 + 4 * T
     peak, peak_src = _peak_hbm()
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload, one `ncu --set full` capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k1_traffic.json")))
+        if args.config == 2 and P1 == 100_000 and T == 1000:
+            traffic = int(tj["dram__bytes_read.sum"]) + int(tj["dram__bytes_write.sum"])
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "feasibility_kernel", "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
+                "traffic": traffic, "kernel": "feasibility_kernel", "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                 "note": "integer-issue bound by design: ~1 bit of compulsory HBM traffic per evaluation (DESIGN.md §K1)"}
 
     # ---- CPU baseline: the oracle on this box's cores, bounded sample of the same workload ---------------

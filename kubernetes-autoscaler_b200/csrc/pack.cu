@@ -769,7 +769,7 @@ int launch_pack(Engine* e) {
   p.bmax_off = per_warp;
   per_warp += (size_t)A1 * p.nblk * 8 + X;
   per_warp = (per_warp + 255) & ~(size_t)255;
-  int warps = std::min(nt, e->sm_count * 16);
+  int warps = std::min(nt, e->sm_count * 20);
   const size_t budget = (size_t)24 << 30;  // keep the slabs within 24 GiB of the 180 GB HBM
   if (per_warp * warps > budget) warps = (int)std::max<size_t>(1, budget / per_warp);
   int blocks = (warps + PACK_WARPS - 1) / PACK_WARPS;
