@@ -101,6 +101,9 @@ class Pod:
     terminating: bool = False
     # engine-unsupported features the flattener must route to the stock path (SURVEY §7 hard part 7)
     has_volumes_or_claims: bool = False
+    # controller reference (drain.ControllerRef): only equivalence.BuildPodGroups reads it
+    owner_uid: str = ""
+    owner_kind: str = ""
 
     def clone(self) -> "Pod":
         return copy.deepcopy(self)
