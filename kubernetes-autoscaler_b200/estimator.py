@@ -153,6 +153,16 @@ class Option:
     pods: List[Pod]
 
 
+def apply_zero_or_max(node_count: int, pods: List[Pod], max_size: int, all_or_nothing: bool) -> Tuple[int, List[Pod]]:
+    """ComputeExpansionOption's special case for groups that only scale from zero to max
+    (core/scaleup/orchestrator/orchestrator.go:505-517)."""
+    if all_or_nothing and node_count > max_size:
+        return 0, []          # capping would strand pods: violates all-or-nothing
+    if node_count > 0:
+        node_count = max_size  # the only valid size
+    return node_count, pods
+
+
 class ScaleUpSimulation:
     """All node groups of one autoscaler tick through the engine in one pass."""
 
@@ -169,8 +179,10 @@ class ScaleUpSimulation:
         reasons = self.engine.feasibility_groups()
         return {ng: [g for g in range(len(self.groups)) if reasons[t][g] == 0] for t, ng in enumerate(self.ids)}
 
-    def compute_expansion_options(self, max_nodes: Optional[Dict[str, int]] = None) -> List[Option]:
-        """orchestrator.go:462-520 for every node group (options with no pods are dropped, :150-157)."""
+    def compute_expansion_options(self, max_nodes: Optional[Dict[str, int]] = None,
+                                  zero_or_max: Optional[Dict[str, int]] = None, all_or_nothing: bool = False) -> List[Option]:
+        """orchestrator.go:462-520 for every node group (options with no pods are dropped, :150-157).
+        zero_or_max: node-group id -> MaxSize for groups with ZeroOrMaxNodeScaling."""
         mn = [0 if max_nodes is None else max_nodes.get(ng, 0) for ng in self.ids]
         self.node_count, self.pod_count, self.sched, self.order = self.engine.estimate_all(mn)
         out = []
@@ -180,8 +192,11 @@ class ScaleUpSimulation:
                 if g < 0:
                     break
                 pods.extend(self.groups[g].pods[:self.sched[t][g]])
+            count = int(self.node_count[t])
+            if zero_or_max and ng in zero_or_max:
+                count, pods = apply_zero_or_max(count, pods, zero_or_max[ng], all_or_nothing)
             if pods:
-                out.append(Option(ng, int(self.node_count[t]), pods))
+                out.append(Option(ng, count, pods))
         return out
 
     def best_options(self, chain: Sequence[str]) -> List[str]:

@@ -100,3 +100,13 @@ def test_synth_is_deterministic():
     a, b = synth.generate(1), synth.generate(1)
     for k in a.arrays:
         assert np.array_equal(a.arrays[k], b.arrays[k]), k
+
+
+def test_zero_or_max_node_scaling():
+    """core/scaleup/orchestrator/orchestrator.go:505-517 (TestZeroOrMaxNodeScaling, orchestrator_test.go:133)."""
+    from kubernetes_autoscaler_b200.estimator import apply_zero_or_max
+    pods = [BuildTestPod("p", 1, 1)]
+    assert apply_zero_or_max(3, pods, 10, False) == (10, pods)      # raised to the only valid size
+    assert apply_zero_or_max(12, pods, 10, False) == (10, pods)     # capped
+    assert apply_zero_or_max(12, pods, 10, True) == (0, [])         # all-or-nothing refuses to cap
+    assert apply_zero_or_max(0, [], 10, False) == (0, [])
