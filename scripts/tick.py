@@ -24,6 +24,13 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--check", type=int, default=0, help="compare the first N templates with the CPU oracle")
     args = ap.parse_args()
+    rank, world, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:   # torchrun: templates sharded over the ranks, ONE all-reduce of int32[2T] (node_count | pod_count)
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import __graft_entry__ as ge
     ge.build()
     from kubernetes_autoscaler_b200 import synth
@@ -31,16 +38,36 @@ def main():
     t0 = time.perf_counter()
     enc = synth.generate(args.config, pods=args.pods, templates=args.templates, cluster_nodes=args.cluster_nodes)
     gen_s = time.perf_counter() - t0
-    eng = Engine()
+    eng = Engine(device=local_rank, rank=rank, world_size=world)
     caps = np.full(enc.T, args.cap, np.int32)
+    counts_t = None
     rows = []
     for rep in range(args.reps):
         t0 = time.perf_counter()
         eng.load(enc)
         t1 = time.perf_counter()
+        if dist is not None:
+            dist.barrier()
+            t0 = time.perf_counter()
+            eng.load(enc)
+            t1 = time.perf_counter()
         nc, pc, sched, order = eng.estimate_all(caps, copy=False)
+        if dist is not None:
+            if counts_t is None:
+                ptr, nbytes = eng.device_buffer(1)
+
+                class _Wrap:
+                    __cuda_array_interface__ = {"shape": (2 * enc.T,), "typestr": "<i4", "data": (ptr, False), "version": 3}
+                counts_t = torch.as_tensor(_Wrap(), device="cuda")
+            dist.all_reduce(counts_t)
+            torch.cuda.synchronize()
+            both = counts_t.cpu().numpy()
+            nc, pc = both[:enc.T].copy(), both[enc.T:].copy()
+            sched_full = torch.from_numpy(np.ascontiguousarray(sched)).cuda()
+            dist.all_reduce(sched_full)          # [T][E] rows of foreign templates are zero: the expander needs them all
+            sched = sched_full.cpu().numpy()
         t2 = time.perf_counter()
-        mask, waste = eng.expander_best([0, 1, 2], nc, pc)
+        mask, waste = eng.expander_best([0, 1, 2], nc, pc, sched if dist is not None else None)
         t3 = time.perf_counter()
         st = eng.stats()
         rows.append({"load_ms": 1e3 * (t1 - t0), "estimate_wall_ms": 1e3 * (t2 - t1), "estimate_dev_ms": st.estimate_ms,
@@ -57,7 +84,11 @@ def main():
         out["oracle_s_for_%d_templates" % n] = time.perf_counter() - t0
         out["parity"] = bool(np.array_equal(nc[:n], onc) and np.array_equal(pc[:n], opc) and
                              np.array_equal(sched[:n], osched) and np.array_equal(order[:n], oorder))
-    print(json.dumps(out))
+    out["n_gpus"] = world
+    if rank == 0:
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
