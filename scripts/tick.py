@@ -43,14 +43,11 @@ def main():
     counts_t = None
     rows = []
     for rep in range(args.reps):
+        if dist is not None:
+            dist.barrier()
         t0 = time.perf_counter()
         eng.load(enc)
         t1 = time.perf_counter()
-        if dist is not None:
-            dist.barrier()
-            t0 = time.perf_counter()
-            eng.load(enc)
-            t1 = time.perf_counter()
         nc, pc, sched, order = eng.estimate_all(caps, copy=False)
         if dist is not None:
             if counts_t is None:
@@ -78,7 +75,7 @@ def main():
            "nodes_total": int(nc.sum()), "pods_scheduled_total": int(pc.sum()), "best_options": int(mask.sum())}
     if args.check:
         from oracle import pyoracle
-        n = min(args.check, enc.T)
+        n = min(args.check, enc.T if dist is None else eng.template_shard(enc.T)[1])   # order rows exist on the owner only
         t0 = time.perf_counter()
         onc, opc, osched, oorder, ev = pyoracle.estimate_all(enc, caps, t_range=(0, n))
         out["oracle_s_for_%d_templates" % n] = time.perf_counter() - t0
