@@ -9,6 +9,7 @@
 //   * per-pod request planes [A][P] (A = resource dims any pending pod asks for) and per-template
 //     free-capacity planes [A][T] are laid out SoA for coalesced int64 loads in the dense pass.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <tuple>
@@ -359,6 +360,24 @@ static int do_load(Engine* e, const cae_objects* o) {
     for (int t = 0; t < T; ++t)
       tslice[(size_t)b * e->Tw + t / 32] |= ((tmpl_w[(size_t)e->feas_sword[b] * T + t] >> e->feas_sshift[b]) & 1u) << (t % 32);
   if (upload_mut(e, tslice, &e->d_tslice)) return -1;
+  // threshold bitmaps for the LUT variant of the dense pass: one row per (dim, request rank)
+  e->lut_rows = 0;
+  for (int a = 0; a < e->A; ++a) {
+    e->lut_base[a] = e->lut_rows;
+    e->lut_rows += (int)rvals[a].size() + 1;
+    e->lut_word[a] = (uint8_t)f_word[a];
+    e->lut_shift[a] = (uint8_t)f_shift[a];
+    e->lut_mask[a] = (1u << (f_bits[a] - 1)) - 1u;
+  }
+  {
+    std::vector<uint32_t> rlut((size_t)std::max(e->lut_rows, 1) * std::max(e->Tw, 1), 0);
+    for (int a = 0; a < e->A; ++a)
+      for (int t = 0; t < T; ++t) {
+        const uint32_t rank_free = (tmpl_w[(size_t)f_word[a] * T + t] >> f_shift[a]) & e->lut_mask[a];
+        for (uint32_t k = 0; k <= rank_free; ++k) rlut[(size_t)(e->lut_base[a] + k) * e->Tw + t / 32] |= 1u << (t % 32);
+      }
+    if (upload_mut(e, rlut, &e->d_rlut)) return -1;
+  }
   if (upload_mut(e, sclass, &e->d_sclass) || upload_mut(e, spec_sc, &e->d_spec_sc) || upload_mut(e, slots, &e->d_tmpl_slots) ||
       upload_mut(e, free_all, &e->d_tmpl_free_all) || upload_mut(e, free_act, &e->d_tmpl_free) || upload_mut(e, cfree, &e->d_c_free) ||
       upload_mut(e, cslots, &e->d_c_slots) || upload_mut(e, spec_w, &e->d_spec_w) || upload_mut(e, tmpl_w, &e->d_tmpl_w) || upload_mut(e, pc_of, &e->d_pc_of) || upload_mut(e, spec_dc, &e->d_spec_dc))
@@ -435,6 +454,7 @@ int32_t cae_create(const cae_config* cfg, cae_engine** out) {
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { cae::set_error("stream create failed"); delete e; return -1; }
   cudaEventCreate(&e->ev0);
   cudaEventCreate(&e->ev1);
+  { const char* v = getenv("CAE_K1_BITSLICE"); e->force_bitslice = v && v[0] == '1'; }
   *out = reinterpret_cast<cae_engine*>(e);
   return 0;
 }

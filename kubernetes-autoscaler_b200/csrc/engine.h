@@ -95,6 +95,13 @@ struct Engine {
   uint32_t feas_fstart = 0;               // bit b set: slice b is the most significant bit of a field
   uint8_t feas_sword[32] = {0}, feas_sshift[32] = {0};  // where bit b sits in the packed pod words
   uint32_t* d_tslice = nullptr;           // [ceil4(B)][Tw] bit-sliced template ranks
+  // threshold bitmaps (feas.cu, LUT variant): row lut_base[a] + k, bit t = "a request of rank k in dim a fits template t"
+  int lut_rows = 0;
+  int lut_base[CAE_MAX_RES] = {0};
+  uint8_t lut_word[CAE_MAX_RES] = {0}, lut_shift[CAE_MAX_RES] = {0};
+  uint32_t lut_mask[CAE_MAX_RES] = {0};
+  uint32_t* d_rlut = nullptr;             // [lut_rows][Tw]
+  bool force_bitslice = false;            // CAE_K1_BITSLICE=1: always take the bit-sliced comparator (tests)
   int32_t* d_pod_sc = nullptr;            // [P]
   int32_t* d_pod_dc = nullptr;            // [P]
   int64_t* d_tmpl_free = nullptr;         // [A][T] allocatable - DaemonSet requested

@@ -321,3 +321,36 @@ def Node_nolabel(name="c-nolabel"):
     n = BuildTestNode(name, 4000, 8 << 30)
     n.allocatable["pods"] = 20
     return n
+
+
+# ---- the two variants of the dense kernel (csrc/feas.cu) ---------------------------------------------
+def test_dense_bitsliced_variant(oracle, monkeypatch):
+    """The LUT kernel is the default; CAE_K1_BITSLICE=1 pins the bit-serial comparator.  Both must agree
+    with the oracle bit for bit (reasons, bit matrix, histogram)."""
+    from kubernetes_autoscaler_b200.engine import Engine
+    monkeypatch.setenv("CAE_K1_BITSLICE", "1")
+    for want_reasons in (True, False):
+        e = Engine(device=0, want_reasons=want_reasons)
+        try:
+            for enc in (synth.generate(1), synth.generate(2, pods=5_000, templates=130), synth.generate(3, pods=3_000, templates=70, cluster_nodes=40)):
+                if want_reasons:
+                    _check_dense(e, oracle, enc)
+                else:
+                    from kubernetes_autoscaler_b200.engine import unpack_bits
+                    e.load(enc)
+                    bits, _, count = e.feasibility()
+                    want, _ = oracle.feasibility_dense(enc)
+                    assert np.array_equal(unpack_bits(bits, enc.P), want == 0)
+                    assert np.array_equal(count, (want == 0).sum(axis=1))
+        finally:
+            e.close()
+
+
+def test_dense_many_distinct_requests(eng, oracle):
+    """> 1024 distinct request values: the threshold tables no longer fit in shared memory and the engine
+    must fall back to the bit-sliced comparator on its own; ragged sizes (P, T not multiples of 32)."""
+    cluster = [NodeInfo(BuildTestNode("n0", 64_000, 256 << 30))]
+    templates = [NodeInfo(BuildTestNode("t%d" % i, 500 + 37 * i, (1 + i % 9) << 30)) for i in range(45)]
+    groups = [makePodEquivalenceGroup(BuildTestPod("p%d" % i, 100 + i, (64 + (i * 7) % 1500) << 20), 1) for i in range(1301)]
+    enc = encode(cluster, templates, groups)
+    _check_dense(eng, oracle, enc)
