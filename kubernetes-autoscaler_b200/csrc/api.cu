@@ -455,6 +455,7 @@ int32_t cae_create(const cae_config* cfg, cae_engine** out) {
   cudaEventCreate(&e->ev0);
   cudaEventCreate(&e->ev1);
   { const char* v = getenv("CAE_K1_BITSLICE"); e->force_bitslice = v && v[0] == '1'; }
+  { const char* v = getenv("CAE_K1_WARPS"); if (v && atoi(v) == 8) e->k1_warps = 8; }
   *out = reinterpret_cast<cae_engine*>(e);
   return 0;
 }

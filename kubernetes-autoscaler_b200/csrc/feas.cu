@@ -17,9 +17,10 @@
 // LUT variant (the default when the tables fit in shared memory): because the ranks are small dictionaries,
 // "rank_req <= rank_free" for 32 templates is ONE word of a threshold bitmap indexed by (dim, rank_req):
 //     lut[base_a + k][tw] bit j = (k <= rank_free_a(template tw*32+j))
-// so a pod's verdict word is the AND of A + 2 shared-memory words (A resource rows, its static-class row,
-// its dynamic-class row) instead of ~3 logic ops per rank bit.  Rows are staged with an odd pitch so that
-// lanes reading different rows hit different banks.
+// so a pod's verdict word is the AND of A shared-memory words and its two class words (pre_ok / post_ok,
+// read through L1: neighbouring pods share classes) instead of ~3 logic ops per rank bit.  Rows are staged
+// with an odd pitch so that lanes reading different rows hit different banks.
+#include <algorithm>
 #include <climits>
 
 #include "engine.h"
@@ -104,7 +105,7 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
 
 // The LAST thread block to finish owns the complete local histogram: it adds it into every rank's exchange
 // buffer over NVLink (system-scope atomics on peer memory), then signals arrival.
-__device__ __forceinline__ void peer_push_tail(const PeerPush& pp, int32_t* __restrict__ fit_count, int T, int tid) {
+__device__ __forceinline__ void peer_push_tail(const PeerPush& pp, int32_t* __restrict__ fit_count, int T, int tid, int nthreads) {
   __shared__ int s_last;
   __syncthreads();
   if (tid == 0) {
@@ -114,7 +115,7 @@ __device__ __forceinline__ void peer_push_tail(const PeerPush& pp, int32_t* __re
   __syncthreads();
   if (s_last) {
     __threadfence();
-    for (int t = tid; t < T; t += K1_THREADS) {
+    for (int t = tid; t < T; t += nthreads) {
       const int v = __ldcg(&fit_count[t]);
       if (v)
         for (int r = 0; r < pp.world; ++r) atomicAdd_system(pp.accum[r] + t, v);
@@ -159,8 +160,8 @@ struct LutLayout {
 };
 constexpr int K1_LPITCH = K1_TW + 1;     // odd row pitch: distinct rows -> distinct banks
 
-template <int A, bool REASONS>
-__global__ void __launch_bounds__(K1_THREADS)
+template <int A, bool REASONS, int NW>
+__global__ void __launch_bounds__(NW * 32)
 feasibility_lut_kernel(int Pl, int Plw, int T, int Tw, int N, int U, int W, LutLayout lay,
                        const uint32_t* __restrict__ pod_w, const int32_t* __restrict__ pod_sc,
                        const int32_t* __restrict__ pod_dc, const uint32_t* __restrict__ rlut,
@@ -170,26 +171,22 @@ feasibility_lut_kernel(int Pl, int Plw, int T, int Tw, int N, int U, int W, LutL
                        uint32_t* __restrict__ fit_bits, int32_t* __restrict__ fit_count,
                        uint8_t* __restrict__ reasons, PeerPush pp) {
   extern __shared__ uint32_t k1_smem[];
-  const int rows = lay.A_rows + lay.SC + lay.DC + 1;            // + one all-zero row: the class row of out-of-range pods
+  const int rows = lay.A_rows;                                 // resource rows only: the class rows stay in global / L1
   uint32_t* s_lut = k1_smem;                                   // [rows][K1_LPITCH]
-  uint32_t* s_out = s_lut + (size_t)rows * K1_LPITCH;          // [K1_WARPS][K1_PAD]
-  int32_t* s_cnt = reinterpret_cast<int32_t*>(s_out + K1_WARPS * K1_PAD);  // [K1_TCHUNK]
+  constexpr int NT = NW * 32;
+  constexpr int PAD = K1_TCHUNK + 32 / NW;   // flush reads (wv, tl) hit 32 distinct banks
+  uint32_t* s_out = s_lut + (size_t)rows * K1_LPITCH;          // [NW][PAD]
+  int32_t* s_cnt = reinterpret_cast<int32_t*>(s_out + NW * PAD);  // [K1_TCHUNK]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int p = blockIdx.x * K1_THREADS + tid;
+  const int p = blockIdx.x * NT + tid;
   const int tw0 = blockIdx.y * K1_TW;
   const int t0 = tw0 * 32;
 
-  for (int i = tid; i < rows * K1_TW; i += K1_THREADS) {
+  for (int i = tid; i < rows * K1_TW; i += NT) {
     const int row = i / K1_TW, w = i % K1_TW;
-    uint32_t v = 0;
-    if (tw0 + w < Tw) {
-      if (row < lay.A_rows) v = rlut[(size_t)row * Tw + tw0 + w];
-      else if (row < lay.A_rows + lay.SC) v = pre_ok[(size_t)(row - lay.A_rows) * Tw + tw0 + w];
-      else if (row < rows - 1) v = post_ok[(size_t)(row - lay.A_rows - lay.SC) * Tw + tw0 + w];
-    }
-    s_lut[row * K1_LPITCH + w] = v;
+    s_lut[row * K1_LPITCH + w] = (tw0 + w < Tw) ? rlut[(size_t)row * Tw + tw0 + w] : 0u;
   }
-  for (int i = tid; i < K1_TCHUNK; i += K1_THREADS) s_cnt[i] = 0;
+  for (int i = tid; i < K1_TCHUNK; i += NT) s_cnt[i] = 0;
   const bool valid = p < Pl;
   int off[A > 0 ? A : 1];
   {
@@ -204,7 +201,11 @@ feasibility_lut_kernel(int Pl, int Plw, int T, int Tw, int N, int U, int W, LutL
   }
   const int sc = valid ? pod_sc[p] : 0;
   const int dc = valid ? pod_dc[p] : 0;
-  const int off_sc = (valid ? lay.A_rows + sc : rows - 1) * K1_LPITCH, off_dc = (lay.A_rows + lay.SC + dc) * K1_LPITCH;
+  // class words of this pod for the 16 template words (mostly L1 hits: neighbouring pods share classes)
+  uint32_t cls[K1_TW];
+#pragma unroll
+  for (int tw = 0; tw < K1_TW; ++tw)
+    cls[tw] = (valid && tw0 + tw < Tw) ? (__ldg(&pre_ok[(size_t)sc * Tw + tw0 + tw]) & __ldg(&post_ok[(size_t)dc * Tw + tw0 + tw])) : 0u;
   const TransposeConsts tc = transpose_consts(lane);
   __syncthreads();
 
@@ -213,7 +214,7 @@ feasibility_lut_kernel(int Pl, int Plw, int T, int Tw, int N, int U, int W, LutL
     uint32_t fit = 0xffffffffu;
 #pragma unroll
     for (int a = 0; a < A; ++a) fit &= s_lut[off[a] + tw];
-    const uint32_t row = fit & s_lut[off_sc + tw] & s_lut[off_dc + tw];
+    const uint32_t row = fit & cls[tw];
     if (REASONS) {
       const int wglob = tw0 + tw;
       if (valid && wglob < Tw) {
@@ -227,21 +228,21 @@ feasibility_lut_kernel(int Pl, int Plw, int T, int Tw, int N, int U, int W, LutL
       }
     }
     const uint32_t col = warp_transpose32c(row, tc);
-    s_out[warp * K1_PAD + tw * 32 + lane] = col;
+    s_out[warp * PAD + tw * 32 + lane] = col;
     atomicAdd(&s_cnt[tw * 32 + lane], __popc(col));
   }
   __syncthreads();
-  const int pw0 = blockIdx.x * K1_WARPS;
-  for (int i = tid; i < K1_TCHUNK * K1_WARPS; i += K1_THREADS) {
-    const int tl = i / K1_WARPS, wv = i % K1_WARPS;
+  const int pw0 = blockIdx.x * NW;
+  for (int i = tid; i < K1_TCHUNK * NW; i += NT) {
+    const int tl = i / NW, wv = i % NW;
     const int t = t0 + tl;
-    if (t < T && pw0 + wv < Plw && fit_bits) fit_bits[(size_t)t * Plw + pw0 + wv] = s_out[wv * K1_PAD + tl];
+    if (t < T && pw0 + wv < Plw && fit_bits) fit_bits[(size_t)t * Plw + pw0 + wv] = s_out[wv * PAD + tl];
   }
-  for (int i = tid; i < K1_TCHUNK; i += K1_THREADS) {
+  for (int i = tid; i < K1_TCHUNK; i += NT) {
     const int c = s_cnt[i];
     if (c && t0 + i < T) atomicAdd(&fit_count[t0 + i], c);
   }
-  if (pp.world) peer_push_tail(pp, fit_count, T, tid);
+  if (pp.world) peer_push_tail(pp, fit_count, T, tid, NT);
 }
 
 template <int B, bool REASONS>
@@ -328,7 +329,7 @@ feasibility_kernel(int Pl, int Plw, int T, int Tw, int N, int U, int W, FeasLayo
     const int c = s_cnt[i];
     if (c && t0 + i < T) atomicAdd(&fit_count[t0 + i], c);
   }
-  if (pp.world) peer_push_tail(pp, fit_count, T, tid);
+  if (pp.world) peer_push_tail(pp, fit_count, T, tid, K1_THREADS);
 }
 
 static PeerPush peer_push_args(Engine* e) {
@@ -372,51 +373,54 @@ static void launch_feas_b(Engine* e, bool want_reasons, dim3 grid, const PeerPus
         e->d_pre_ok, e->d_post_ok, e->d_pre_code, e->d_post_code, e->d_fit_bits, e->d_fit_count, e->d_reasons, pp);
 }
 
-template <int A, bool REASONS>
-static int launch_feas_lut_ar(Engine* e, dim3 grid, const PeerPush& pp, const LutLayout& lay, size_t smem) {
-  auto kern = feasibility_lut_kernel<A, REASONS>;
+template <int A, bool REASONS, int NW>
+static int launch_feas_lut_arw(Engine* e, const PeerPush& pp, const LutLayout& lay, int rows) {
+  dim3 grid((e->Pl + NW * 32 - 1) / (NW * 32), (e->Tw + K1_TW - 1) / K1_TW);
+  const size_t smem = sizeof(uint32_t) * ((size_t)std::max(rows, 1) * K1_LPITCH + NW * (K1_TCHUNK + 32 / NW) + K1_TCHUNK);
+  auto kern = feasibility_lut_kernel<A, REASONS, NW>;
   if (smem > 48 * 1024) CAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, K1_THREADS, smem, e->stream>>>(
+  kern<<<grid, NW * 32, smem, e->stream>>>(
       e->Pl, e->Plw, e->T, e->Tw, e->N, e->U, e->W, lay, e->d_pod_w, e->d_pod_sc, e->d_pod_dc, e->d_rlut, e->d_tmpl_slots,
       e->d_pre_ok, e->d_post_ok, e->d_pre_code, e->d_post_code, e->d_fit_bits, e->d_fit_count, e->d_reasons, pp);
   return 0;
 }
 
 template <int A>
-static int launch_feas_lut_a(Engine* e, bool want_reasons, dim3 grid, const PeerPush& pp, const LutLayout& lay, size_t smem) {
-  return want_reasons ? launch_feas_lut_ar<A, true>(e, grid, pp, lay, smem) : launch_feas_lut_ar<A, false>(e, grid, pp, lay, smem);
+static int launch_feas_lut_a(Engine* e, bool want_reasons, const PeerPush& pp, const LutLayout& lay, int rows) {
+  if (e->k1_warps == 8)
+    return want_reasons ? launch_feas_lut_arw<A, true, 8>(e, pp, lay, rows) : launch_feas_lut_arw<A, false, 8>(e, pp, lay, rows);
+  return want_reasons ? launch_feas_lut_arw<A, true, 16>(e, pp, lay, rows) : launch_feas_lut_arw<A, false, 16>(e, pp, lay, rows);
 }
 
 constexpr int K1_LUT_MAX_ROWS = 1024;    // 68 KB of threshold rows per thread block at most
 
 int launch_feasibility(Engine* e, bool want_reasons) {
   CAE_CUDA(cudaMemsetAsync(e->d_fit_count, 0, sizeof(int32_t) * e->T, e->stream));
-  dim3 grid((e->Pl + K1_THREADS - 1) / K1_THREADS, (e->Tw + K1_TW - 1) / K1_TW);
-  if (grid.x == 0 || grid.y == 0) return 0;
+  if (e->Pl == 0 || e->Tw == 0) return 0;
   const PeerPush pp = peer_push_args(e);
-  const int rows = e->lut_rows + e->SC + e->DC;
+  const int rows = e->lut_rows;
   if (!e->force_bitslice && rows <= K1_LUT_MAX_ROWS) {
     LutLayout lay{};
     lay.A_rows = e->lut_rows; lay.SC = e->SC; lay.DC = e->DC;
     for (int a = 0; a < e->A; ++a) {
       lay.base[a] = e->lut_base[a]; lay.mask[a] = e->lut_mask[a]; lay.word[a] = e->lut_word[a]; lay.shift[a] = e->lut_shift[a];
     }
-    const size_t smem = sizeof(uint32_t) * ((size_t)(rows + 1) * K1_LPITCH + K1_WARPS * K1_PAD + K1_TCHUNK);
     int rc = 0;
     switch (e->A) {
-      case 0: rc = launch_feas_lut_a<0>(e, want_reasons, grid, pp, lay, smem); break;
-      case 1: rc = launch_feas_lut_a<1>(e, want_reasons, grid, pp, lay, smem); break;
-      case 2: rc = launch_feas_lut_a<2>(e, want_reasons, grid, pp, lay, smem); break;
-      case 3: rc = launch_feas_lut_a<3>(e, want_reasons, grid, pp, lay, smem); break;
-      case 4: rc = launch_feas_lut_a<4>(e, want_reasons, grid, pp, lay, smem); break;
-      case 5: rc = launch_feas_lut_a<5>(e, want_reasons, grid, pp, lay, smem); break;
-      case 6: rc = launch_feas_lut_a<6>(e, want_reasons, grid, pp, lay, smem); break;
-      case 7: rc = launch_feas_lut_a<7>(e, want_reasons, grid, pp, lay, smem); break;
-      default: rc = launch_feas_lut_a<8>(e, want_reasons, grid, pp, lay, smem); break;
+      case 0: rc = launch_feas_lut_a<0>(e, want_reasons, pp, lay, rows); break;
+      case 1: rc = launch_feas_lut_a<1>(e, want_reasons, pp, lay, rows); break;
+      case 2: rc = launch_feas_lut_a<2>(e, want_reasons, pp, lay, rows); break;
+      case 3: rc = launch_feas_lut_a<3>(e, want_reasons, pp, lay, rows); break;
+      case 4: rc = launch_feas_lut_a<4>(e, want_reasons, pp, lay, rows); break;
+      case 5: rc = launch_feas_lut_a<5>(e, want_reasons, pp, lay, rows); break;
+      case 6: rc = launch_feas_lut_a<6>(e, want_reasons, pp, lay, rows); break;
+      case 7: rc = launch_feas_lut_a<7>(e, want_reasons, pp, lay, rows); break;
+      default: rc = launch_feas_lut_a<8>(e, want_reasons, pp, lay, rows); break;
     }
     if (rc) return rc;
   } else {
     // slices beyond feas_B are all-zero with r = 0: they change nothing (padding to a multiple of 4)
+    dim3 grid((e->Pl + K1_THREADS - 1) / K1_THREADS, (e->Tw + K1_TW - 1) / K1_TW);
     const int Bp = e->feas_B == 0 ? 0 : (e->feas_B + 3) / 4 * 4;
     switch (Bp) {
       case 0: launch_feas_b<0>(e, want_reasons, grid, pp); break;
