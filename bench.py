@@ -305,8 +305,8 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (feasibility_kernel) -----------------------------------------
-    # algorithmic bytes of feasibility_kernel: per pod W packed-rank words + 2 class ids,
+    # ---- roofline of the dominant kernel (feasibility_lut_kernel) -----------------------------------------
+    # algorithmic bytes of the dense kernel: per pod W packed-rank words + 2 class ids,
     # per template W words, the bit matrix, the fit histogram
     req = enc.arrays["ps_req"][np.unique(enc.arrays["pend_spec"])]
     bits = 0
@@ -326,8 +326,8 @@ def main():
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "feasibility_kernel", "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
-                "note": "integer-issue bound by design: ~1 bit of compulsory HBM traffic per evaluation (DESIGN.md §K1)"}
+                "traffic": traffic, "kernel": "feasibility_lut_kernel", "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
+                "note": "shuffle / shared-memory issue bound: ~1 bit of compulsory HBM traffic per evaluation (DESIGN.md §K1)"}
 
     # ---- CPU baseline: the oracle on this box's cores, bounded sample of the same workload ---------------
     # (a fresh process: the oracle's worker pool must fork before any CUDA context exists)

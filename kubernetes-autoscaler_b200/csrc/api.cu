@@ -207,6 +207,7 @@ static int do_load(Engine* e, const cae_objects* o) {
   const int N = o->num_cluster_nodes, T = o->num_templates, NT = N + T;
   e->N = N; e->T = T; e->U = N + 2 * T; e->E = o->num_groups; e->P = o->num_pending;
   e->Tw = (T + 31) / 32;
+  e->Twp = (e->Tw + FEAS_TW - 1) / FEAS_TW * FEAS_TW;
   e->num_podspecs = o->num_podspecs;
   const int W = std::max(1, e->cfg.world_size), rk = e->cfg.rank;
   e->p_begin = (int)((int64_t)e->P * rk / W);
@@ -370,11 +371,11 @@ static int do_load(Engine* e, const cae_objects* o) {
     e->lut_mask[a] = (1u << (f_bits[a] - 1)) - 1u;
   }
   {
-    std::vector<uint32_t> rlut((size_t)std::max(e->lut_rows, 1) * std::max(e->Tw, 1), 0);
+    std::vector<uint32_t> rlut((size_t)std::max(e->lut_rows, 1) * std::max(e->Twp, 1), 0);
     for (int a = 0; a < e->A; ++a)
       for (int t = 0; t < T; ++t) {
         const uint32_t rank_free = (tmpl_w[(size_t)f_word[a] * T + t] >> f_shift[a]) & e->lut_mask[a];
-        for (uint32_t k = 0; k <= rank_free; ++k) rlut[(size_t)(e->lut_base[a] + k) * e->Tw + t / 32] |= 1u << (t % 32);
+        for (uint32_t k = 0; k <= rank_free; ++k) rlut[(size_t)(e->lut_base[a] + k) * e->Twp + t / 32] |= 1u << (t % 32);
       }
     if (upload_mut(e, rlut, &e->d_rlut)) return -1;
   }
@@ -383,11 +384,12 @@ static int do_load(Engine* e, const cae_objects* o) {
       upload_mut(e, cslots, &e->d_c_slots) || upload_mut(e, spec_w, &e->d_spec_w) || upload_mut(e, tmpl_w, &e->d_tmpl_w) || upload_mut(e, pc_of, &e->d_pc_of) || upload_mut(e, spec_dc, &e->d_spec_dc))
     return -1;
 
-  if (dev_alloc(e, &e->d_pre_code, (size_t)e->SC * e->U) || dev_alloc(e, &e->d_pre_ok, (size_t)e->SC * std::max(e->Tw, 1)) ||
-      dev_alloc(e, &e->d_post_code, (size_t)e->DC * std::max(T, 1), true) || dev_alloc(e, &e->d_post_ok, (size_t)e->DC * std::max(e->Tw, 1)) ||
+  if (dev_alloc(e, &e->d_pre_code, (size_t)e->SC * e->U) || dev_alloc(e, &e->d_pre_ok, (size_t)e->SC * std::max(e->Twp, 1)) ||
+      dev_alloc(e, &e->d_post_code, (size_t)e->DC * std::max(T, 1), true) || dev_alloc(e, &e->d_post_ok, (size_t)e->DC * std::max(e->Twp, 1)) ||
       dev_alloc(e, &e->d_pod_w, (size_t)std::max(e->W, 1) * std::max(e->Pl, 1)) || dev_alloc(e, &e->d_pod_sc, (size_t)std::max(e->Pl, 1)) ||
       dev_alloc(e, &e->d_pod_dc, (size_t)std::max(e->Pl, 1)) || dev_alloc(e, &e->d_fit_bits, (size_t)std::max(T, 1) * std::max(e->Plw, 1)) ||
-      dev_alloc(e, &e->d_fit_count, (size_t)std::max(T, 1), true) || dev_alloc(e, &e->d_group_reason, (size_t)std::max(T, 1) * std::max(e->E, 1)) ||
+      dev_alloc(e, &e->d_fit_count, (size_t)std::max(T, 1), true) || dev_alloc(e, &e->d_fit_acc, (size_t)std::max(T, 1), true) ||
+      dev_alloc(e, &e->d_chunk_done, (size_t)std::max(e->Twp / FEAS_TW, 1), true) || dev_alloc(e, &e->d_group_reason, (size_t)std::max(T, 1) * std::max(e->E, 1)) ||
       dev_alloc(e, &e->d_counts2, (size_t)2 * std::max(T, 1), true) || dev_alloc(e, &e->d_sched, (size_t)std::max(T, 1) * std::max(e->E, 1), true) ||
       dev_alloc(e, &e->d_order, (size_t)std::max(T, 1) * std::max(e->E, 1)) || dev_alloc(e, &e->d_order_n, (size_t)std::max(T, 1), true) ||
       dev_alloc(e, &e->d_max_nodes, (size_t)std::max(T, 1), true) || dev_alloc(e, &e->d_work_counter, 4, true) ||

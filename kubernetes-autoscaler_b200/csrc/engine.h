@@ -13,6 +13,7 @@
 namespace cae {
 
 constexpr int FEAS_MAX_W = 4;
+constexpr int FEAS_TW = 16;                // template words per thread block of the dense pass; row pitch Twp is a multiple
 
 void set_error(const std::string& msg);
 
@@ -72,6 +73,7 @@ struct Engine {
   int act_dim[CAE_MAX_RES] = {0};
   int SC = 0, DC = 0;                     // static / dynamic classes
   int Tw = 0;                             // ceil(T/32)
+  int Twp = 0;                            // Tw rounded up to whole FEAS_TW chunks: pitch of pre_ok / post_ok / rlut
   int p_begin = 0, p_end = 0;             // pod shard of this rank (feasibility)
   int t_begin = 0, t_end = 0;             // template shard of this rank (estimate)
   int Pl = 0, Plw = 0;                    // local pods, ceil(Pl/32)
@@ -81,11 +83,11 @@ struct Engine {
   // derived device tables
   StaticClass* d_sclass = nullptr;        // [SC]
   uint8_t* d_pre_code = nullptr;          // [SC][U] static_code()
-  uint32_t* d_pre_ok = nullptr;           // [SC][Tw] bit t: low nibble of pre_code[sc][N+t] == 0 and template has a pod slot
+  uint32_t* d_pre_ok = nullptr;           // [SC][Twp] bit t: low nibble of pre_code[sc][N+t] == 0 and template has a pod slot
   int32_t* d_spec_sc = nullptr;           // [num_podspecs] static class of each spec
   int32_t* d_spec_dc = nullptr;           // [num_podspecs] dynamic class (0 = none)
   uint8_t* d_post_code = nullptr;         // [DC][T] PTS / IPA reason on the empty template (0 = ok)
-  uint32_t* d_post_ok = nullptr;          // [DC][Tw]
+  uint32_t* d_post_ok = nullptr;          // [DC][Twp]
   int W = 0;                              // 32-bit words of the packed rank encoding (feas.cu)
   uint32_t feas_guard[4] = {0, 0, 0, 0};  // guard-bit mask per word
   uint32_t* d_spec_w = nullptr;           // [num_podspecs][FEAS_MAX_W] packed request ranks
@@ -100,7 +102,7 @@ struct Engine {
   int lut_base[CAE_MAX_RES] = {0};
   uint8_t lut_word[CAE_MAX_RES] = {0}, lut_shift[CAE_MAX_RES] = {0};
   uint32_t lut_mask[CAE_MAX_RES] = {0};
-  uint32_t* d_rlut = nullptr;             // [lut_rows][Tw]
+  uint32_t* d_rlut = nullptr;             // [lut_rows][Twp]
   int k1_warps = 16;                      // warps per thread block of the LUT variant (CAE_K1_WARPS=8|16)
   bool force_bitslice = false;            // CAE_K1_BITSLICE=1: always take the bit-sliced comparator (tests)
   int32_t* d_pod_sc = nullptr;            // [P]
@@ -113,6 +115,8 @@ struct Engine {
   uint32_t* d_fit_bits = nullptr;         // [T][Plw]
   uint8_t* d_reasons = nullptr;           // [T][Pl] (want_reasons)
   int32_t* d_fit_count = nullptr;         // [T]
+  int32_t* d_fit_acc = nullptr;           // [T] self-cleaning accumulators of the dense pass
+  int32_t* d_chunk_done = nullptr;        // [Twp / FEAS_TW] arrival counters per template chunk
   uint8_t* d_group_reason = nullptr;      // [T][E]
   bool group_reason_valid = false;
   int32_t* d_counts2 = nullptr;           // [2T] node_count | pod_count

@@ -99,9 +99,9 @@ int launch_class_matrices(Engine* e) {
     class_matrix_kernel<<<grid, 128, 0, e->stream>>>(e->dobj, e->d_sclass, e->SC, e->U, e->d_pre_code);
     e->stats.kernel_launches++;
   }
-  if (e->Tw > 0) {
-    dim3 g1((e->Tw + 63) / 64, e->SC);
-    pack_ok_bits_kernel<<<g1, 64, 0, e->stream>>>(e->d_pre_code, e->U, e->N, e->SC, e->T, e->Tw, e->d_tmpl_slots, e->d_pre_ok);
+  if (e->Tw > 0) {   // rows padded to the pitch Twp; the padding words are written as zeros
+    dim3 g1((e->Twp + 63) / 64, e->SC);
+    pack_ok_bits_kernel<<<g1, 64, 0, e->stream>>>(e->d_pre_code, e->U, e->N, e->SC, e->T, e->Twp, e->d_tmpl_slots, e->d_pre_ok);
     e->stats.kernel_launches += 1;
   }
   CAE_KERNEL_OK();
@@ -110,8 +110,8 @@ int launch_class_matrices(Engine* e) {
 
 int launch_post_bits(Engine* e) {
   if (e->Tw > 0) {
-    dim3 g2((e->Tw + 63) / 64, e->DC);
-    pack_ok_bits_kernel<<<g2, 64, 0, e->stream>>>(e->d_post_code, e->T, 0, e->DC, e->T, e->Tw, nullptr, e->d_post_ok);
+    dim3 g2((e->Twp + 63) / 64, e->DC);
+    pack_ok_bits_kernel<<<g2, 64, 0, e->stream>>>(e->d_post_code, e->T, 0, e->DC, e->T, e->Twp, nullptr, e->d_post_ok);
     e->stats.kernel_launches += 1;
   }
   CAE_KERNEL_OK();
