@@ -308,6 +308,10 @@ int32_t cae_get_stats(cae_engine* e, cae_stats* out);
  * / NCCL on the caller's side): 0 = fit_count int32[T], 1 = node_count|pod_count int32[2T]. */
 void* cae_device_buffer(cae_engine* e, int32_t which, size_t* bytes);
 
+/* The CUDA stream (cudaStream_t) every launch and copy of this engine is ordered on, for callers that order
+ * their own device work with it (a collective on the result buffers, an L2 flush in a benchmark). */
+void* cae_stream(cae_engine* e);
+
 /* Page-locked host memory for the caller's large input / output buffers (fit_bits, reasons): copies
  * to and from pinned memory run at full PCIe speed and asynchronously. */
 /* Fused histogram exchange for the multi-GPU dense pass (one process per GPU, one node).  Each engine owns

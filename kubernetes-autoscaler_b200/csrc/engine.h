@@ -92,6 +92,7 @@ struct Engine {
   uint32_t feas_guard[4] = {0, 0, 0, 0};  // guard-bit mask per word
   uint32_t* d_spec_w = nullptr;           // [num_podspecs][FEAS_MAX_W] packed request ranks
   uint32_t* d_pod_w = nullptr;            // [W][Pl] per pending pod
+  uint16_t* d_pod_row = nullptr;          // [A][Pl] threshold-row id per active dim (LUT variant)
   uint32_t* d_tmpl_w = nullptr;           // [W][T] packed free-capacity ranks + guard bits
   int feas_B = 0;                         // bit slices of the free-capacity ranks (all fields)
   uint32_t feas_fstart = 0;               // bit b set: slice b is the most significant bit of a field

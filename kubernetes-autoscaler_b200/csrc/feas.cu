@@ -31,22 +31,45 @@
 
 namespace cae {
 
-__global__ void expand_pods_kernel(const int32_t* __restrict__ pend_spec, int p_begin, int Pl, int W,
+struct LutLayout {
+  int A, rows;               // active dims, threshold rows (all dims)
+  int base[CAE_MAX_RES];
+  uint32_t mask[CAE_MAX_RES];
+  uint8_t word[CAE_MAX_RES], shift[CAE_MAX_RES];
+};
+
+static LutLayout lut_layout(const Engine* e) {
+  LutLayout lay{};
+  lay.A = e->A;
+  lay.rows = e->lut_rows;
+  for (int d = 0; d < e->A; ++d) {
+    lay.base[d] = e->lut_base[d]; lay.mask[d] = e->lut_mask[d]; lay.word[d] = e->lut_word[d]; lay.shift[d] = e->lut_shift[d];
+  }
+  return lay;
+}
+
+// per pending pod of this rank's shard: packed request ranks (bit-sliced variant), the threshold-row id of every
+// active dim (LUT variant: base_a + rank_req_a, 0xFFFF when the rows do not fit 16 bits) and the two class ids
+__global__ void expand_pods_kernel(const int32_t* __restrict__ pend_spec, int p_begin, int Pl, int W, LutLayout lay,
                                    const uint32_t* __restrict__ spec_w, const int32_t* __restrict__ spec_sc,
                                    const int32_t* __restrict__ spec_dc, uint32_t* __restrict__ pod_w,
-                                   int32_t* __restrict__ pod_sc, int32_t* __restrict__ pod_dc) {
+                                   uint16_t* __restrict__ pod_row, int32_t* __restrict__ pod_sc, int32_t* __restrict__ pod_dc) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= Pl) return;
   int spec = pend_spec[p_begin + p];
   for (int w = 0; w < W; ++w) pod_w[(size_t)w * Pl + p] = spec_w[(size_t)spec * FEAS_MAX_W + w];
+  for (int d = 0; d < lay.A; ++d) {
+    const int row = lay.base[d] + (int)((spec_w[(size_t)spec * FEAS_MAX_W + lay.word[d]] >> lay.shift[d]) & lay.mask[d]);
+    pod_row[(size_t)d * Pl + p] = (uint16_t)min(row, 0xFFFF);
+  }
   pod_sc[p] = spec_sc[spec];
   pod_dc[p] = spec_dc[spec];
 }
 
 int launch_expand_pods(Engine* e) {
   if (e->Pl == 0) return 0;
-  expand_pods_kernel<<<(e->Pl + 255) / 256, 256, 0, e->stream>>>(e->dobj.pend_spec, e->p_begin, e->Pl, e->W, e->d_spec_w,
-                                                                   e->d_spec_sc, e->d_spec_dc, e->d_pod_w, e->d_pod_sc, e->d_pod_dc);
+  expand_pods_kernel<<<(e->Pl + 255) / 256, 256, 0, e->stream>>>(e->dobj.pend_spec, e->p_begin, e->Pl, e->W, lut_layout(e), e->d_spec_w,
+                                                                   e->d_spec_sc, e->d_spec_dc, e->d_pod_w, e->d_pod_row, e->d_pod_sc, e->d_pod_dc);
   e->stats.kernel_launches++;
   CAE_KERNEL_OK();
   return 0;
@@ -89,8 +112,9 @@ __global__ void peer_wait_kernel(int32_t* __restrict__ accum, volatile int32_t* 
 
 struct K1Args {
   int Pl, Plw, T, Tw, Twp, N, U, W;
-  int G;                                  // thread blocks per template chunk; the pod words are split evenly over them
+  int G, gq, gr;                          // thread blocks per template chunk; block x takes gq (+1 if x < gr) pod words
   const uint32_t* pod_w;
+  const uint16_t* pod_row;                // [A][Pl] threshold-row ids
   const int32_t *pod_sc, *pod_dc;
   const uint32_t *tslice, *rlut;
   const int32_t* tmpl_slots;
@@ -209,48 +233,35 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
 }
 
 // ---- LUT variant --------------------------------------------------------------------------------------------
-struct LutLayout {
-  int rows;                  // threshold rows (all dims)
-  int base[CAE_MAX_RES];
-  uint32_t mask[CAE_MAX_RES];
-  uint8_t word[CAE_MAX_RES], shift[CAE_MAX_RES];
-};
 
 template <int A, bool REASONS, int NW>
 __global__ void __launch_bounds__(NW * 32, 48 / NW)
-feasibility_lut_kernel(K1Args a, LutLayout lay, PeerPush pp) {
+feasibility_lut_kernel(K1Args a, int rows, PeerPush pp) {
   extern __shared__ uint32_t k1_smem[];
   constexpr int NT = NW * 32;
   constexpr int PAD = K1_TCHUNK + 32 / NW;                     // flush reads (wv, tl) hit 32 distinct banks
   uint32_t* s_lut = k1_smem;                                   // [rows][K1_LPITCH]
-  uint32_t* s_out = s_lut + (size_t)max(lay.rows, 1) * K1_LPITCH;   // [NW][PAD]
+  uint32_t* s_out = s_lut + (size_t)max(rows, 1) * K1_LPITCH;       // [NW][PAD]
   int32_t* s_cnt = reinterpret_cast<int32_t*>(s_out + NW * PAD);    // [K1_TCHUNK]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tw0 = blockIdx.y * K1_TW;
   const int t0 = tw0 * 32;
-  // this block's run of pod words (an even split of Plw over the G blocks of the chunk; at most NW words)
-  const int pwb = (int)((long long)a.Plw * blockIdx.x / a.G);
-  const int npw = (int)((long long)a.Plw * (blockIdx.x + 1) / a.G) - pwb;
+  // this block's run of pod words (an even split of Plw over the G blocks of the chunk; 1..NW words)
+  const int pwb = (int)blockIdx.x * a.gq + min((int)blockIdx.x, a.gr);
+  const int npw = a.gq + ((int)blockIdx.x < a.gr ? 1 : 0);
   const int p = (pwb + warp) * 32 + lane;
   const bool valid = warp < npw && p < a.Pl;
 
-  for (int i = tid; i < lay.rows * K1_TW; i += NT) {
+#pragma unroll 1
+  for (int i = tid; i < rows * K1_TW; i += NT) {
     const int row = i / K1_TW, w = i % K1_TW;
     s_lut[row * K1_LPITCH + w] = a.rlut[(size_t)row * a.Twp + tw0 + w];   // pitch padded to whole chunks: always in bounds
   }
   for (int i = tid; i < K1_TCHUNK; i += NT) s_cnt[i] = 0;
 
   int off[A > 0 ? A : 1];
-  {
-    uint32_t pw[FEAS_MAX_W];
 #pragma unroll
-    for (int w = 0; w < FEAS_MAX_W; ++w) pw[w] = (valid && w < a.W) ? a.pod_w[(size_t)w * a.Pl + p] : 0u;
-#pragma unroll
-    for (int d = 0; d < A; ++d) {
-      const uint32_t word = lay.word[d] == 0 ? pw[0] : lay.word[d] == 1 ? pw[1] : lay.word[d] == 2 ? pw[2] : pw[3];
-      off[d] = (lay.base[d] + (int)((word >> lay.shift[d]) & lay.mask[d])) * K1_LPITCH;
-    }
-  }
+  for (int d = 0; d < A; ++d) off[d] = valid ? (int)a.pod_row[(size_t)d * a.Pl + p] * K1_LPITCH : 0;
   const int sc = valid ? a.pod_sc[p] : 0;
   const int dc = valid ? a.pod_dc[p] : 0;
   // class words of this pod for the chunk's K1_TW template words (rows are 64 B aligned: 128-bit loads)
@@ -310,9 +321,10 @@ feasibility_lut_kernel(K1Args a, LutLayout lay, PeerPush pp) {
     if (wv < npw) {
       uint32_t* dst = a.fit_bits + (size_t)(t0 + tid / NW) * a.Plw + pwb + wv;
       const uint32_t* src = s_out + wv * PAD + tid / NW;
+      const size_t stride = (size_t)32 * a.Plw;
+      const int kmax = min(K1_TCHUNK / 32, (a.T - t0 - tid / NW + 31) / 32);   // rows t0 + tid/NW + 32k < T
 #pragma unroll 4
-      for (int k = 0; k < K1_TCHUNK / 32; ++k)
-        if (t0 + tid / NW + k * 32 < a.T) dst[(size_t)k * 32 * a.Plw] = src[k * 32];
+      for (int k = 0; k < kmax; ++k, dst += stride, src += 32) *dst = *src;
     }
   }
   k1_finish(a, pp, s_cnt, t0, tid, NT);
@@ -434,7 +446,7 @@ static K1Args k1_args(Engine* e) {
   K1Args a{};
   a.Pl = e->Pl; a.Plw = e->Plw; a.T = e->T; a.Tw = e->Tw; a.Twp = e->Twp; a.N = e->N; a.U = e->U; a.W = e->W;
   a.G = 1;
-  a.pod_w = e->d_pod_w; a.pod_sc = e->d_pod_sc; a.pod_dc = e->d_pod_dc;
+  a.pod_w = e->d_pod_w; a.pod_row = e->d_pod_row; a.pod_sc = e->d_pod_sc; a.pod_dc = e->d_pod_dc;
   a.tslice = e->d_tslice; a.rlut = e->d_rlut; a.tmpl_slots = e->d_tmpl_slots;
   a.pre_ok = e->d_pre_ok; a.post_ok = e->d_post_ok; a.pre_code = e->d_pre_code; a.post_code = e->d_post_code;
   a.fit_bits = e->d_fit_bits; a.fit_count = e->d_fit_count; a.fit_acc = e->d_fit_acc; a.chunk_done = e->d_chunk_done;
@@ -454,25 +466,27 @@ static void launch_feas_b(Engine* e, bool want_reasons, K1Args a, const PeerPush
 }
 
 template <int A, bool REASONS, int NW>
-static int launch_feas_lut_arw(Engine* e, K1Args a, const PeerPush& pp, const LutLayout& lay) {
+static int launch_feas_lut_arw(Engine* e, K1Args a, const PeerPush& pp) {
   const int chunks = e->Twp / K1_TW;
   // one wave when it fits: the pod words are split evenly over as many blocks as the SMs hold at once
   const int slots = e->sm_count * (48 / NW);
   const int g_min = (e->Plw + NW - 1) / NW;
   a.G = std::max(g_min, std::min(e->Plw, std::max(1, slots / chunks)));
+  a.gq = e->Plw / a.G;
+  a.gr = e->Plw % a.G;
   dim3 grid(a.G, chunks);
-  const size_t smem = sizeof(uint32_t) * ((size_t)std::max(lay.rows, 1) * K1_LPITCH + NW * (K1_TCHUNK + 32 / NW) + K1_TCHUNK);
+  const size_t smem = sizeof(uint32_t) * ((size_t)std::max(e->lut_rows, 1) * K1_LPITCH + NW * (K1_TCHUNK + 32 / NW) + K1_TCHUNK);
   auto kern = feasibility_lut_kernel<A, REASONS, NW>;
   if (smem > 48 * 1024) CAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, NW * 32, smem, e->stream>>>(a, lay, pp);
+  kern<<<grid, NW * 32, smem, e->stream>>>(a, e->lut_rows, pp);
   return 0;
 }
 
 template <int A>
-static int launch_feas_lut_a(Engine* e, bool want_reasons, const K1Args& a, const PeerPush& pp, const LutLayout& lay) {
+static int launch_feas_lut_a(Engine* e, bool want_reasons, const K1Args& a, const PeerPush& pp) {
   if (e->k1_warps == 8)
-    return want_reasons ? launch_feas_lut_arw<A, true, 8>(e, a, pp, lay) : launch_feas_lut_arw<A, false, 8>(e, a, pp, lay);
-  return want_reasons ? launch_feas_lut_arw<A, true, 16>(e, a, pp, lay) : launch_feas_lut_arw<A, false, 16>(e, a, pp, lay);
+    return want_reasons ? launch_feas_lut_arw<A, true, 8>(e, a, pp) : launch_feas_lut_arw<A, false, 8>(e, a, pp);
+  return want_reasons ? launch_feas_lut_arw<A, true, 16>(e, a, pp) : launch_feas_lut_arw<A, false, 16>(e, a, pp);
 }
 
 constexpr int K1_LUT_MAX_ROWS = 1024;    // 68 KB of threshold rows per thread block at most
@@ -482,22 +496,17 @@ int launch_feasibility(Engine* e, bool want_reasons) {
   const PeerPush pp = peer_push_args(e);
   const K1Args a = k1_args(e);
   if (!e->force_bitslice && e->lut_rows <= K1_LUT_MAX_ROWS) {
-    LutLayout lay{};
-    lay.rows = e->lut_rows;
-    for (int d = 0; d < e->A; ++d) {
-      lay.base[d] = e->lut_base[d]; lay.mask[d] = e->lut_mask[d]; lay.word[d] = e->lut_word[d]; lay.shift[d] = e->lut_shift[d];
-    }
     int rc = 0;
     switch (e->A) {
-      case 0: rc = launch_feas_lut_a<0>(e, want_reasons, a, pp, lay); break;
-      case 1: rc = launch_feas_lut_a<1>(e, want_reasons, a, pp, lay); break;
-      case 2: rc = launch_feas_lut_a<2>(e, want_reasons, a, pp, lay); break;
-      case 3: rc = launch_feas_lut_a<3>(e, want_reasons, a, pp, lay); break;
-      case 4: rc = launch_feas_lut_a<4>(e, want_reasons, a, pp, lay); break;
-      case 5: rc = launch_feas_lut_a<5>(e, want_reasons, a, pp, lay); break;
-      case 6: rc = launch_feas_lut_a<6>(e, want_reasons, a, pp, lay); break;
-      case 7: rc = launch_feas_lut_a<7>(e, want_reasons, a, pp, lay); break;
-      default: rc = launch_feas_lut_a<8>(e, want_reasons, a, pp, lay); break;
+      case 0: rc = launch_feas_lut_a<0>(e, want_reasons, a, pp); break;
+      case 1: rc = launch_feas_lut_a<1>(e, want_reasons, a, pp); break;
+      case 2: rc = launch_feas_lut_a<2>(e, want_reasons, a, pp); break;
+      case 3: rc = launch_feas_lut_a<3>(e, want_reasons, a, pp); break;
+      case 4: rc = launch_feas_lut_a<4>(e, want_reasons, a, pp); break;
+      case 5: rc = launch_feas_lut_a<5>(e, want_reasons, a, pp); break;
+      case 6: rc = launch_feas_lut_a<6>(e, want_reasons, a, pp); break;
+      case 7: rc = launch_feas_lut_a<7>(e, want_reasons, a, pp); break;
+      default: rc = launch_feas_lut_a<8>(e, want_reasons, a, pp); break;
     }
     if (rc) return rc;
   } else {

@@ -191,6 +191,10 @@ class Engine:
         self._check(self.lib.cae_get_stats(self.h, C.byref(s)))
         return s
 
+    def stream(self) -> int:
+        """cudaStream_t of the engine (e.g. for torch.cuda.ExternalStream)."""
+        return int(self.lib.cae_stream(self.h) or 0)
+
     def device_buffer(self, which: int) -> Tuple[int, int]:
         n = C.c_size_t(0)
         p = self.lib.cae_device_buffer(self.h, which, C.byref(n))
