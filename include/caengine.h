@@ -312,19 +312,21 @@ void* cae_device_buffer(cae_engine* e, int32_t which, size_t* bytes);
  * their own device work with it (a collective on the result buffers, an L2 flush in a benchmark). */
 void* cae_stream(cae_engine* e);
 
-/* Page-locked host memory for the caller's large input / output buffers (fit_bits, reasons): copies
- * to and from pinned memory run at full PCIe speed and asynchronously. */
 /* Fused histogram exchange for the multi-GPU dense pass (one process per GPU, one node).  Each engine owns
  * an exchange buffer in its HBM; after cae_peer_attach the LAST thread block of every cae_feasibility
- * launch adds the rank's per-template fit counts straight into every peer's buffer over NVLink (P2P
- * atomics on CUDA-IPC mapped memory) and a tiny wait kernel publishes the all-reduced histogram as
- * fit_count — no separate collective launch.  Equivalent to all_reduce(sum, int32[T]).
+ * launch writes the rank's per-template fit counts into its slot of every rank's buffer over NVLink (stores
+ * to CUDA-IPC mapped peer memory), signals arrival, waits for all ranks and publishes the summed histogram
+ * as fit_count — inside the same kernel, no collective launch.  Equivalent to all_reduce(sum, int32[T]).
+ * Every rank must call cae_feasibility the same number of times; a rank that never arrives makes the others
+ * fail with status < 0 after ~2 s instead of hanging.
  *   cae_peer_handle: writes the 64-byte CUDA IPC handle of this engine's exchange buffer.
  *   cae_peer_attach: handles of all ranks in rank order (world * 64 bytes). */
 #define CAE_PEER_HANDLE_BYTES 64
 int32_t cae_peer_handle(cae_engine* e, void* handle);
 int32_t cae_peer_attach(cae_engine* e, const void* handles, int32_t world);
 
+/* Page-locked host memory for the caller's large input / output buffers (fit_bits, reasons): copies
+ * to and from pinned memory run at full PCIe speed and asynchronously. */
 void* cae_host_alloc(size_t bytes);
 void cae_host_free(void* p);
 

@@ -79,36 +79,19 @@ constexpr int K1_TW = FEAS_TW;            // template words (x32 templates) per 
 constexpr int K1_TCHUNK = K1_TW * 32;
 constexpr int K1_LPITCH = K1_TW + 1;      // odd row pitch of the staged threshold rows
 
-// Fused exchange of the fit histogram over peer memory (see cae_peer_attach in include/caengine.h)
+// Fused exchange of the fit histogram over peer memory (see cae_peer_attach in include/caengine.h): an
+// all-gather.  Every rank owns an exchange buffer [2 parities][PEER_MAX ranks][PEER_CAP]; a step writes the local
+// histogram into slot `rank` of EVERY rank's buffer (plain coalesced stores over NVLink), signals arrival with a
+// system-scope atomic, waits for all ranks and sums the slots.  Parities alternate between steps: a rank can only
+// reach step s+2 after every peer signalled s+1, i.e. after every peer finished reading step s.
 struct PeerPush {
-  int world;                 // 0 = disabled
-  int32_t* accum[8];         // every rank's accumulator slot for this step (P2P-mapped)
-  int32_t* arrive[8];        // every rank's arrival counter of that slot
+  int world, rank;           // world 0 = disabled
+  int target;                // arrival count that completes this step
+  int32_t* data[8];          // every rank's [PEER_MAX][PEER_CAP] block of this step's parity (P2P-mapped)
+  int32_t* arrive[8];        // every rank's arrival counter of that parity
   int32_t* done_ctr;         // local: template chunks published
+  int32_t* status;           // local: set to 1 when a peer never arrived
 };
-
-// Publishes the all-reduced histogram once every rank's contribution has arrived, and clears the slot.
-__global__ void peer_wait_kernel(int32_t* __restrict__ accum, volatile int32_t* arrive, int target, int T,
-                                 int32_t* __restrict__ fit_count, int32_t* __restrict__ status) {
-  __shared__ int s_ok;
-  if (threadIdx.x == 0) {
-    const long long t0 = clock64();
-    int ok = 1;
-    while (*arrive < target) {
-      if (clock64() - t0 > 4000000000ll) { ok = 0; break; }  // ~2 s: a peer died; fail instead of hanging the GPU
-      __nanosleep(200);
-    }
-    __threadfence_system();
-    s_ok = ok;
-    if (!ok) atomicExch(status, 1);
-  }
-  __syncthreads();
-  if (!s_ok) return;
-  for (int t = threadIdx.x; t < T; t += blockDim.x) {
-    fit_count[t] = __ldcg(&accum[t]);
-    accum[t] = 0;
-  }
-}
 
 struct K1Args {
   int Pl, Plw, T, Tw, Twp, N, U, W;
@@ -160,16 +143,36 @@ __device__ __forceinline__ void k1_finish(const K1Args& a, const PeerPush& pp, c
   }
   __syncthreads();
   if (!s_flag) return;
+  // the block that published the LAST chunk owns the complete local histogram: all-gather it
   __threadfence();
-  for (int t = tid; t < a.T; t += nthreads) {
-    const int v = __ldcg(&a.fit_count[t]);
-    if (v)
-      for (int r = 0; r < pp.world; ++r) atomicAdd_system(pp.accum[r] + t, v);
+  for (int r = 0; r < pp.world; ++r) {
+    int32_t* dst = pp.data[r] + (size_t)pp.rank * Engine::PEER_CAP;
+    for (int t = tid; t < a.T; t += nthreads) dst[t] = __ldcg(&a.fit_count[t]);
   }
   __threadfence_system();
   __syncthreads();
   if (tid < pp.world) atomicAdd_system(pp.arrive[tid], 1);
-  if (tid == 0) *pp.done_ctr = 0;
+  if (tid == 0) {
+    volatile int32_t* arr = pp.arrive[pp.rank];
+    const long long c0 = clock64();
+    int ok = 1;
+    while (*arr < pp.target) {
+      if (clock64() - c0 > 4000000000ll) { ok = 0; break; }  // ~2 s: a peer died; fail instead of hanging the GPU
+      __nanosleep(100);
+    }
+    __threadfence_system();
+    s_flag = ok;
+    if (!ok) atomicExch(pp.status, 1);
+    *pp.done_ctr = 0;
+  }
+  __syncthreads();
+  if (!s_flag) return;
+  const int32_t* mine = pp.data[pp.rank];
+  for (int t = tid; t < a.T; t += nthreads) {
+    int v = 0;
+    for (int r = 0; r < pp.world; ++r) v += __ldcg(&mine[(size_t)r * Engine::PEER_CAP + t]);
+    a.fit_count[t] = v;
+  }
 }
 
 // ---- 32x32 bit transposes across a warp ---------------------------------------------------------------------
@@ -420,26 +423,21 @@ feasibility_kernel(K1Args a, FeasLayout lay, PeerPush pp) {
 static PeerPush peer_push_args(Engine* e) {
   PeerPush pp{};
   if (e->peer_world > 1 && e->T <= Engine::PEER_CAP) {
-    const int slot = (int)(e->peer_step & 1);
+    const int par = (int)(e->peer_step & 1);
+    const size_t blk = (size_t)Engine::PEER_MAX * Engine::PEER_CAP;
     pp.world = e->peer_world;
+    pp.rank = e->cfg.rank;
+    e->peer_uses[par] += 1;
+    e->peer_step += 1;
+    pp.target = (int)(e->peer_uses[par] * e->peer_world);
     for (int r = 0; r < e->peer_world; ++r) {
-      pp.accum[r] = e->peer_base[r] + (size_t)slot * Engine::PEER_CAP;
-      pp.arrive[r] = e->peer_base[r] + (size_t)2 * Engine::PEER_CAP + slot;
+      pp.data[r] = e->peer_base[r] + par * blk;
+      pp.arrive[r] = e->peer_base[r] + 2 * blk + par;
     }
-    pp.done_ctr = e->d_xbuf + (size_t)2 * Engine::PEER_CAP + 8;
+    pp.done_ctr = e->d_xbuf + 2 * blk + 8;
+    pp.status = e->d_xbuf + 2 * blk + 9;
   }
   return pp;
-}
-
-static void launch_peer_wait(Engine* e) {
-  const int slot = (int)(e->peer_step & 1);
-  e->peer_uses[slot] += 1;
-  e->peer_step += 1;
-  peer_wait_kernel<<<1, 256, 0, e->stream>>>(e->d_xbuf + (size_t)slot * Engine::PEER_CAP,
-                                             e->d_xbuf + (size_t)2 * Engine::PEER_CAP + slot,
-                                             (int)(e->peer_uses[slot] * e->peer_world), e->T, e->d_fit_count,
-                                             e->d_xbuf + (size_t)2 * Engine::PEER_CAP + 9);
-  e->stats.kernel_launches++;
 }
 
 static K1Args k1_args(Engine* e) {
@@ -526,10 +524,6 @@ int launch_feasibility(Engine* e, bool want_reasons) {
   }
   e->stats.kernel_launches++;
   CAE_KERNEL_OK();
-  if (pp.world) {
-    launch_peer_wait(e);
-    CAE_KERNEL_OK();
-  }
   return 0;
 }
 
