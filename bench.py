@@ -28,18 +28,30 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 
-def _clock_sampler(stop, samples, dev):
-    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-    while not stop.is_set():
-        try:
-            out = subprocess.run(["nvidia-smi", "-i", str(dev), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                 capture_output=True, text=True, timeout=5).stdout.strip()
-            if out:
-                samples.append([x.strip() for x in out.split(",")])
-        except Exception:
-            pass
-        stop.wait(0.2)
+_CLOCK_QUERY = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+
+def _clock_sampler_start(devs):
+    """ONE looping nvidia-smi for the whole timed region (the profiling recipe's clocks line), started by rank 0
+    only: spawning nvidia-smi per sample from every rank stalls kernel launches on a multi-GPU box for milliseconds."""
+    try:
+        return subprocess.Popen(["nvidia-smi", "-i", ",".join(str(d) for d in devs), "--query-gpu=" + _CLOCK_QUERY,
+                                 "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except Exception:
+        return None
+
+
+def _clock_sampler_stop(proc):
+    if proc is None:
+        return []
+    try:
+        proc.terminate()
+        out, _ = proc.communicate(timeout=5)
+    except Exception:
+        proc.kill()
+        return []
+    return [[x.strip() for x in line.split(",")] for line in out.strip().splitlines() if line.count(",") >= 5]
 
 
 def _clocks_summary(samples):
@@ -255,9 +267,9 @@ def main():
         step_resident()
     torch.cuda.synchronize()
 
-    samples, stop = [], threading.Event()
-    th = threading.Thread(target=_clock_sampler, args=(stop, samples, local_rank), daemon=True)
-    th.start()
+    sampler = _clock_sampler_start(range(world)) if rank == 0 else None
+    if sampler is not None:
+        time.sleep(0.5)            # nvidia-smi initialises NVML on every GPU of the box: keep that out of the timed steps
     launches0 = eng.stats().kernel_launches
     dev_ms, wall_ms, ar_ms = [], [], []
     for _ in range(args.steps):
@@ -311,8 +323,7 @@ def main():
         tt = torch.tensor([e2e_step], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_step = float(tt[0])
-    stop.set()
-    th.join(timeout=2)
+    samples = _clock_sampler_stop(sampler)
 
     if rank != 0:
         if dist is not None:

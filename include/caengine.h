@@ -302,6 +302,27 @@ int32_t cae_expander_best(cae_engine* e, const int32_t* chain, int32_t chain_len
                           uint8_t* best_mask /* [T] 1 = in the surviving option set */,
                           double* waste_score /* [T], may be NULL */);
 
+/* The step BEFORE the scale-up path: filterOutSchedulablePodListProcessor.filterOutSchedulableByPacking ->
+ * HintingSimulator.TrySchedulePods on the cluster snapshot (cluster-autoscaler/core/podlistprocessor/
+ * filter_out_schedulable.go:96-126, simulator/scheduling/hinting_simulator.go:53-135), including the
+ * SimilarPodsScheduling shortcut (simulator/scheduling/similar_pods.go:59-112).  Pending pods that fit on the free
+ * capacity of EXISTING nodes are placed there, one by one in `pod_order`, and do not need a scale-up.
+ *   pod_order [n_pods]     pending-pod indices in processing order: the caller's priority sort (Go's sort.Slice is
+ *                          unstable, so the order among equal priorities is the caller's); fastest when identical
+ *                          pods are adjacent
+ *   hint_node [num_pending] cluster node hinted for a pod (Hints.Get), -1 = none; NULL = no hints
+ *   sim_class [num_pending] id of (controller UID, labels, spec) for pods owned by a non-DaemonSet controller, -1
+ *                          otherwise; NULL = none.  class_ctrl [n_classes] = controller id (>= 0) of a class
+ *   node_ok [N]            isNodeAcceptable, NULL = scheduling.ScheduleAnywhere
+ *   last_index_in          SchedulerPluginRunner.lastIndex before the call (0 for a fresh runner)
+ * Outputs: assigned_node [num_pending] = cluster node index, -1 = stays unschedulable (also for pods not in
+ * pod_order); the runner's lastIndex afterwards; SimilarPodsScheduling.OverflowingControllerCount().
+ * Uses the tables of the last cae_load (its templates are ignored); does not change the estimator's results. */
+int32_t cae_filter_schedulable(cae_engine* e, const int32_t* pod_order, int32_t n_pods, const int32_t* hint_node,
+                               const int32_t* sim_class, const int32_t* class_ctrl, int32_t n_classes, const uint8_t* node_ok,
+                               int32_t last_index_in, int32_t break_on_failure, int32_t* assigned_node,
+                               int32_t* last_index_out, int32_t* overflowing_controllers);
+
 int32_t cae_get_stats(cae_engine* e, cae_stats* out);
 
 /* Raw device pointers of the engine's result buffers, for zero-copy collectives (torch.distributed

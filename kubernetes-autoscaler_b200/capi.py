@@ -150,6 +150,9 @@ def load_engine_lib() -> C.CDLL:
     lib.cae_peer_attach.restype = C.c_int32
     lib.cae_device_buffer.argtypes = [C.c_void_p, C.c_int32, P(C.c_size_t)]
     lib.cae_device_buffer.restype = C.c_void_p
+    lib.cae_filter_schedulable.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                           C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.cae_filter_schedulable.restype = C.c_int32
     lib.cae_stream.argtypes = [C.c_void_p]
     lib.cae_stream.restype = C.c_void_p
     _engine_lib = lib

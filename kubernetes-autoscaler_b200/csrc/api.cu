@@ -336,7 +336,7 @@ static int do_load(Engine* e, const cae_objects* o) {
         uint32_t rank = (uint32_t)(std::upper_bound(rvals[a].begin(), rvals[a].end(), f) - rvals[a].begin());
         tmpl_w[(size_t)f_word[a] * T + t] |= (rank | (1u << (f_bits[a] - 1))) << f_shift[a];
       }
-    } else if (e->has_dynamic) {
+    } else {   // cluster nodes: run state of the hostname-spread fallback (K3) and of the filter-out-schedulable pass
       for (int a = 0; a < e->A; ++a) cfree[(size_t)a * N + row] = o->node_alloc[(size_t)row * R + e->act_dim[a]] - reqd[e->act_dim[a]];
       cslots[row] = o->node_allowed_pods[row] - npods;
     }
@@ -469,6 +469,8 @@ void cae_destroy(cae_engine* h) {
   e->up.release();
   e->scratch.release();
   if (e->d_pack_scratch) cudaFree(e->d_pack_scratch);
+  if (e->d_fm_scratch) cudaFree(e->d_fm_scratch);
+  if (e->d_fm_blob) cudaFree(e->d_fm_blob);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -666,6 +668,106 @@ void* cae_device_buffer(cae_engine* h, int32_t which, size_t* bytes) {
   if (which == 0) { if (bytes) *bytes = sizeof(int32_t) * e->T; return e->d_fit_count; }
   if (which == 1) { if (bytes) *bytes = sizeof(int32_t) * 2 * e->T; return e->d_counts2; }
   return nullptr;
+}
+
+int32_t cae_filter_schedulable(cae_engine* h, const int32_t* pod_order, int32_t n_pods, const int32_t* hint_node,
+                               const int32_t* sim_class, const int32_t* class_ctrl, int32_t n_classes, const uint8_t* node_ok,
+                               int32_t last_index_in, int32_t break_on_failure, int32_t* assigned_node,
+                               int32_t* last_index_out, int32_t* overflowing_controllers) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (!e || !e->loaded) { cae::set_error("cae_filter_schedulable before cae_load"); return -2; }
+  if (n_pods < 0 || (n_pods > 0 && !pod_order) || !assigned_node || (sim_class && n_classes > 0 && !class_ctrl)) {
+    cae::set_error("cae_filter_schedulable: bad arguments");
+    return -2;
+  }
+  cudaSetDevice(e->cfg.device);
+  const int P = e->P, N = e->N;
+  if (last_index_in < 0 || (N > 0 && last_index_in >= N)) last_index_in = 0;
+  // runs: consecutive pods of the order with the same spec and similarity class and no hint
+  std::vector<int32_t> run_off;
+  for (int k = 0; k < n_pods; ++k) {
+    const int pod = pod_order[k];
+    if (pod < 0 || pod >= P) { cae::set_error("cae_filter_schedulable: pod index out of range"); return -2; }
+    bool start = k == 0;
+    if (!start) {
+      const int prev = pod_order[k - 1];
+      start = e->h_pend_spec[pod] != e->h_pend_spec[prev] || (hint_node && (hint_node[pod] >= 0 || hint_node[prev] >= 0)) ||
+              (sim_class && sim_class[pod] != sim_class[prev]);
+    }
+    if (start) run_off.push_back(k);
+  }
+  run_off.push_back(n_pods);
+  const int runs = (int)run_off.size() - 1;
+  int nctrl = 0;
+  if (!sim_class) n_classes = 0;
+  for (int c = 0; c < n_classes; ++c) {
+    if (class_ctrl[c] < 0) { cae::set_error("cae_filter_schedulable: negative controller id"); return -2; }
+    nctrl = std::max(nctrl, class_ctrl[c] + 1);
+  }
+  if (sim_class)
+    for (int i = 0; i < P; ++i)
+      if (sim_class[i] >= n_classes) { cae::set_error("cae_filter_schedulable: similarity class out of range"); return -2; }
+  // one blob: run_off | pods | hint | class | class_ctrl | assigned | out[4] | ctrl_cnt | node_ok, class_mark, ctrl_over (bytes)
+  auto words = [](size_t bytes) { return (bytes + 3) / 4; };
+  size_t off = 0;
+  const size_t o_run = off; off += runs + 1;
+  const size_t o_pods = off; off += std::max(n_pods, 1);
+  const size_t o_hint = off; off += hint_node ? P : 0;
+  const size_t o_cls = off; off += sim_class ? P : 0;
+  const size_t o_cc = off; off += std::max(n_classes, 1);
+  const size_t o_in_end = off;
+  const size_t o_nodeok = off; off += node_ok ? words(N) : 0;
+  const size_t o_in_end2 = off;
+  const size_t o_asg = off; off += std::max(P, 1);
+  const size_t o_out = off; off += 4;
+  const size_t o_cnt = off; off += std::max(nctrl, 1);
+  const size_t o_mark = off; off += words(std::max(n_classes, 1));
+  const size_t o_over = off; off += words(std::max(nctrl, 1));
+  (void)o_in_end;
+  if (off > e->fm_blob_words) {
+    if (e->d_fm_blob) cudaFree(e->d_fm_blob);
+    e->d_fm_blob = nullptr;
+    e->fm_blob_words = 0;
+    CAE_CUDA(cudaMalloc(&e->d_fm_blob, off * 4));
+    e->fm_blob_words = off;
+  }
+  std::vector<int32_t> hostblob(o_in_end2, 0);
+  std::copy(run_off.begin(), run_off.end(), hostblob.begin() + o_run);
+  if (n_pods) std::copy(pod_order, pod_order + n_pods, hostblob.begin() + o_pods);
+  if (hint_node) std::copy(hint_node, hint_node + P, hostblob.begin() + o_hint);
+  if (sim_class) std::copy(sim_class, sim_class + P, hostblob.begin() + o_cls);
+  if (n_classes) std::copy(class_ctrl, class_ctrl + n_classes, hostblob.begin() + o_cc);
+  if (node_ok && N) memcpy(hostblob.data() + o_nodeok, node_ok, N);
+  CAE_CUDA(cudaMemcpyAsync(e->d_fm_blob, hostblob.data(), o_in_end2 * 4, cudaMemcpyHostToDevice, e->stream));
+  CAE_CUDA(cudaMemsetAsync(e->d_fm_blob + o_asg, 0xFF, (size_t)std::max(P, 1) * 4, e->stream));   // -1 = stays unschedulable
+  CAE_CUDA(cudaMemsetAsync(e->d_fm_blob + o_out, 0, (off - o_out) * 4, e->stream));
+  cae::FilterLaunch f{};
+  f.runs = runs; f.n_pods = n_pods; f.last_index = last_index_in; f.break_on_failure = break_on_failure ? 1 : 0; f.nctrl = nctrl;
+  f.run_off = e->d_fm_blob + o_run; f.pods = e->d_fm_blob + o_pods;
+  f.hint = hint_node ? e->d_fm_blob + o_hint : nullptr;
+  f.cls = sim_class ? e->d_fm_blob + o_cls : nullptr;
+  f.class_ctrl = e->d_fm_blob + o_cc;
+  f.node_ok = node_ok ? reinterpret_cast<const uint8_t*>(e->d_fm_blob + o_nodeok) : nullptr;
+  f.assigned = e->d_fm_blob + o_asg; f.out = e->d_fm_blob + o_out; f.ctrl_cnt = e->d_fm_blob + o_cnt;
+  f.class_mark = reinterpret_cast<uint8_t*>(e->d_fm_blob + o_mark);
+  f.ctrl_over = reinterpret_cast<uint8_t*>(e->d_fm_blob + o_over);
+  cudaEventRecord(e->ev0, e->stream);
+  if (runs > 0 && cae::launch_filter(e, f)) return -1;
+  cudaEventRecord(e->ev1, e->stream);
+  int32_t out[4] = {last_index_in, 0, 0, 0}, status = 0;
+  if (P) CAE_CUDA(cudaMemcpyAsync(assigned_node, e->d_fm_blob + o_asg, (size_t)P * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (runs > 0) {
+    CAE_CUDA(cudaMemcpyAsync(out, e->d_fm_blob + o_out, sizeof(out), cudaMemcpyDeviceToHost, e->stream));
+    CAE_CUDA(cudaMemcpyAsync(&status, e->d_work_counter + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+  }
+  CAE_CUDA(cudaStreamSynchronize(e->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+  e->stats.estimate_ms = ms;
+  if (status) { cae::set_error("placement log overflow in the filter pass"); return 1; }
+  if (last_index_out) *last_index_out = out[0];
+  if (overflowing_controllers) *overflowing_controllers = out[1];
+  return 0;
 }
 
 void* cae_stream(cae_engine* h) {

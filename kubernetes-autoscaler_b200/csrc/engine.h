@@ -133,6 +133,11 @@ struct Engine {
   void* d_pack_scratch = nullptr;
   size_t pack_scratch_bytes = 0;
   size_t pack_layout_sig = 0;
+  // filter-out-schedulable pass (pack.cu, FM): own slab + input blob
+  void* d_fm_scratch = nullptr;
+  size_t fm_scratch_bytes = 0, fm_layout_sig = 0;
+  int32_t* d_fm_blob = nullptr;
+  size_t fm_blob_words = 0;
   // fused histogram exchange over peer memory (feas.cu)
   static constexpr int PEER_MAX = 8, PEER_CAP = 1 << 16;
   int32_t* d_xbuf = nullptr;              // [2][PEER_MAX][PEER_CAP] all-gather slots + [2] arrival counters, done counter, status
@@ -159,6 +164,14 @@ int launch_feasibility(Engine* e, bool want_reasons);
 int launch_group_feasibility(Engine* e);
 int launch_order(Engine* e);
 int launch_pack(Engine* e);
+struct FilterLaunch {
+  int runs, n_pods, last_index, break_on_failure, nctrl;
+  const int32_t *run_off, *pods, *hint, *cls, *class_ctrl;
+  const uint8_t* node_ok;
+  int32_t *assigned, *out, *ctrl_cnt;
+  uint8_t *class_mark, *ctrl_over;
+};
+int launch_filter(Engine* e, const FilterLaunch& f);
 int launch_expander(Engine* e, const int32_t* chain, int chain_len, const int32_t* d_node_count,
                     const int32_t* d_pod_count, const int32_t* d_sched, uint8_t* d_mask, double* d_waste);
 

@@ -18,6 +18,13 @@
 // the nodes added so far and the run's placement log, then updated on every placement; nodes that
 // failed are stamped and skipped until a counter minimum / presence changes (only then can a failed
 // node become feasible again).
+//
+// FM = true turns the same machinery into HintingSimulator.TrySchedulePods on the CLUSTER snapshot
+// (simulator/scheduling/hinting_simulator.go:53-135; filterOutSchedulableByPacking,
+// core/podlistprocessor/filter_out_schedulable.go:96-126): one simulation (one warp), no template, the node
+// list is the N cluster nodes, pods arrive as runs of consecutive identical pods in the caller's order and
+// every pod is placed with the per-pod loop (hint first, then SchedulePodOnAnyNodeMatching from lastIndex),
+// with the SimilarPodsScheduling shortcut (similar_pods.go:59-104).
 #include <climits>
 
 #include "engine.h"
@@ -39,6 +46,14 @@ struct PackParams {
   int32_t *node_count, *pod_count, *sched, *work_counter, *status;
   unsigned char* scratch;
   size_t scratch_per_warp;
+  // FM (filter-out-schedulable) only
+  int fm_runs, fm_last_index, fm_break;
+  const int32_t *fm_run_off, *fm_pods, *fm_hint, *fm_class, *fm_class_ctrl;
+  const uint8_t* fm_node_ok;
+  int32_t *fm_assigned, *fm_out;          // [P] node or -1; {lastIndex, overflowing controllers, pods scheduled}
+  int32_t* fm_ctrl_cnt;                   // [controllers] classes stored per controller (zeroed)
+  uint8_t *fm_class_mark, *fm_ctrl_over;  // [classes] known unschedulable, [controllers] overflowing (zeroed)
+  int fm_nctrl;
 };
 
 __device__ __forceinline__ int wsum(int v) {
@@ -73,7 +88,7 @@ struct WarpDyn {
 
 constexpr int PACK_WARPS = 4;
 
-template <int A>
+template <int A, bool FM>
 __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, DynTables d, PackParams p) {
   __shared__ WarpDyn s_wd[PACK_WARPS];
   const int lane = threadIdx.x & 31;
@@ -81,7 +96,8 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   unsigned char* slab = p.scratch + (size_t)warp_global * p.scratch_per_warp;
   const int N = p.N, NT = p.N + p.T;
-  const int Neff = p.has_dyn ? N : 0;  // cluster nodes carry run state only when a fallback can reach them
+  if (FM && warp_global != 0) return;
+  const int Neff = (p.has_dyn || FM) ? N : 0;  // cluster nodes carry run state only when a placement can reach them
   const int X = Neff + p.cap;
   int32_t* hdr = reinterpret_cast<int32_t*>(slab);  // stamp / version counters survive across launches
   int64_t* nfree = reinterpret_cast<int64_t*>(slab + 16);                             // [A][X]
@@ -108,13 +124,13 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
 
     int64_t tfree[A > 0 ? A : 1];
 #pragma unroll
-    for (int a = 0; a < A; ++a) tfree[a] = p.tmpl_free[(size_t)a * p.T + t];
-    const int tslots = p.tmpl_slots[t];
-    const int max_nodes = p.max_nodes ? p.max_nodes[t] : 0;
+    for (int a = 0; a < A; ++a) tfree[a] = FM ? 0 : p.tmpl_free[(size_t)a * p.T + t];
+    const int tslots = FM ? 0 : p.tmpl_slots[t];
+    const int max_nodes = (!FM && p.max_nodes) ? p.max_nodes[t] : 0;
     const int col_new = N + p.T + t;  // universe column of the sanitized template
-    int n_new = 0, nodes_with_pods = 0, pods_total = 0, last_index = 0, log_n = 0;
-    bool new_nodes_available = true, cl_init = false, overflow = false;
-    const int n_groups = p.order_n[t];
+    int n_new = 0, nodes_with_pods = 0, pods_total = 0, last_index = FM ? p.fm_last_index : 0, log_n = 0;
+    bool new_nodes_available = !FM, cl_init = false, overflow = false, fm_stop = false;
+    const int n_groups = FM ? p.fm_runs : p.order_n[t];
 
     // ---- shared helpers -----------------------------------------------------------------------
     auto slot_of = [&](int q, int x) -> int {
@@ -156,24 +172,29 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
     };
 
     for (int gi = 0; gi < n_groups; ++gi) {
-      const int g = p.order[(size_t)t * p.E + gi];
-      const int pb = o.group_off[g];
-      int n = o.group_off[g + 1] - pb;
-      const int spec = o.pend_spec[pb];
+      const int g = FM ? 0 : p.order[(size_t)t * p.E + gi];
+      const int pb = FM ? p.fm_run_off[gi] : o.group_off[g];
+      int n = (FM ? p.fm_run_off[gi + 1] : o.group_off[g + 1]) - pb;
+      const int spec = o.pend_spec[FM ? p.fm_pods[pb] : pb];
       int64_t req[A > 0 ? A : 1];
 #pragma unroll
       for (int a = 0; a < A; ++a) req[a] = o.ps_req[(size_t)spec * R + p.act_dim[a]];
       const int sc = p.spec_sc[spec];
       const int dc = p.has_dyn ? p.spec_dc[spec] : 0;
-      const bool static_new = (p.pre_code[(size_t)sc * p.U + col_new] & 0x0F) == 0;
+      const bool static_new = !FM && (p.pre_code[(size_t)sc * p.U + col_new] & 0x0F) == 0;
       const int plist = o.ps_port_list[spec];
       const bool has_ports = o.port_off[plist + 1] > o.port_off[plist];
       const unsigned long long pconf = has_ports ? p.port_conf[plist] : 0ull;  // port sets this pod collides with
       const unsigned long long pbit = has_ports ? (1ull << p.pc_of[plist]) : 0ull;
-      const bool feeds = p.has_dyn && d.group_feeds[g];
+      bool feeds = p.has_dyn && !FM && d.group_feeds[g];
+      if (FM && p.has_dyn) {   // runs are not groups: log every placement that some counter counts
+        bool any = false;
+        for (int q = lane; q < d.Q; q += 32) any |= d.wmat[(size_t)q * d.S + spec] != 0;
+        feeds = __ballot_sync(0xffffffffu, any) != 0u;
+      }
       int placed = 0;
 
-      if (dc == 0) {
+      if (dc == 0 && !FM) {
         // ======================= plain group: closed form =======================================
         if (n_new > 0 && static_new) {
           const int list_len = N + n_new;
@@ -369,24 +390,24 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
         __syncwarp();
         if (lane == 0) {
           int nq = 0;
-          for (int q = d.dc_q_off[dc]; q < d.dc_q_off[dc + 1]; ++q) {
+          for (int q = p.has_dyn ? d.dc_q_off[dc] : 0; q < (p.has_dyn ? d.dc_q_off[dc + 1] : 0); ++q) {
             if (!d.q_active[q]) continue;
             const int k = d.q_k[q], kind = d.q_kind[q];
             wd.qid[nq] = q; wd.kind[nq] = kind; wd.k[nq] = k; wd.host[nq] = d.is_host[k]; wd.Dc[nq] = d.Dc[k];
-            const int td = d.dom[(size_t)k * NT + N + t];
+            const int td = FM ? -1 : d.dom[(size_t)k * NT + N + t];   // FM: no template, nothing is ever added
             wd.tslot[nq] = td < 0 ? -1 : (td < d.Dc[k] ? td : d.Dc[k]);
             wd.wown[nq] = d.q_wown[q]; wd.self[nq] = d.q_self[q];
             wd.maxskew[nq] = kind == Q_PTS ? o.pts_max_skew[d.q_p0[q]] : 0;
             wd.mindom[nq] = kind == Q_PTS ? o.pts_min_domains[d.q_p0[q]] : 0;
-            wd.elig_new[nq] = d.elig[(size_t)q * p.U + col_new];
-            wd.dsw[nq] = d.ds_w[(size_t)q * p.T + t];
+            wd.elig_new[nq] = FM ? 0 : d.elig[(size_t)q * p.U + col_new];
+            wd.dsw[nq] = FM ? 0 : d.ds_w[(size_t)q * p.T + t];
             wd.tot[nq] = d.base_tot[q];
             wd.boff[nq] = d.q_base_off[q];
             wd.minv[nq] = d.st_min1[q]; wd.nmin[nq] = d.st_nmin[q]; wd.ndom[nq] = d.st_ndom[q];
             ++nq;
           }
           wd.nq = nq;
-          wd.aff_self = d.dc_aff_self[dc];
+          wd.aff_self = p.has_dyn ? d.dc_aff_self[dc] : 0;
         }
         __syncwarp();
         const int nq = wd.nq;
@@ -454,7 +475,7 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
             }
           }
           __syncwarp();
-          if (d.q_nfeed[wd.qid[q]] - (wd.wown[q] > 0 ? 1 : 0) > 0) need_log = true;
+          if (FM || d.q_nfeed[wd.qid[q]] - (wd.wown[q] > 0 ? 1 : 0) > 0) need_log = true;   // FM: earlier runs of this very spec count too
           if (full) recompute(q);
         }
         __syncwarp();
@@ -634,6 +655,59 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
         };
         (void)n_new_start;
 
+        if (FM) {
+          // ---- HintingSimulator.TrySchedulePods over the cluster nodes, pod by pod ----
+          ensure_cluster();
+          const int len = N;
+          const int run_n = n;
+          const int cls = p.fm_class ? p.fm_class[p.fm_pods[pb]] : -1;
+          bool blocked = cls >= 0 && p.fm_class_mark[cls] != 0;   // IsSimilarUnschedulable (similar_pods.go:68-84)
+          bool run_failed = false;  // a pod of this run fitted nowhere: the identical pods behind it see the same state
+          for (int i = 0; i < run_n; ++i) {
+            const int pod = p.fm_pods[pb + i];
+            int where = -1;
+            if (!fm_stop) {
+              const int h = p.fm_hint ? p.fm_hint[pod] : -1;   // tryScheduleUsingHints (:80-106); lastIndex untouched
+              if (h >= 0 && h < N && (!p.fm_node_ok || p.fm_node_ok[h]) && eval(h) == CAE_R_OK) { place(h); where = h; }
+              if (where < 0 && !blocked && !run_failed && len > 0) {
+                // SchedulePodOnAnyNodeMatching (:117): whole list, cyclic from lastIndex
+                int hit = -1;
+                for (int base = 0; base < len && hit < 0; base += 32) {
+                  const int pos = base + lane;
+                  int idx = last_index + pos;
+                  if (idx >= len) idx -= len;
+                  bool ok = false;
+                  if (pos < len && !o.node_unschedulable[idx] && (!p.fm_node_ok || p.fm_node_ok[idx]) && stamp[idx] != cur_stamp) {
+                    ok = eval(idx) == CAE_R_OK;
+                    if (!ok) stamp[idx] = cur_stamp;
+                  }
+                  const unsigned m = __ballot_sync(0xffffffffu, ok);
+                  if (m) hit = __shfl_sync(0xffffffffu, idx, __ffs(m) - 1);
+                }
+                if (hit >= 0) {
+                  place(hit);
+                  last_index = (hit + 1) % len;
+                  where = hit;
+                } else {
+                  run_failed = true;
+                  if (cls >= 0) {  // SetUnschedulable (similar_pods.go:87-104): at most 10 infos per controller
+                    const int ctrl = p.fm_class_ctrl[cls];
+                    const int cnt = p.fm_ctrl_cnt[ctrl];
+                    __syncwarp();
+                    if (lane == 0) {
+                      if (cnt >= 10) p.fm_ctrl_over[ctrl] = 1;
+                      else { p.fm_ctrl_cnt[ctrl] = cnt + 1; p.fm_class_mark[cls] = 1; }
+                    }
+                    if (cnt < 10) blocked = true;
+                    __syncwarp();
+                  }
+                }
+              }
+              if (where < 0 && p.fm_break) fm_stop = true;   // breakOnFailure (:71-73)
+            }
+            if (lane == 0) p.fm_assigned[pod] = where;
+          }
+        } else {
         // ---- tryToScheduleOnExistingNodes: per pod, first passing added node in cyclic order ----
         while (n > 0 && n_new > 0) {
           const int s = last_index >= N ? last_index - N : 0;
@@ -721,11 +795,21 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
             place(Neff + n_new - 1);
           }
         }
+        }  // !FM
       }
       pods_total += placed;
-      if (lane == 0 && p.sched) p.sched[(size_t)t * p.E + g] = placed;
+      if (!FM && lane == 0 && p.sched) p.sched[(size_t)t * p.E + g] = placed;
     }
-    if (lane == 0) {
+    if (FM) {
+      int over = 0;
+      for (int c = lane; c < p.fm_nctrl; c += 32) over += p.fm_ctrl_over[c] != 0;
+      over = wsum(over);
+      if (lane == 0) {
+        hdr[0] = stamp_ctr; hdr[1] = gver_ctr;
+        p.fm_out[0] = last_index; p.fm_out[1] = over; p.fm_out[2] = pods_total;
+        if (overflow && p.status) atomicExch(p.status, 1);
+      }
+    } else if (lane == 0) {
       hdr[0] = stamp_ctr; hdr[1] = gver_ctr;
       p.node_count[t] = nodes_with_pods;
       p.pod_count[t] = pods_total;
@@ -735,33 +819,35 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
   }
 }
 
-template <int A>
+template <int A, bool FM>
 static void launch_pack_a(int blocks, cudaStream_t st, const DevObjects& o, const DynTables& d, const PackParams& p) {
-  pack_kernel<A><<<blocks, PACK_WARPS * 32, 0, st>>>(o, d, p);
+  pack_kernel<A, FM><<<blocks, PACK_WARPS * 32, 0, st>>>(o, d, p);
 }
 
-int launch_pack(Engine* e) {
-  int nt = e->t_end - e->t_begin;
-  if (nt <= 0) return 0;
-  PackParams p{};
-  p.E = e->E; p.T = e->T; p.N = e->N; p.U = e->U; p.t_begin = e->t_begin; p.t_end = e->t_end;
-  p.has_dyn = e->has_dynamic ? 1 : 0;
-  for (int a = 0; a < CAE_MAX_RES; ++a) p.act_dim[a] = e->act_dim[a];
-  p.order = e->d_order; p.order_n = e->d_order_n; p.pre_code = e->d_pre_code; p.spec_sc = e->d_spec_sc; p.spec_dc = e->d_spec_dc;
-  p.tmpl_free = e->d_tmpl_free; p.tmpl_slots = e->d_tmpl_slots; p.max_nodes = e->d_max_nodes;
-  p.pc_of = e->d_pc_of; p.port_conf = e->d_port_conf; p.c_free = e->d_c_free; p.c_slots = e->d_c_slots;
-  p.node_count = e->d_counts2; p.pod_count = e->d_counts2 + e->T; p.sched = e->d_sched;
-  p.work_counter = e->d_work_counter; p.status = e->d_work_counter + 1;
-  // node capacity of a slab: the largest limiter cap, or (unlimited) one node per pod + 1
-  // (every added node but possibly one holds >= 1 pod)
-  const int cap = std::max(1, std::min(e->P + 1, e->pack_cap));
+template <bool FM>
+static void launch_pack_any(int A, int blocks, cudaStream_t st, const DevObjects& o, const DynTables& d, const PackParams& p) {
+  switch (A) {
+    case 0: launch_pack_a<0, FM>(blocks, st, o, d, p); break;
+    case 1: launch_pack_a<1, FM>(blocks, st, o, d, p); break;
+    case 2: launch_pack_a<2, FM>(blocks, st, o, d, p); break;
+    case 3: launch_pack_a<3, FM>(blocks, st, o, d, p); break;
+    case 4: launch_pack_a<4, FM>(blocks, st, o, d, p); break;
+    case 5: launch_pack_a<5, FM>(blocks, st, o, d, p); break;
+    case 6: launch_pack_a<6, FM>(blocks, st, o, d, p); break;
+    case 7: launch_pack_a<7, FM>(blocks, st, o, d, p); break;
+    default: launch_pack_a<8, FM>(blocks, st, o, d, p); break;
+  }
+}
+
+// slab layout shared by the estimator and the filter pass: returns bytes per warp, fills the layout fields of p
+static size_t pack_layout(const Engine* e, PackParams& p, int cap, bool cluster_state, int log_cap) {
   p.cap = cap;
-  const int Neff = p.has_dyn ? e->N : 0;
+  const int Neff = cluster_state ? e->N : 0;
   const size_t X = (size_t)Neff + cap;
   int dmax = 1;
   for (int k = 0; k < e->dyn.K; ++k) dmax = std::max(dmax, e->dyn.Dc[k] + 1 + (e->dyn.is_host[k] ? cap : 0));
   p.dstride = p.has_dyn ? dmax : 1;
-  p.log_cap = p.has_dyn ? (int)std::min<size_t>(4 * X + 1024, (size_t)1 << 24) : 1;
+  p.log_cap = log_cap;
   const int A1 = std::max(e->A, 1);
   p.nblk = (cap + 31) / 32 + 1;
   size_t per_warp = 16 + X * ((size_t)A1 * 8 + 8 + 4 + 4 + 4) + (size_t)3 * DYN_MAX_Q * p.dstride * 4 + (size_t)p.log_cap * 12 + (size_t)(p.nblk + p.nblk / 32 + 2) * 4;
@@ -769,6 +855,33 @@ int launch_pack(Engine* e) {
   p.bmax_off = per_warp;
   per_warp += (size_t)A1 * p.nblk * 8 + X;
   per_warp = (per_warp + 255) & ~(size_t)255;
+  return per_warp;
+}
+
+static void pack_common(const Engine* e, PackParams& p) {
+  p.E = e->E; p.T = e->T; p.N = e->N; p.U = e->U;
+  p.has_dyn = e->has_dynamic ? 1 : 0;
+  for (int a = 0; a < CAE_MAX_RES; ++a) p.act_dim[a] = e->act_dim[a];
+  p.order = e->d_order; p.order_n = e->d_order_n; p.pre_code = e->d_pre_code; p.spec_sc = e->d_spec_sc; p.spec_dc = e->d_spec_dc;
+  p.tmpl_free = e->d_tmpl_free; p.tmpl_slots = e->d_tmpl_slots; p.max_nodes = e->d_max_nodes;
+  p.pc_of = e->d_pc_of; p.port_conf = e->d_port_conf; p.c_free = e->d_c_free; p.c_slots = e->d_c_slots;
+  p.node_count = e->d_counts2; p.pod_count = e->d_counts2 + e->T; p.sched = e->d_sched;
+  p.work_counter = e->d_work_counter; p.status = e->d_work_counter + 1;
+}
+
+int launch_pack(Engine* e) {
+  int nt = e->t_end - e->t_begin;
+  if (nt <= 0) return 0;
+  PackParams p{};
+  pack_common(e, p);
+  p.t_begin = e->t_begin; p.t_end = e->t_end;
+  // node capacity of a slab: the largest limiter cap, or (unlimited) one node per pod + 1
+  // (every added node but possibly one holds >= 1 pod)
+  const int cap = std::max(1, std::min(e->P + 1, e->pack_cap));
+  const size_t X = (size_t)(p.has_dyn ? e->N : 0) + cap;
+  const int log_cap = p.has_dyn ? (int)std::min<size_t>(4 * X + 1024, (size_t)1 << 24) : 1;
+  const size_t per_warp = pack_layout(e, p, cap, p.has_dyn != 0, log_cap);
+  const int A1 = std::max(e->A, 1);
   int warps = std::min(nt, e->sm_count * 20);
   const size_t budget = (size_t)24 << 30;  // keep the slabs within 24 GiB of the 180 GB HBM
   if (per_warp * warps > budget) warps = (int)std::max<size_t>(1, budget / per_warp);
@@ -791,17 +904,42 @@ int launch_pack(Engine* e) {
   p.scratch = static_cast<unsigned char*>(e->d_pack_scratch);
   p.scratch_per_warp = per_warp;
   CAE_CUDA(cudaMemsetAsync(e->d_work_counter, 0, sizeof(int32_t) * 2, e->stream));
-  switch (e->A) {
-    case 0: launch_pack_a<0>(blocks, e->stream, e->dobj, e->dyn, p); break;
-    case 1: launch_pack_a<1>(blocks, e->stream, e->dobj, e->dyn, p); break;
-    case 2: launch_pack_a<2>(blocks, e->stream, e->dobj, e->dyn, p); break;
-    case 3: launch_pack_a<3>(blocks, e->stream, e->dobj, e->dyn, p); break;
-    case 4: launch_pack_a<4>(blocks, e->stream, e->dobj, e->dyn, p); break;
-    case 5: launch_pack_a<5>(blocks, e->stream, e->dobj, e->dyn, p); break;
-    case 6: launch_pack_a<6>(blocks, e->stream, e->dobj, e->dyn, p); break;
-    case 7: launch_pack_a<7>(blocks, e->stream, e->dobj, e->dyn, p); break;
-    default: launch_pack_a<8>(blocks, e->stream, e->dobj, e->dyn, p); break;
+  launch_pack_any<false>(e->A, blocks, e->stream, e->dobj, e->dyn, p);
+  e->stats.kernel_launches++;
+  CAE_KERNEL_OK();
+  return 0;
+}
+
+// HintingSimulator.TrySchedulePods on the cluster snapshot (one warp).  `in` = device blob laid out by
+// cae_filter_schedulable (api.cu); scratch (class marks, controller counters) is zeroed here.
+int launch_filter(Engine* e, const FilterLaunch& f) {
+  PackParams p{};
+  pack_common(e, p);
+  p.t_begin = 0; p.t_end = 1;
+  p.fm_runs = f.runs; p.fm_last_index = f.last_index; p.fm_break = f.break_on_failure;
+  p.fm_run_off = f.run_off; p.fm_pods = f.pods; p.fm_hint = f.hint; p.fm_class = f.cls; p.fm_class_ctrl = f.class_ctrl;
+  p.fm_node_ok = f.node_ok; p.fm_assigned = f.assigned; p.fm_out = f.out;
+  p.fm_ctrl_cnt = f.ctrl_cnt; p.fm_class_mark = f.class_mark; p.fm_ctrl_over = f.ctrl_over; p.fm_nctrl = f.nctrl;
+  const int log_cap = p.has_dyn ? f.n_pods + 1024 : 1;   // one entry per placement at most
+  const size_t per_warp = pack_layout(e, p, 1, true, log_cap);
+  const size_t need = per_warp * PACK_WARPS;
+  const size_t sig = per_warp * 1000003u + (size_t)e->N * 10007u + (size_t)p.dstride * 101u + (size_t)p.log_cap * 7u + (size_t)std::max(e->A, 1);
+  if (need > e->fm_scratch_bytes) {
+    if (e->d_fm_scratch) cudaFree(e->d_fm_scratch);
+    e->d_fm_scratch = nullptr;
+    e->fm_scratch_bytes = 0;
+    CAE_CUDA(cudaMalloc(&e->d_fm_scratch, need));
+    e->fm_scratch_bytes = need;
+    e->fm_layout_sig = 0;
   }
+  if (sig != e->fm_layout_sig) {
+    CAE_CUDA(cudaMemsetAsync(e->d_fm_scratch, 0, need, e->stream));
+    e->fm_layout_sig = sig;
+  }
+  p.scratch = static_cast<unsigned char*>(e->d_fm_scratch);
+  p.scratch_per_warp = per_warp;
+  CAE_CUDA(cudaMemsetAsync(e->d_work_counter, 0, sizeof(int32_t) * 2, e->stream));
+  launch_pack_any<true>(e->A, 1, e->stream, e->dobj, e->dyn, p);
   e->stats.kernel_launches++;
   CAE_KERNEL_OK();
   return 0;

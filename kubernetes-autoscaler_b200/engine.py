@@ -175,6 +175,24 @@ class Engine:
         self._check(self.lib.cae_expander_best(self.h, vp(ch), len(ch), vp(nc), vp(pc), vp(sc), vp(mask), vp(waste)))
         return mask, waste
 
+    def filter_schedulable(self, pod_order: Sequence[int], hint_node=None, sim_class=None, class_ctrl=None, node_ok=None,
+                           last_index: int = 0, break_on_failure: bool = False):
+        """HintingSimulator.TrySchedulePods on the cluster snapshot of the last load.  Returns (assigned[P] cluster node
+        index or -1, lastIndex afterwards, overflowing controller count)."""
+        enc = self.enc
+        order = np.ascontiguousarray(pod_order, np.int32)
+        hn = None if hint_node is None else np.ascontiguousarray(hint_node, np.int32)
+        sc = None if sim_class is None else np.ascontiguousarray(sim_class, np.int32)
+        cc = None if class_ctrl is None else np.ascontiguousarray(class_ctrl, np.int32)
+        ok = None if node_ok is None else np.ascontiguousarray(node_ok, np.uint8)
+        assigned = np.full(max(enc.P, 1), -1, np.int32)
+        li, ov = np.zeros(1, np.int32), np.zeros(1, np.int32)
+        vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        self._check(self.lib.cae_filter_schedulable(self.h, vp(order), len(order), vp(hn), vp(sc), vp(cc),
+                                                    0 if cc is None else len(cc), vp(ok), int(last_index), int(break_on_failure),
+                                                    vp(assigned), vp(li), vp(ov)))
+        return assigned[:enc.P], int(li[0]), int(ov[0])
+
     # ---- fused histogram exchange over peer memory (multi-GPU dense pass) -------------------------
     def peer_handle(self) -> bytes:
         buf = C.create_string_buffer(capi.CONST["CAE_PEER_HANDLE_BYTES"])

@@ -104,6 +104,8 @@ class Pod:
     # controller reference (drain.ControllerRef): only equivalence.BuildPodGroups reads it
     owner_uid: str = ""
     owner_kind: str = ""
+    # spec.priority (corev1helpers.PodPriority: 0 when unset); only the filter-out-schedulable ordering reads it
+    priority: int = 0
 
     def clone(self) -> "Pod":
         return copy.deepcopy(self)

@@ -104,6 +104,7 @@ def pod_from_json(p: Dict[str, Any]) -> Pod:
     pod.pod_affinity = _affinity_terms((aff.get("podAffinity") or {}).get("requiredDuringSchedulingIgnoredDuringExecution"))
     pod.pod_anti_affinity = _affinity_terms((aff.get("podAntiAffinity") or {}).get("requiredDuringSchedulingIgnoredDuringExecution"))
     pod.terminating = meta.get("deletionTimestamp") is not None
+    pod.priority = int(spec.get("priority") or 0)
     # pods the engine must hand to the stock path (SURVEY §7 hard part 7): PVC / ephemeral volumes, DRA claims
     vols = spec.get("volumes") or []
     pod.has_volumes_or_claims = bool(spec.get("resourceClaims")) or any(

@@ -697,6 +697,60 @@ int cao_estimate_all(const cae_objects* o, const int32_t* max_nodes, int t_begin
 
 double cao_pod_score(const cae_objects* o, int spec, int tmpl) { return podScore(o, spec, o->num_cluster_nodes + tmpl); }
 
+/* filterOutSchedulablePodListProcessor.filterOutSchedulableByPacking -> HintingSimulator.TrySchedulePods
+ * (core/podlistprocessor/filter_out_schedulable.go:96-126, simulator/scheduling/hinting_simulator.go:53-135,
+ * simulator/scheduling/similar_pods.go:59-112), breakOnFailure = false, on the cluster snapshot.
+ *   pod_order   pending-pod indices in processing order (the caller's priority sort; Go's sort.Slice is unstable,
+ *               so the order among equal priorities is the caller's to fix)
+ *   hint_node   [num_pending] hinted cluster node of a pod (Hints.Get), -1 = none; NULL = no hints
+ *   sim_class   [num_pending] id of (controller UID, labels, spec) for pods with a controller that is not a
+ *               DaemonSet, -1 otherwise (ControllerRef nil / IsDaemonSetPod); NULL = none
+ *   class_ctrl  [classes] controller id of a class
+ *   node_ok     [N] isNodeAcceptable, NULL = ScheduleAnywhere
+ * Outputs: assigned[num_pending] = cluster node the pod was placed on, -1 = stays unschedulable;
+ * the runner's lastIndex afterwards; OverflowingControllerCount. */
+int cao_filter_schedulable(const cae_objects* o, const int32_t* pod_order, int n_pods, const int32_t* hint_node,
+                           const int32_t* sim_class, const int32_t* class_ctrl, const uint8_t* node_ok, int last_index_in,
+                           int break_on_failure, int32_t* assigned, int32_t* last_index_out, int32_t* overflowing) {
+  Snapshot s(o);
+  s.loadCluster();
+  s.last_index = last_index_in;
+  const int N = o->num_cluster_nodes;
+  for (int i = 0; i < o->num_pending; ++i) assigned[i] = -1;
+  std::map<int, std::vector<int>> items;   /* controller -> classes known unschedulable (SimilarPodsScheduling.items) */
+  std::set<int> over;                      /* overflowingControllers */
+  for (int k = 0; k < n_pods; ++k) {
+    const int pod = pod_order[k];
+    const int spec = o->pend_spec[pod];
+    int where = -1;
+    /* tryScheduleUsingHints (:80-106) */
+    const int h = hint_node ? hint_node[pod] : -1;
+    if (h >= 0 && h < N && (!node_ok || node_ok[h]) && s.schedulePod(spec, h) == CAE_R_OK) where = h;
+    if (where < 0) {
+      /* trySchedule (:110-130) */
+      const int cls = sim_class ? sim_class[pod] : -1;
+      bool similar_unsched = false;
+      if (cls >= 0) {
+        auto it = items.find(class_ctrl[cls]);
+        if (it != items.end()) similar_unsched = std::find(it->second.begin(), it->second.end(), cls) != it->second.end();
+      }
+      if (!similar_unsched) {
+        where = s.schedulePodOnAnyNodeMatching(spec, [&](const NodeState&, int idx) { return !node_ok || node_ok[idx]; });
+        if (where < 0 && cls >= 0) { /* SetUnschedulable (similar_pods.go:87-104) */
+          std::vector<int>& pm = items[class_ctrl[cls]];
+          if ((int)pm.size() >= 10) over.insert(class_ctrl[cls]);
+          else pm.push_back(cls);
+        }
+      }
+    }
+    assigned[pod] = where;
+    if (where < 0 && break_on_failure) break; /* hinting_simulator.go:71-73 */
+  }
+  if (last_index_out) *last_index_out = s.last_index;
+  if (overflowing) *overflowing = (int32_t)over.size();
+  return 0;
+}
+
 /* getMinLimit (estimator/threshold_based_limiter.go:45-53) */
 int64_t cao_get_min_limit(int64_t base, int64_t target) {
   if (base < 0 || target < 0) return -1;

@@ -52,6 +52,8 @@ def lib() -> C.CDLL:
         l.cao_waste_score.restype = C.c_double
         l.cao_expander.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
         l.cao_expander.restype = i32
+        l.cao_filter_schedulable.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32, i32, vp, vp, vp]
+        l.cao_filter_schedulable.restype = i32
         _lib = l
     return _lib
 
@@ -142,3 +144,21 @@ def cluster_capacity_limit(has_ctx: bool, max_limit: int, current: int) -> int:
 def sng_capacity_limit(has_ctx: bool, max_sizes: Sequence[int], target_sizes: Sequence[int]) -> int:
     a, b = np.asarray(max_sizes, np.int32), np.asarray(target_sizes, np.int32)
     return lib().cao_sng_capacity_limit(int(has_ctx), _p(a), _p(b), len(a))
+
+
+def filter_schedulable(enc, pod_order: Sequence[int], hint_node=None, sim_class=None, class_ctrl=None, node_ok=None,
+                       last_index: int = 0, break_on_failure: bool = False):
+    """filterOutSchedulableByPacking / HintingSimulator.TrySchedulePods on the cluster snapshot.
+    Returns (assigned[num_pending] node index or -1, lastIndex afterwards, overflowing controller count)."""
+    order = np.ascontiguousarray(pod_order, np.int32)
+    hn = None if hint_node is None else np.ascontiguousarray(hint_node, np.int32)
+    sc = None if sim_class is None else np.ascontiguousarray(sim_class, np.int32)
+    cc = None if class_ctrl is None else np.ascontiguousarray(class_ctrl, np.int32)
+    ok = None if node_ok is None else np.ascontiguousarray(node_ok, np.uint8)
+    assigned = np.full(enc.P, -1, np.int32)
+    li = np.zeros(1, np.int32)
+    ov = np.zeros(1, np.int32)
+    rc = lib().cao_filter_schedulable(enc.ptr(), _p(order), len(order), _p(hn), _p(sc), _p(cc), _p(ok), int(last_index),
+                                      int(break_on_failure), _p(assigned), _p(li), _p(ov))
+    assert rc == 0
+    return assigned, int(li[0]), int(ov[0])

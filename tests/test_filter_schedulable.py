@@ -1,0 +1,263 @@
+"""filter-out-schedulable / HintingSimulator.
+
+CPU part: the oracle's restatement against the reference's own test tables
+(simulator/scheduling/hinting_simulator_test.go:32-182,184-260; core/podlistprocessor/filter_out_schedulable_test.go:35-210).
+GPU part: the engine through the C ABI against the oracle, bit-exact (assigned node per pod, lastIndex,
+overflowing controllers)."""
+import numpy as np
+import pytest
+
+from kubernetes_autoscaler_b200 import podlistprocessor as plp
+from kubernetes_autoscaler_b200.objects import (BuildTestNode, BuildTestPod, LabelSelector, NodeInfo, PodAffinityTerm, Taint,
+                                                TopologySpreadConstraint, WithLabels, WithPodAffinity, WithPodAntiAffinity, makeNode)
+
+
+class OracleSimulator(plp.HintingSimulator):
+    """Same host logic, placement loop on the CPU oracle."""
+
+    def _run(self, x, breakOnFailure):
+        from oracle import pyoracle
+        return pyoracle.filter_schedulable(x.enc, x.order, x.hint, x.sim_class, x.class_ctrl, x.node_ok,
+                                           self.last_index if self.last_index < len(x.cluster) else 0, breakOnFailure)
+
+
+def _ready_node(name, cpu, mem):
+    return BuildTestNode(name, cpu, mem)
+
+
+def _scheduled(name, cpu, mem):
+    return BuildTestPod(name, cpu, mem)
+
+
+def _two_nodes():
+    return [NodeInfo(_ready_node("n1", 1000, 2000000), [_scheduled("p1", 300, 500000)]), NodeInfo(_ready_node("n2", 1000, 2000000))]
+
+
+TRY_CASES = [
+    # (new pods (name, cpu, mem), hints {name: node}, acceptable node or None, expected [(pod, node)])
+    ("two new pods, two nodes", [("p2", 800), ("p3", 500)], {}, None, [("p2", "n2"), ("p3", "n1")]),
+    ("hinted Node no longer in the cluster", [("p2", 800), ("p3", 500)], {"p2": "non-existing-node"}, None, [("p2", "n2"), ("p3", "n1")]),
+    ("three new pods, two nodes, no fit", [("p2", 800), ("p3", 500), ("p4", 700)], {}, None, [("p2", "n2"), ("p3", "n1")]),
+    ("no new pods, two nodes", [], {}, None, []),
+    ("two nodes, but only one acceptable", [("p2", 500), ("p3", 500)], {}, "n2", [("p2", "n2"), ("p3", "n2")]),
+    ("two nodes, but only one acceptable, no fit", [("p2", 500), ("p3", 500)], {}, "n1", [("p2", "n1")]),
+]
+
+
+def _run_try_case(sim, case):
+    _, new, hints, only, want = case
+    pods = [BuildTestPod(n, c, 500000) for n, c in new]
+    for p in pods:
+        if p.name in hints:
+            sim.hints.Set(plp.HintKeyFromPod(p), hints[p.name])
+    ok = plp.ScheduleAnywhere if only is None else (lambda ni: ni.node.name == only)
+    statuses, _ = sim.TrySchedulePods(_two_nodes(), pods, ok, False)
+    assert [(s.pod.name, s.node_name) for s in statuses] == want
+    sim.DropOldHints()
+    for pod_name, node in want:   # new hints match the nodes actually used
+        assert sim.hints.Get(("default", pod_name)) == node
+
+
+@pytest.mark.parametrize("case", TRY_CASES, ids=[c[0] for c in TRY_CASES])
+def test_oracle_try_schedule_pods_kat(case):
+    _run_try_case(OracleSimulator(), case)
+
+
+HINT_CASES = [
+    {"p1": "n2"},
+    {"p1": "n2", "p2": "n2", "p3": "n2"},
+    {"p1": "n1", "p2": "n2", "p3": "n3"},
+    {"p1": "n1", "p2": "n1", "p3": "n1", "p4": "n2", "p5": "n2", "p6": "n2", "p7": "n3", "p8": "n3", "p9": "n3"},
+]
+
+
+def _run_hint_case(sim, pod_nodes):
+    cluster = [NodeInfo(_ready_node(n, 9999, 9999)) for n in ("n1", "n2", "n3")]
+    pods = [BuildTestPod(p, 1, 1) for p in pod_nodes]
+    for p in pods:
+        sim.hints.Set(plp.HintKeyFromPod(p), pod_nodes[p.name])
+    statuses, _ = sim.TrySchedulePods(cluster, pods)
+    assert [(s.pod.name, s.node_name) for s in statuses] == list(pod_nodes.items())
+
+
+@pytest.mark.parametrize("pod_nodes", HINT_CASES)
+def test_oracle_pod_schedules_on_hinted_node_kat(pod_nodes):
+    _run_hint_case(OracleSimulator(), pod_nodes)
+
+
+def _prio(name, cpu, mem, prio):
+    p = BuildTestPod(name, cpu, mem)
+    p.priority = prio
+    return p
+
+
+FILTER_CASES = [
+    # (resident pods on the single 2000m node, candidates, expected scheduled names, expected unscheduled names, node filter)
+    ("single empty node, no pods", [], [], [], [], True),
+    ("single empty node, single schedulable pod", [], [("pod", 500, 0)], ["pod"], [], True),
+    ("single empty node, many schedulable pods", [], [("pod1", 200, 0), ("pod2", 500, 0), ("pod3", 800, 0)], ["pod1", "pod2", "pod3"], [], True),
+    ("single empty node, single unschedulable pod", [], [("pod1", 3000, 0)], [], ["pod1"], True),
+    ("single empty node, various pods", [], [("pod1", 200, 0), ("pod2", 500, 0), ("pod3", 1800, 0)], ["pod1", "pod2"], ["pod3"], True),
+    ("single empty node, some priority pods", [], [("pod1", 200, 0), ("pod2", 500, 10), ("pod3", 1800, 20)], ["pod3", "pod1"], ["pod2"], True),
+    ("non-empty node with a single pods scheduled", [500], [("pod2", 1000, 0), ("pod3", 300, 0), ("pod4", 300, 0)], ["pod2", "pod3"], ["pod4"], True),
+    ("non-empty node with many pods scheduled", [500, 1000], [("pod3", 1000, 0), ("pod4", 300, 0), ("pod5", 300, 0)], ["pod4"], ["pod3", "pod5"], True),
+    ("node should not be considered", [], [("pod1", 200, 0), ("pod2", 500, 0), ("pod3", 1800, 0)], [], ["pod1", "pod2", "pod3"], False),
+]
+
+
+def _run_filter_case(make_processor, case):
+    _, resident, cands, want_sched, want_unsched, all_nodes = case
+    node = NodeInfo(BuildTestNode("node", 2000, 100), [BuildTestPod("r%d" % i, c, 10) for i, c in enumerate(resident)])
+    pods = [_prio(n, c, 10, pr) for n, c, pr in cands]
+    proc = make_processor((lambda ni: True) if all_nodes else (lambda ni: False))
+    left = proc.Process([node], pods)
+    assert sorted(p.name for p in left) == sorted(want_unsched)
+    assert sorted(p.name for p in pods if p not in left) == sorted(want_sched)
+
+
+def _oracle_processor(node_filter):
+    proc = plp.FilterOutSchedulablePodListProcessor(node_filter)
+    proc.schedulingSimulator = OracleSimulator()
+    return proc
+
+
+@pytest.mark.parametrize("case", FILTER_CASES, ids=[c[0] for c in FILTER_CASES])
+def test_oracle_filter_out_schedulable_kat(case):
+    _run_filter_case(_oracle_processor, case)
+
+
+# ---- semantics the reference tests do not pin: similar pods, overflow, unschedulable nodes, spread / affinity --------
+def _owned(name, cpu, uid, labels=None, kind="ReplicaSet"):
+    p = BuildTestPod(name, cpu, 10)
+    p.owner_uid, p.owner_kind = uid, kind
+    if labels:
+        p.labels = dict(labels)
+    return p
+
+
+def _scenarios():
+    out = []
+    # 1. the similar-pods shortcut CHANGES the result: r2 would fit after "friend" lands (affinity), but a similar pod failed first
+    aff = PodAffinityTerm(LabelSelector({"app": "friend"}), "kubernetes.io/hostname")
+    cluster = [NodeInfo(makeNode(4000, 4000, 10, "n1", "z1")), NodeInfo(makeNode(4000, 4000, 10, "n2", "z1"))]
+    r1, r2 = _owned("r1", 100, "rs-a"), _owned("r2", 100, "rs-a")
+    for r in (r1, r2):
+        WithPodAffinity(aff)(r)
+    friend = BuildTestPod("friend", 100, 10, WithLabels({"app": "friend"}))
+    lone = BuildTestPod("lone", 100, 10, WithPodAffinity(aff))   # no controller: evaluated on its own, fits next to friend
+    out.append(("similar shortcut", cluster, [r1, friend, r2, lone]))
+    # 2. more than 10 distinct unschedulable specs of one controller: overflowing, every pod evaluated
+    cluster = [NodeInfo(BuildTestNode("n1", 1000, 1 << 30))]
+    pods = [_owned("big%d" % i, 2000 + i, "rs-over") for i in range(13)] + [_owned("big%d-b" % i, 2000 + i, "rs-over") for i in range(13)]
+    out.append(("overflowing controller", cluster, pods))
+    # 3. unschedulable / tainted nodes are skipped, lastIndex wraps, DaemonSet pods never enter the shortcut
+    n_bad = BuildTestNode("n-unsched", 4000, 1 << 30)
+    n_bad.unschedulable = True
+    n_taint = BuildTestNode("n-taint", 4000, 1 << 30)
+    n_taint.taints = [Taint("k", "v", "NoSchedule")]
+    cluster = [NodeInfo(n_bad), NodeInfo(BuildTestNode("n1", 1000, 1 << 30)), NodeInfo(n_taint), NodeInfo(BuildTestNode("n2", 1000, 1 << 30))]
+    pods = [_owned("a%d" % i, 300, "rs-b") for i in range(8)] + [_owned("ds%d" % i, 900, "ds-1", kind="DaemonSet") for i in range(3)]
+    out.append(("unschedulable nodes", cluster, pods))
+    # 4. hostname spread + anti-affinity over existing nodes with resident pods
+    cluster = [NodeInfo(makeNode(4000, 4000, 10, "n%d" % i, "z%d" % (i % 2)),
+                        [BuildTestPod("res%d" % i, 500, 10, WithLabels({"app": "web"}))] if i % 3 == 0 else []) for i in range(7)]
+    spread = TopologySpreadConstraint(1, "kubernetes.io/hostname", LabelSelector({"app": "web"}))
+    web = []
+    for i in range(9):
+        p = _owned("web%d" % i, 400, "rs-web", {"app": "web"})
+        p.topology_spread = [spread]
+        web.append(p)
+    anti = [BuildTestPod("solo%d" % i, 200, 10, WithLabels({"app": "solo"}),
+                         WithPodAntiAffinity(PodAffinityTerm(LabelSelector({"app": "solo"}), "topology.kubernetes.io/zone"))) for i in range(3)]
+    out.append(("spread and anti-affinity", cluster, web[:4] + anti + web[4:]))
+    return out
+
+
+SCENARIOS = _scenarios()
+
+
+def test_oracle_similar_pods_semantics():
+    sim = OracleSimulator()
+    name, cluster, pods = SCENARIOS[0]
+    st, over = sim.TrySchedulePods(cluster, pods)
+    # r1 fails (no friend yet) -> rs-a/spec marked; friend lands; r2 is skipped although it would fit; lone fits
+    assert [(s.pod.name) for s in st] == ["friend", "lone"] and over == 0
+    sim = OracleSimulator()
+    st, over = sim.TrySchedulePods(SCENARIOS[1][1], SCENARIOS[1][2])
+    assert st == [] and over == 1
+    sim = OracleSimulator()
+    st, _ = sim.TrySchedulePods(SCENARIOS[2][1], SCENARIOS[2][2])
+    assert {s.node_name for s in st} == {"n1", "n2"} and len(st) == 6   # 3 x 300m per schedulable node; the 900m DaemonSet pods fit nowhere
+    sim = OracleSimulator()
+    st, _ = sim.TrySchedulePods(SCENARIOS[0][1], SCENARIOS[0][2], breakOnFailure=True)
+    assert st == []   # r1 fails first and breakOnFailure stops the loop
+
+
+# ---- GPU parity --------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def gpu_engine():
+    import __graft_entry__ as g
+    g.build()
+    from kubernetes_autoscaler_b200.engine import Engine
+    e = Engine(device=0)
+    yield e
+    e.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", TRY_CASES, ids=[c[0] for c in TRY_CASES])
+def test_gpu_try_schedule_pods_kat(gpu_engine, case):
+    _run_try_case(plp.HintingSimulator(gpu_engine), case)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pod_nodes", HINT_CASES)
+def test_gpu_pod_schedules_on_hinted_node_kat(gpu_engine, pod_nodes):
+    _run_hint_case(plp.HintingSimulator(gpu_engine), pod_nodes)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", FILTER_CASES, ids=[c[0] for c in FILTER_CASES])
+def test_gpu_filter_out_schedulable_kat(gpu_engine, case):
+    _run_filter_case(lambda f: plp.FilterOutSchedulablePodListProcessor(f, gpu_engine), case)
+
+
+def _both(gpu_engine, cluster, pods, hints=None, ok=plp.ScheduleAnywhere, brk=False, last_index=0):
+    from oracle import pyoracle
+    h = plp.Hints()
+    for k, v in (hints or {}).items():
+        h.Set(("default", k), v)
+    x = plp.prepare_try_schedule(cluster, pods, h, ok)
+    want = pyoracle.filter_schedulable(x.enc, x.order, x.hint, x.sim_class, x.class_ctrl, x.node_ok, last_index, brk)
+    gpu_engine.load(x.enc)
+    got = gpu_engine.filter_schedulable(x.order, x.hint, x.sim_class, x.class_ctrl, x.node_ok, last_index, brk)
+    assert np.array_equal(got[0], want[0]), (got[0], want[0])
+    assert got[1:] == want[1:]
+    return want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scn", SCENARIOS, ids=[s[0] for s in SCENARIOS])
+def test_gpu_filter_semantics(gpu_engine, scn):
+    _, cluster, pods = scn
+    for brk in (False, True):
+        for li in (0, len(cluster) - 1):
+            _both(gpu_engine, cluster, pods, brk=brk, last_index=li)
+    _both(gpu_engine, cluster, pods, hints={pods[-1].name: cluster[-1].node.name, pods[0].name: cluster[0].node.name})
+    _both(gpu_engine, cluster, pods, ok=lambda ni: ni.node.name != cluster[0].node.name)
+
+
+@pytest.mark.gpu
+def test_gpu_filter_synthetic(gpu_engine):
+    """Config-3 shaped cluster (2000 -> 300 nodes with free capacity, resident pods, zone / hostname spread) with the
+    synthetic pending pods tried on it, in group order and in a scrambled order."""
+    from kubernetes_autoscaler_b200 import synth
+    from oracle import pyoracle
+    enc = synth.generate(3, pods=4_000, templates=8, cluster_nodes=300)
+    rng = np.random.default_rng(7)
+    for order in (np.arange(enc.P), rng.permutation(enc.P)[:1500]):
+        want = pyoracle.filter_schedulable(enc, order)
+        gpu_engine.load(enc)
+        got = gpu_engine.filter_schedulable(order)
+        assert np.array_equal(got[0], want[0])
+        assert got[1:] == want[1:]
