@@ -150,3 +150,61 @@ def test_random_scenarios(eng, oracle, block):
         mask, waste = eng.expander_best([0, 1, 2], nc, pc)
         omask, owaste = oracle.expander(enc, [0, 1, 2], nc, pc, sched)
         assert np.array_equal(mask, omask) and np.array_equal(waste, owaste), "seed %d expander" % seed
+
+
+def _filter_scenario(seed):
+    rng = random.Random(seed)
+    residents = [_rand_pod(rng, "r%d" % i) for i in range(8)]
+    for r in residents:
+        r.requests = {"cpu": rng.choice([100, 400]), "memory": 1 << 26}
+        r.host_ports = []
+    cluster = []
+    for i in range(rng.randint(1, 45)):
+        n = _rand_node(rng, "c%d" % i, False)
+        if rng.random() < 0.1:
+            n.unschedulable = True
+        cluster.append(NodeInfo(n, [rng.choice(residents) for _ in range(rng.randint(0, 3))]))
+    protos = [_rand_pod(rng, "p%d" % i) for i in range(rng.randint(1, 7))]
+    pods = []
+    for i in range(rng.randint(1, 70)):
+        p = rng.choice(protos).clone()
+        p.name = "q%d" % i
+        if rng.random() < 0.7:
+            p.owner_uid = rng.choice(["rs-1", "rs-2", "ds-1"])
+            p.owner_kind = "DaemonSet" if p.owner_uid == "ds-1" else "ReplicaSet"
+        pods.append(p)
+    if rng.random() < 0.5:   # identical pods adjacent (long runs) vs fully interleaved
+        pods.sort(key=lambda p: (p.owner_uid, sorted(p.labels.items()), sorted(p.requests.items())))
+    hints = {p.name: rng.choice(cluster).node.name for p in pods if rng.random() < 0.15}
+    namespaces = [Namespace("other", {"team": "a"})] if rng.random() < 0.5 else []
+    banned = {ni.node.name for ni in cluster if rng.random() < 0.15} if rng.random() < 0.3 else set()
+    return cluster, pods, hints, namespaces, banned, rng.random() < 0.2, rng.randrange(len(cluster))
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_random_filter_scenarios(eng, oracle, block):
+    """HintingSimulator.TrySchedulePods (cae_filter_schedulable) on random snapshots: assigned node per pod, lastIndex and
+    overflowing controllers identical to the oracle; random order, hints, similarity classes, node filter, breakOnFailure."""
+    from kubernetes_autoscaler_b200 import podlistprocessor as plp
+    from kubernetes_autoscaler_b200.engine import EngineUnsupported
+    refused = placed = 0
+    for seed in range(block * 40, block * 40 + 40):
+        cluster, pods, hints, namespaces, banned, brk, li = _filter_scenario(5000 + seed)
+        h = plp.Hints()
+        for name, node in hints.items():
+            h.Set(("default", name), node)
+            h.Set(("other", name), node)
+        ok = plp.ScheduleAnywhere if not banned else (lambda ni: ni.node.name not in banned)
+        x = plp.prepare_try_schedule(cluster, pods, h, ok, namespaces)
+        try:
+            eng.load(x.enc)
+        except EngineUnsupported:
+            refused += 1
+            assert refused <= 2
+            continue
+        want = oracle.filter_schedulable(x.enc, x.order, x.hint, x.sim_class, x.class_ctrl, x.node_ok, li, brk)
+        got = eng.filter_schedulable(x.order, x.hint, x.sim_class, x.class_ctrl, x.node_ok, li, brk)
+        assert np.array_equal(got[0], want[0]), "seed %d assigned %s vs %s" % (seed, got[0], want[0])
+        assert got[1:] == want[1:], "seed %d lastIndex / overflowing %s vs %s" % (seed, got[1:], want[1:])
+        placed += int((want[0] >= 0).sum())
+    assert placed > 0
