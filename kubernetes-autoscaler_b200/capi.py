@@ -119,11 +119,12 @@ def load_engine_lib() -> C.CDLL:
     global _engine_lib
     if _engine_lib is not None:
         return _engine_lib
-    if not os.path.exists(ENGINE_LIB):
+    path = os.environ.get("CAE_ENGINE_LIB", ENGINE_LIB)     # experiments: another build of the same library
+    if not os.path.exists(path):
         raise RuntimeError(
             "libcaengine.so is missing (%s): build it with `python -c 'import __graft_entry__ as g; "
-            "g.build()'`. The engine has no CPU fallback." % ENGINE_LIB)
-    lib = C.CDLL(ENGINE_LIB, mode=C.RTLD_GLOBAL)
+            "g.build()'`. The engine has no CPU fallback." % path)
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
     P = C.POINTER
     lib.cae_create.argtypes = [P(cae_config), P(C.c_void_p)]
     lib.cae_create.restype = C.c_int32

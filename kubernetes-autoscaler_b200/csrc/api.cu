@@ -458,6 +458,7 @@ int32_t cae_create(const cae_config* cfg, cae_engine** out) {
   cudaEventCreate(&e->ev1);
   { const char* v = getenv("CAE_K1_BITSLICE"); e->force_bitslice = v && v[0] == '1'; }
   { const char* v = getenv("CAE_K1_WARPS"); if (v && atoi(v) == 8) e->k1_warps = 8; }
+  { const char* v = getenv("CAE_PACK_WARPS_PER_SM"); if (v && atoi(v) >= 1 && atoi(v) <= 64) e->pack_warps_per_sm = atoi(v); }
   *out = reinterpret_cast<cae_engine*>(e);
   return 0;
 }

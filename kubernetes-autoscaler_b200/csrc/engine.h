@@ -104,6 +104,7 @@ struct Engine {
   uint8_t lut_word[CAE_MAX_RES] = {0}, lut_shift[CAE_MAX_RES] = {0};
   uint32_t lut_mask[CAE_MAX_RES] = {0};
   uint32_t* d_rlut = nullptr;             // [lut_rows][Twp]
+  int pack_warps_per_sm = 20;             // resident estimator warps per SM (CAE_PACK_WARPS_PER_SM)
   int k1_warps = 16;                      // warps per thread block of the LUT variant (CAE_K1_WARPS=8|16)
   bool force_bitslice = false;            // CAE_K1_BITSLICE=1: always take the bit-sliced comparator (tests)
   int32_t* d_pod_sc = nullptr;            // [P]

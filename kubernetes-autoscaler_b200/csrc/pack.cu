@@ -87,12 +87,18 @@ struct WarpDyn {
 };
 
 constexpr int PACK_WARPS = 4;
+constexpr int PACK_HIST = 256;             // capacities up to this use the histogram; above, a binary search
+#ifndef PACK_MIN_BLOCKS
+#define PACK_MIN_BLOCKS 1
+#endif
 
 template <int A, bool FM>
-__global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, DynTables d, PackParams p) {
+__global__ void __launch_bounds__(PACK_WARPS * 32, PACK_MIN_BLOCKS) pack_kernel(DevObjects o, DynTables d, PackParams p) {
   __shared__ WarpDyn s_wd[PACK_WARPS];
+  __shared__ int s_hist[PACK_WARPS][PACK_HIST + 1];   // plain groups: #nodes per capacity value (closed-form lap count)
   const int lane = threadIdx.x & 31;
   WarpDyn& wd = s_wd[threadIdx.x >> 5];
+  int* hist = s_hist[threadIdx.x >> 5];
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   unsigned char* slab = p.scratch + (size_t)warp_global * p.scratch_per_warp;
   const int N = p.N, NT = p.N + p.T;
@@ -209,6 +215,9 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
           };
           long long total = 0;
           int kmax = 0;
+#pragma unroll
+          for (int i = 0; i < PACK_HIST / 32; ++i) hist[lane * (PACK_HIST / 32) + i + 1] = 0;
+          __syncwarp();
           for (int cb = 0; cb < nb; cb += 32) {
             const int b2 = cb + lane;
             unsigned cm = __ballot_sync(0xffffffffu, b2 < nb && block_may_fit(b2));
@@ -235,6 +244,12 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
                 total += k;
                 kmax = max(kmax, k);
                 kblk = k;
+              }
+              {  // histogram of the capacities: lanes with the same value elect one writer (no atomics)
+                const bool cnt = kblk > 0 && kblk <= PACK_HIST;
+                const unsigned peers = __match_any_sync(0xffffffffu, cnt ? kblk : 0);
+                if (cnt && lane == __ffs(peers) - 1) hist[kblk] += __popc(peers);
+                __syncwarp();
               }
               // a candidate block that cannot take a single pod had a stale bound: tighten it so that the
               // following groups skip it without touching its nodes
@@ -263,7 +278,37 @@ __global__ void __launch_bounds__(PACK_WARPS * 32) pack_kernel(DevObjects o, Dyn
             };
             int L, rem;
             if (total <= n) { L = kmax; rem = 0; }
-            else {
+            else if (kmax <= PACK_HIST) {
+              // f(L) = sum_j min(k_j, L) = sum_{l <= L} G(l), G(l) = #{k_j >= l}: two warp scans over the histogram
+              constexpr int PB = PACK_HIST / 32;
+              int c[PB], G[PB];
+              int lane_tot = 0;
+#pragma unroll
+              for (int i = 0; i < PB; ++i) { c[i] = hist[lane * PB + i + 1]; lane_tot += c[i]; }
+              int suf = lane_tot;   // inclusive suffix sum over lanes
+#pragma unroll
+              for (int off = 1; off < 32; off <<= 1) {
+                const int v = __shfl_down_sync(0xffffffffu, suf, off);
+                if (lane + off < 32) suf += v;
+              }
+              int run = suf - lane_tot, gsum = 0;   // counts of the lanes above
+#pragma unroll
+              for (int i = PB - 1; i >= 0; --i) { run += c[i]; G[i] = run; gsum += run; }
+              int pre = gsum;       // inclusive prefix sum over lanes
+#pragma unroll
+              for (int off = 1; off < 32; off <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, pre, off);
+                if (lane >= off) pre += v;
+              }
+              int f = pre - gsum, cnt = 0, fbest = 0;
+#pragma unroll
+              for (int i = 0; i < PB; ++i) {
+                f += G[i];          // f(lane * PB + i + 1)
+                if (f <= n) { ++cnt; fbest = f; }
+              }
+              L = wsum(cnt);        // f is strictly increasing up to kmax and f(kmax) = total > n
+              rem = n - wmax(fbest);
+            } else {
               int lo = 0, hi = kmax;  // f(lo) <= n < f(hi), f(L) = sum min(k_j, L)
               while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
@@ -882,7 +927,7 @@ int launch_pack(Engine* e) {
   const int log_cap = p.has_dyn ? (int)std::min<size_t>(4 * X + 1024, (size_t)1 << 24) : 1;
   const size_t per_warp = pack_layout(e, p, cap, p.has_dyn != 0, log_cap);
   const int A1 = std::max(e->A, 1);
-  int warps = std::min(nt, e->sm_count * 20);
+  int warps = std::min(nt, e->sm_count * e->pack_warps_per_sm);
   const size_t budget = (size_t)24 << 30;  // keep the slabs within 24 GiB of the 180 GB HBM
   if (per_warp * warps > budget) warps = (int)std::max<size_t>(1, budget / per_warp);
   int blocks = (warps + PACK_WARPS - 1) / PACK_WARPS;
