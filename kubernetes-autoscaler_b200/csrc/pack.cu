@@ -459,17 +459,23 @@ __global__ void __launch_bounds__(PACK_WARPS * 32, PACK_MIN_BLOCKS) pack_kernel(
         // Working counters are copy-on-write over the cluster base counts: a slot is valid only when its
         // version equals this group's, otherwise it reads as its default (base count for cluster domains,
         // DaemonSet weight for the fresh hostname domain of an added node, 0 for a template-only value).
+        auto def_cnt = [&](int q, int sl) -> int {
+          const int Dc = wd.Dc[q];
+          return sl < Dc ? d.base_cnt[wd.boff[q] + sl] : (sl == Dc ? 0 : (wd.elig_new[q] ? wd.dsw[q] : 0));
+        };
+        auto def_pres = [&](int q, int sl) -> int {
+          const int Dc = wd.Dc[q];
+          return sl < Dc ? d.base_pres[wd.boff[q] + sl] : (sl == Dc ? 0 : (wd.elig_new[q] ? 1 : 0));
+        };
         auto rd_cnt = [&](int q, int sl) -> int {
           const size_t o2 = (size_t)q * p.dstride + sl;
           if (wver[o2] == gver) return wcnt[o2];
-          const int Dc = wd.Dc[q];
-          return sl < Dc ? d.base_cnt[wd.boff[q] + sl] : (sl == Dc ? 0 : (wd.elig_new[q] ? wd.dsw[q] : 0));
+          return def_cnt(q, sl);
         };
         auto rd_pres = [&](int q, int sl) -> int {
           const size_t o2 = (size_t)q * p.dstride + sl;
           if (wver[o2] == gver) return wpres[o2];
-          const int Dc = wd.Dc[q];
-          return sl < Dc ? d.base_pres[wd.boff[q] + sl] : (sl == Dc ? 0 : (wd.elig_new[q] ? 1 : 0));
+          return def_pres(q, sl);
         };
         auto wr = [&](int q, int sl, int c, int pr) {  // single lane
           const size_t o2 = (size_t)q * p.dstride + sl;
@@ -524,22 +530,43 @@ __global__ void __launch_bounds__(PACK_WARPS * 32, PACK_MIN_BLOCKS) pack_kernel(
           if (full) recompute(q);
         }
         __syncwarp();
-        if (need_log && log_n > 0) {  // pods other groups placed earlier in this run (rare: serial on lane 0)
+        if (need_log && log_n > 0) {  // pods other groups (FM: earlier runs) placed before: replay the placement log
+          const int nlog = min(log_n, p.log_cap);
           for (int q = 0; q < nq; ++q) {
             const int qid = wd.qid[q];
+            // lanes stride over the log.  Pass 1 materialises the touched copy-on-write slots with their defaults
+            // (identical values from every lane), pass 2 stamps the version and adds the weights atomically.
+            auto entry = [&](int i, int& w, size_t& o2) -> bool {
+              const int x = logbuf[i * 3];
+              w = d.wmat[(size_t)qid * d.S + logbuf[i * 3 + 1]];
+              if (w == 0 || !elig_of(q, x)) return false;
+              const int sl = slot_of(q, x);
+              if (sl < 0) return false;
+              o2 = (size_t)q * p.dstride + sl;
+              if (wver[o2] != gver) { wcnt[o2] = def_cnt(q, sl); wpres[o2] = def_pres(q, sl); }
+              return true;
+            };
             bool touched = false;
-            if (lane == 0) {
-              for (int i = 0; i < min(log_n, p.log_cap); ++i) {
-                const int x = logbuf[i * 3], w = d.wmat[(size_t)qid * d.S + logbuf[i * 3 + 1]];
-                if (w == 0 || !elig_of(q, x)) continue;
-                const int sl = slot_of(q, x);
-                if (sl < 0) continue;
-                wr(q, sl, rd_cnt(q, sl) + w * logbuf[i * 3 + 2], rd_pres(q, sl));
-                wd.tot[q] += w * logbuf[i * 3 + 2];
-                touched = true;
-              }
+            int dt = 0;
+            for (int i = lane; i < nlog; i += 32) {
+              int w; size_t o2;
+              if (entry(i, w, o2)) { touched = true; dt += w * logbuf[i * 3 + 2]; }
             }
-            touched = __shfl_sync(0xffffffffu, touched, 0);
+            __syncwarp();
+            for (int i = lane; i < nlog; i += 32) {
+              const int x = logbuf[i * 3];
+              const int w = d.wmat[(size_t)qid * d.S + logbuf[i * 3 + 1]];
+              if (w == 0 || !elig_of(q, x)) continue;
+              const int sl = slot_of(q, x);
+              if (sl < 0) continue;
+              const size_t o2 = (size_t)q * p.dstride + sl;
+              wver[o2] = gver;
+              atomicAdd(&wcnt[o2], w * logbuf[i * 3 + 2]);
+            }
+            __syncwarp();
+            dt = wsum(dt);
+            touched = __ballot_sync(0xffffffffu, touched) != 0u;
+            if (lane == 0) wd.tot[q] += dt;
             __syncwarp();
             if (touched && wd.kind[q] == Q_PTS) recompute(q);
           }
