@@ -267,7 +267,7 @@ def main():
         step_resident()
     torch.cuda.synchronize()
 
-    sampler = _clock_sampler_start(range(world)) if rank == 0 else None
+    sampler = _clock_sampler_start([local_rank]) if rank == 0 else None   # rank 0's GPU only: NVML queries delay launches
     if sampler is not None:
         time.sleep(0.5)            # nvidia-smi initialises NVML on every GPU of the box: keep that out of the timed steps
     launches0 = eng.stats().kernel_launches
@@ -400,6 +400,7 @@ def main():
                    "l2": "flushed between timed iterations (512 MiB memset on the engine's stream)",
                    "timing": "CUDA events on the engine's stream, queued behind the flush + a spin kernel (no host launch latency in the window)"},
         "kernel_ms": kern_ms, "allreduce_ms": allreduce_ms,
+        "step_ms_rank0": {"min": float(np.min(dev_ms)), "median": float(np.median(dev_ms)), "max": float(np.max(dev_ms))},
         "collective": ("none" if world == 1 else ("fused P2P atomics over NVLink (peer memory)" if fused else "NCCL all_reduce int32[T]")), "wall_ms_per_step": float(np.mean(wall_ms)), "clocks": _clocks_summary(samples),
         "e2e": {"value": (P1 * world) * T / (e2e_step * 1e-3), "unit": "evals/s", "ms_per_step": e2e_step,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
