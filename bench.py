@@ -250,10 +250,15 @@ def main():
     # window measures device time only.  wall_ms_per_step keeps the host view.
     estream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local_rank))
 
+    sync_t = torch.zeros(1, device="cuda")
+
     def flush_l2():
         with torch.cuda.stream(estream):
             flush.zero_()                                      # > L2: evicts everything the previous step left
             torch.cuda._sleep(100_000)                         # ~50 us spin: covers the host's enqueue of the step
+            if dist is not None:
+                dist.all_reduce(sync_t)                        # device-side barrier on the engine's stream: the ranks' timed
+                                                               # windows open together (a host barrier cannot align queued work)
 
     def step_resident():
         eng.lib.cae_feasibility(eng.h, None, None, None)       # kernel only; results stay in HBM
