@@ -255,7 +255,7 @@ def main():
     def flush_l2():
         with torch.cuda.stream(estream):
             flush.zero_()                                      # > L2: evicts everything the previous step left
-            torch.cuda._sleep(100_000)                         # ~50 us spin: covers the host's enqueue of the step
+            torch.cuda._sleep(300_000)                         # ~150 us spin: covers the host's enqueue of the step
             if dist is not None:
                 dist.all_reduce(sync_t)                        # device-side barrier on the engine's stream: the ranks' timed
                                                                # windows open together (a host barrier cannot align queued work)
