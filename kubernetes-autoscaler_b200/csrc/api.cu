@@ -9,10 +9,13 @@
 //   * per-pod request planes [A][P] (A = resource dims any pending pod asks for) and per-template
 //     free-capacity planes [A][T] are laid out SoA for coalesced int64 loads in the dense pass.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <tuple>
+#include <unordered_map>
 
 #include "engine.h"
 
@@ -40,17 +43,19 @@ int Arena::alloc(void** dev, void** stage, size_t bytes) {
   c.used += bytes;
   return 0;
 }
-void Arena::reset() { for (auto& c : chunks) c.used = 0; cur = 0; }
+void Arena::reset() { for (auto& c : chunks) c.used = c.flushed = 0; cur = 0; }
 void Arena::release() {
   for (auto& c : chunks) { cudaFree(c.dev); if (c.host) cudaFreeHost(c.host); }
   chunks.clear();
   cur = 0;
 }
 int Arena::flush(cudaStream_t st, int64_t* bytes) {
-  for (auto& c : chunks)
-    if (c.used) {
-      if (cudaMemcpyAsync(c.dev, c.host, c.used, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("H2D failed"); return -1; }
-      if (bytes) *bytes += (int64_t)c.used;
+  for (auto& c : chunks)   // incremental: only what was staged since the last flush
+    if (c.used > c.flushed) {
+      if (cudaMemcpyAsync(static_cast<char*>(c.dev) + c.flushed, static_cast<char*>(c.host) + c.flushed, c.used - c.flushed,
+                          cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("H2D failed"); return -1; }
+      if (bytes) *bytes += (int64_t)(c.used - c.flushed);
+      c.flushed = c.used;
     }
   return 0;
 }
@@ -196,7 +201,24 @@ static int build_dynamic(Engine* e, const cae_objects* o, const std::vector<uint
   return 0;
 }
 
+struct LoadTimer {   // CAE_LOAD_TIMING=1: host wall clock of the phases of cae_load on stderr
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  std::string out;
+  LoadTimer() : on(getenv("CAE_LOAD_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char* what) {
+    if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    char buf[96];
+    snprintf(buf, sizeof(buf), " %s=%.1fus", what, std::chrono::duration<double, std::micro>(t1 - t0).count());
+    out += buf;
+    t0 = t1;
+  }
+  ~LoadTimer() { if (on) fprintf(stderr, "cae_load:%s\n", out.c_str()); }
+};
+
 static int do_load(Engine* e, const cae_objects* o) {
+  LoadTimer lt;
   if (o->abi_version != CAE_ABI_VERSION) { set_error("cae_objects.abi_version mismatch"); return -2; }
   if (o->num_res < 3 || o->num_res > CAE_MAX_RES) { set_error("num_res out of range"); return 1; }
   e->up.reset();
@@ -251,19 +273,29 @@ static int do_load(Engine* e, const cae_objects* o) {
   // ---- host-side interning of pod specs into classes (no predicate is evaluated here) ----
   const int S = o->num_podspecs;
   std::vector<uint8_t> spec_pending(S, 0);
-  for (int p = 0; p < o->num_pending; ++p) spec_pending[o->pend_spec[p]] = 1;
-  std::map<std::tuple<int, int, int, int>, int> sc_ids;
+  for (int p = 0, prev = -1; p < o->num_pending; ++p)   // pods of a group are adjacent and share a spec: touch the flag on changes only
+    if (o->pend_spec[p] != prev) { prev = o->pend_spec[p]; spec_pending[prev] = 1; }
+  struct Key4 { int a, b, c, d; bool operator==(const Key4& k) const { return a == k.a && b == k.b && c == k.c && d == k.d; } };
+  struct Key4Hash {
+    size_t operator()(const Key4& k) const {
+      uint64_t h = (uint64_t)(uint32_t)k.a * 0x9E3779B97F4A7C15ull;
+      h = (h ^ (uint32_t)k.b) * 0xBF58476D1CE4E5B9ull;
+      h = (h ^ (uint32_t)k.c) * 0x94D049BB133111EBull;
+      h = (h ^ (uint32_t)k.d) * 0x9E3779B97F4A7C15ull;
+      return (size_t)(h ^ (h >> 29));
+    }
+  };
+  std::unordered_map<Key4, int, Key4Hash> sc_ids;
+  sc_ids.reserve((size_t)S * 2);
   std::vector<StaticClass> sclass;
+  sclass.reserve(S);
   std::vector<int32_t> spec_sc(S, 0), spec_dc(S, 0);
   for (int s = 0; s < S; ++s) {
     if (!spec_pending[s]) continue;
-    auto key = std::make_tuple(o->ps_tol_list[s], o->ps_naff[s], o->ps_node_name[s], o->ps_port_list[s]);
-    auto it = sc_ids.find(key);
-    if (it == sc_ids.end()) {
-      it = sc_ids.emplace(key, (int)sclass.size()).first;
-      sclass.push_back({o->ps_tol_list[s], o->ps_naff[s], o->ps_node_name[s], o->ps_port_list[s]});
-    }
-    spec_sc[s] = it->second;
+    const Key4 key{o->ps_tol_list[s], o->ps_naff[s], o->ps_node_name[s], o->ps_port_list[s]};
+    auto ins = sc_ids.emplace(key, (int)sclass.size());   // ids in order of first appearance
+    if (ins.second) sclass.push_back({key.a, key.b, key.c, key.d});
+    spec_sc[s] = ins.first->second;
   }
   // host-port lists of pending pods get compact ids (one bit each in a node's used-port mask)
   std::vector<int32_t> pc_of(o->num_port_lists, -1);
@@ -278,7 +310,17 @@ static int do_load(Engine* e, const cae_objects* o) {
   e->SC = (int)sclass.size();
   e->DC = 1;  // class 0: no topology-spread / inter-pod-affinity involvement
   e->h_dc_of_spec_valid = false;
+  // The object tables and the static classes are complete: ship them and start the class matrix now, so that the
+  // device works while the host goes on interning (dynamic classes, rank encoding).
+  if (upload_mut(e, sclass, &e->d_sclass) || upload_mut(e, pc_of, &e->d_pc_of) || dev_alloc(e, &e->d_pre_code, (size_t)e->SC * e->U) ||
+      dev_alloc(e, &e->d_port_conf, (size_t)std::max(o->num_port_lists, 1)))
+    return -1;
+  if (e->up.flush(e->stream, &e->stats.h2d_bytes)) return -1;
+  if (launch_port_conflicts(e, o->num_port_lists)) return -1;
+  if (launch_class_matrix(e)) return -1;
+  lt.mark("stage+classes");
   { int rc = build_dynamic(e, o, spec_pending, spec_sc, spec_dc); if (rc) return rc; }
+  lt.mark("build_dynamic");
 
   // active resource dims + free capacity of templates and cluster nodes
   e->A = 0;
@@ -355,12 +397,6 @@ static int do_load(Engine* e, const cae_objects* o) {
       ++e->feas_B;
     }
   }
-  const int Bpad = std::max(4, (e->feas_B + 3) / 4 * 4);
-  std::vector<uint32_t> tslice((size_t)Bpad * std::max(e->Tw, 1), 0);
-  for (int b = 0; b < e->feas_B; ++b)
-    for (int t = 0; t < T; ++t)
-      tslice[(size_t)b * e->Tw + t / 32] |= ((tmpl_w[(size_t)e->feas_sword[b] * T + t] >> e->feas_sshift[b]) & 1u) << (t % 32);
-  if (upload_mut(e, tslice, &e->d_tslice)) return -1;
   // threshold bitmaps for the LUT variant of the dense pass: one row per (dim, request rank)
   e->lut_rows = 0;
   for (int a = 0; a < e->A; ++a) {
@@ -369,6 +405,15 @@ static int do_load(Engine* e, const cae_objects* o) {
     e->lut_word[a] = (uint8_t)f_word[a];
     e->lut_shift[a] = (uint8_t)f_shift[a];
     e->lut_mask[a] = (1u << (f_bits[a] - 1)) - 1u;
+  }
+  e->d_tslice = nullptr;
+  if (e->force_bitslice || e->lut_rows > FEAS_LUT_MAX_ROWS) {   // only the fallback variant of the dense pass reads the slices
+    const int Bpad = std::max(4, (e->feas_B + 3) / 4 * 4);
+    std::vector<uint32_t> tslice((size_t)Bpad * std::max(e->Tw, 1), 0);
+    for (int b = 0; b < e->feas_B; ++b)
+      for (int t = 0; t < T; ++t)
+        tslice[(size_t)b * e->Tw + t / 32] |= ((tmpl_w[(size_t)e->feas_sword[b] * T + t] >> e->feas_sshift[b]) & 1u) << (t % 32);
+    if (upload_mut(e, tslice, &e->d_tslice)) return -1;
   }
   {
     std::vector<uint32_t> rlut((size_t)std::max(e->lut_rows, 1) * std::max(e->Twp, 1), 0);
@@ -379,12 +424,13 @@ static int do_load(Engine* e, const cae_objects* o) {
       }
     if (upload_mut(e, rlut, &e->d_rlut)) return -1;
   }
-  if (upload_mut(e, sclass, &e->d_sclass) || upload_mut(e, spec_sc, &e->d_spec_sc) || upload_mut(e, slots, &e->d_tmpl_slots) ||
+  if (upload_mut(e, spec_sc, &e->d_spec_sc) || upload_mut(e, slots, &e->d_tmpl_slots) ||
       upload_mut(e, free_all, &e->d_tmpl_free_all) || upload_mut(e, free_act, &e->d_tmpl_free) || upload_mut(e, cfree, &e->d_c_free) ||
-      upload_mut(e, cslots, &e->d_c_slots) || upload_mut(e, spec_w, &e->d_spec_w) || upload_mut(e, tmpl_w, &e->d_tmpl_w) || upload_mut(e, pc_of, &e->d_pc_of) || upload_mut(e, spec_dc, &e->d_spec_dc))
+      upload_mut(e, cslots, &e->d_c_slots) || upload_mut(e, spec_w, &e->d_spec_w) || upload_mut(e, tmpl_w, &e->d_tmpl_w) || upload_mut(e, spec_dc, &e->d_spec_dc))
     return -1;
 
-  if (dev_alloc(e, &e->d_pre_code, (size_t)e->SC * e->U) || dev_alloc(e, &e->d_pre_ok, (size_t)e->SC * std::max(e->Twp, 1)) ||
+  lt.mark("ranks+tables");
+  if (dev_alloc(e, &e->d_pre_ok, (size_t)e->SC * std::max(e->Twp, 1)) ||
       dev_alloc(e, &e->d_post_code, (size_t)e->DC * std::max(T, 1), true) || dev_alloc(e, &e->d_post_ok, (size_t)e->DC * std::max(e->Twp, 1)) ||
       dev_alloc(e, &e->d_pod_w, (size_t)std::max(e->W, 1) * std::max(e->Pl, 1)) || dev_alloc(e, &e->d_pod_row, (size_t)std::max(e->A, 1) * std::max(e->Pl, 1)) || dev_alloc(e, &e->d_pod_sc, (size_t)std::max(e->Pl, 1)) ||
       dev_alloc(e, &e->d_pod_dc, (size_t)std::max(e->Pl, 1)) || dev_alloc(e, &e->d_fit_bits, (size_t)std::max(T, 1) * std::max(e->Plw, 1)) ||
@@ -393,7 +439,7 @@ static int do_load(Engine* e, const cae_objects* o) {
       dev_alloc(e, &e->d_counts2, (size_t)2 * std::max(T, 1), true) || dev_alloc(e, &e->d_sched, (size_t)std::max(T, 1) * std::max(e->E, 1), true) ||
       dev_alloc(e, &e->d_order, (size_t)std::max(T, 1) * std::max(e->E, 1)) || dev_alloc(e, &e->d_order_n, (size_t)std::max(T, 1), true) ||
       dev_alloc(e, &e->d_max_nodes, (size_t)std::max(T, 1), true) || dev_alloc(e, &e->d_work_counter, 4, true) ||
-      dev_alloc(e, &e->d_port_conf, (size_t)std::max(o->num_port_lists, 1)) || dev_alloc(e, &e->d_act_dim, CAE_MAX_RES))
+      dev_alloc(e, &e->d_act_dim, CAE_MAX_RES))
     return -1;
   e->d_score = nullptr;
   e->d_reasons = nullptr;
@@ -403,10 +449,10 @@ static int do_load(Engine* e, const cae_objects* o) {
   e->h_group_off.assign(o->group_off, o->group_off + o->num_groups + 1);
   e->h_pend_spec.assign(o->pend_spec, o->pend_spec + o->num_pending);
 
+  lt.mark("dev_alloc+memsets");
   if (e->up.flush(e->stream, &e->stats.h2d_bytes)) return -1;   // ONE pinned H2D copy per arena chunk
   CAE_CUDA(cudaMemcpyAsync(e->d_act_dim, e->act_dim, sizeof(int) * CAE_MAX_RES, cudaMemcpyHostToDevice, e->stream));
-  if (launch_port_conflicts(e, o->num_port_lists)) return -1;
-  if (launch_class_matrices(e)) return -1;
+  if (launch_pre_ok_bits(e)) return -1;
   if (e->has_dynamic) {
     if (launch_dynamic_tables(e, e->d_spec_used, e->d_dc_ngroups)) return -1;
     // classes none of whose counters can ever be non-zero are plain: fold them back into class 0
@@ -422,7 +468,9 @@ static int do_load(Engine* e, const cae_objects* o) {
   if (launch_post_bits(e)) return -1;
   if (launch_expand_pods(e)) return -1;
   cudaEventRecord(e->ev1, e->stream);
+  lt.mark("launches");
   CAE_CUDA(cudaStreamSynchronize(e->stream));
+  lt.mark("sync");
   float ms = 0;
   cudaEventElapsedTime(&ms, e->ev0, e->ev1);
   e->stats.h2d_ms = ms;

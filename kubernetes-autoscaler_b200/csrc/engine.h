@@ -13,6 +13,7 @@
 namespace cae {
 
 constexpr int FEAS_MAX_W = 4;
+constexpr int FEAS_LUT_MAX_ROWS = 1024;     // threshold rows (68 KB of shared memory) above which the dense pass falls back to bit slices
 constexpr int FEAS_TW = 16;                // template words per thread block of the dense pass; row pitch Twp is a multiple
 
 void set_error(const std::string& msg);
@@ -38,7 +39,7 @@ void set_error(const std::string& msg);
 // Chunked bump allocator that persists across loads.  `mirrored` arenas pair every device chunk with a
 // pinned host chunk at the same offsets so a whole load is ONE cudaMemcpyAsync per chunk.
 struct Arena {
-  struct Chunk { void* dev = nullptr; void* host = nullptr; size_t size = 0, used = 0; };
+  struct Chunk { void* dev = nullptr; void* host = nullptr; size_t size = 0, used = 0, flushed = 0; };
   std::vector<Chunk> chunks;
   size_t cur = 0;
   size_t min_chunk = (size_t)32 << 20;
@@ -156,7 +157,8 @@ struct Engine {
 };
 
 // kernels.cu
-int launch_class_matrices(Engine* e);
+int launch_class_matrix(Engine* e);      // pre_code[SC][U]: needs only the object tables + the static classes
+int launch_pre_ok_bits(Engine* e);       // pre_ok[SC][Twp]: needs pre_code and the templates' pod slots
 int launch_post_bits(Engine* e);
 int launch_dynamic_tables(Engine* e, const uint8_t* d_spec_used, const int32_t* d_dc_ngroups);
 int launch_expand_pods(Engine* e);

@@ -487,7 +487,7 @@ static int launch_feas_lut_a(Engine* e, bool want_reasons, const K1Args& a, cons
   return want_reasons ? launch_feas_lut_arw<A, true, 16>(e, a, pp) : launch_feas_lut_arw<A, false, 16>(e, a, pp);
 }
 
-constexpr int K1_LUT_MAX_ROWS = 1024;    // 68 KB of threshold rows per thread block at most
+constexpr int K1_LUT_MAX_ROWS = FEAS_LUT_MAX_ROWS;
 
 int launch_feasibility(Engine* e, bool want_reasons) {
   if (e->Pl == 0 || e->Tw == 0) return 0;

@@ -93,12 +93,17 @@ int launch_group_feasibility(Engine* e) {
   return 0;
 }
 
-int launch_class_matrices(Engine* e) {
+int launch_class_matrix(Engine* e) {
   if (e->SC > 0 && e->U > 0) {
     dim3 grid((e->U + 127) / 128, e->SC);
     class_matrix_kernel<<<grid, 128, 0, e->stream>>>(e->dobj, e->d_sclass, e->SC, e->U, e->d_pre_code);
     e->stats.kernel_launches++;
   }
+  CAE_KERNEL_OK();
+  return 0;
+}
+
+int launch_pre_ok_bits(Engine* e) {
   if (e->Tw > 0) {   // rows padded to the pitch Twp; the padding words are written as zeros
     dim3 g1((e->Twp + 63) / 64, e->SC);
     pack_ok_bits_kernel<<<g1, 64, 0, e->stream>>>(e->d_pre_code, e->U, e->N, e->SC, e->T, e->Twp, e->d_tmpl_slots, e->d_pre_ok);
