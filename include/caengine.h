@@ -323,6 +323,15 @@ int32_t cae_filter_schedulable(cae_engine* e, const int32_t* pod_order, int32_t 
                                int32_t last_index_in, int32_t break_on_failure, int32_t* assigned_node,
                                int32_t* last_index_out, int32_t* overflowing_controllers);
 
+/* The two halves of cae_expander_best for templates sharded over ranks (no [T][E] matrix ever leaves a GPU):
+ * cae_waste_scores returns the least-waste score (expander/waste/waste.go:44-72) of this rank's template shard from
+ * the device-resident result of the last cae_estimate_all, 0.0 for the rows of other ranks, so that a SUM all-reduce of
+ * double[T] assembles the vector bit-exactly; cae_expander_chain runs the filter chain on the host from the all-reduced
+ * node_count | pod_count and that vector (no engine state is read). */
+int32_t cae_waste_scores(cae_engine* e, double* waste_score /* [T] */);
+int32_t cae_expander_chain(const int32_t* chain, int32_t chain_len, int32_t num_templates, const int32_t* node_count,
+                           const int32_t* pod_count, const double* waste_score, uint8_t* best_mask /* [T] */);
+
 int32_t cae_get_stats(cae_engine* e, cae_stats* out);
 
 /* Raw device pointers of the engine's result buffers, for zero-copy collectives (torch.distributed

@@ -154,6 +154,10 @@ def load_engine_lib() -> C.CDLL:
     lib.cae_filter_schedulable.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                            C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.cae_filter_schedulable.restype = C.c_int32
+    lib.cae_waste_scores.argtypes = [C.c_void_p, C.c_void_p]
+    lib.cae_waste_scores.restype = C.c_int32
+    lib.cae_expander_chain.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.cae_expander_chain.restype = C.c_int32
     lib.cae_stream.argtypes = [C.c_void_p]
     lib.cae_stream.restype = C.c_void_p
     _engine_lib = lib

@@ -482,6 +482,46 @@ static int do_load(Engine* e, const cae_objects* o) {
 
 using cae::Engine;
 
+// The expander filter chain is a sequential scan over <= T options in option order
+// (expander/factory/chain.go:36-45) — it keeps the reference's order-dependent quirks
+// (waste.go:58-65: equality tested before the nil/less-than branch).
+static int32_t run_expander_chain(const int32_t* chain, int32_t chain_len, int T, const int32_t* node_count,
+                                  const int32_t* pod_count, const double* waste, uint8_t* best_mask) {
+  std::vector<int> opts;
+  for (int t = 0; t < T; ++t) if (node_count[t] > 0) opts.push_back(t);
+  for (int c = 0; c < chain_len; ++c) {
+    std::vector<int> best;
+    if (chain[c] == CAE_EXP_LEAST_WASTE) {
+      double least = 0.0;
+      for (int t : opts) {
+        double w = waste[t];
+        if (w == least) best.push_back(t);
+        if (best.empty() || w < least) { least = w; best.assign(1, t); }
+      }
+    } else if (chain[c] == CAE_EXP_MOST_PODS) {
+      int mx = 0;
+      for (int t : opts) {
+        if (pod_count[t] == mx) { best.push_back(t); continue; }
+        if (pod_count[t] > mx) { mx = pod_count[t]; best.assign(1, t); }
+      }
+    } else if (chain[c] == CAE_EXP_LEAST_NODES) {
+      int least = INT32_MAX;
+      for (int t : opts) {
+        if (node_count[t] == 0) continue;
+        if (node_count[t] == least) { best.push_back(t); continue; }
+        if (node_count[t] < least) { least = node_count[t]; best.assign(1, t); }
+      }
+    } else { cae::set_error("unknown expander filter"); return 1; }
+    opts.swap(best);
+    if (opts.size() == 1) break;
+  }
+  if (best_mask) {
+    std::fill(best_mask, best_mask + T, 0);
+    for (int t : opts) best_mask[t] = 1;
+  }
+  return 0;
+}
+
 extern "C" {
 
 const char* cae_last_error(void) { return cae::g_err.c_str(); }
@@ -667,42 +707,30 @@ int32_t cae_expander_best(cae_engine* h, const int32_t* chain, int32_t chain_len
   cudaEventElapsedTime(&ms, e->ev0, e->ev1);
   e->stats.expander_ms = ms;
   if (waste_score) std::copy(waste.begin(), waste.end(), waste_score);
-  // The filter chain itself is a sequential scan over <= T options in option order
-  // (expander/factory/chain.go:36-45) — it keeps the reference's order-dependent quirks
-  // (waste.go:58-65: equality tested before the nil/less-than branch).
-  std::vector<int> opts;
-  for (int t = 0; t < T; ++t) if (node_count[t] > 0) opts.push_back(t);
-  for (int c = 0; c < chain_len; ++c) {
-    std::vector<int> best;
-    if (chain[c] == CAE_EXP_LEAST_WASTE) {
-      double least = 0.0;
-      for (int t : opts) {
-        double w = waste[t];
-        if (w == least) best.push_back(t);
-        if (best.empty() || w < least) { least = w; best.assign(1, t); }
-      }
-    } else if (chain[c] == CAE_EXP_MOST_PODS) {
-      int mx = 0;
-      for (int t : opts) {
-        if (pod_count[t] == mx) { best.push_back(t); continue; }
-        if (pod_count[t] > mx) { mx = pod_count[t]; best.assign(1, t); }
-      }
-    } else if (chain[c] == CAE_EXP_LEAST_NODES) {
-      int least = INT32_MAX;
-      for (int t : opts) {
-        if (node_count[t] == 0) continue;
-        if (node_count[t] == least) { best.push_back(t); continue; }
-        if (node_count[t] < least) { least = node_count[t]; best.assign(1, t); }
-      }
-    } else { cae::set_error("unknown expander filter"); return 1; }
-    opts.swap(best);
-    if (opts.size() == 1) break;
-  }
-  if (best_mask) {
-    std::fill(best_mask, best_mask + T, 0);
-    for (int t : opts) best_mask[t] = 1;
-  }
+  return run_expander_chain(chain, chain_len, T, node_count, pod_count, waste.data(), best_mask);
+}
+
+int32_t cae_waste_scores(cae_engine* h, double* waste_score) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (!e || !e->loaded || !waste_score) { cae::set_error("cae_waste_scores before cae_load"); return -2; }
+  cudaSetDevice(e->cfg.device);
+  const int T = e->T;
+  if (T == 0) return 0;
+  void* pw = nullptr;
+  if (e->scratch.alloc(&pw, nullptr, sizeof(double) * T)) return -1;
+  const int32_t chain0 = CAE_EXP_LEAST_WASTE;
+  if (cae::launch_expander(e, &chain0, 1, e->d_counts2, nullptr, e->d_sched, nullptr, static_cast<double*>(pw))) return -1;
+  CAE_CUDA(cudaMemcpyAsync(waste_score, pw, sizeof(double) * T, cudaMemcpyDeviceToHost, e->stream));
+  CAE_CUDA(cudaStreamSynchronize(e->stream));
+  for (int t = 0; t < T; ++t)
+    if (t < e->t_begin || t >= e->t_end) waste_score[t] = 0.0;   // rows of other ranks: x + 0.0 == x, a sum all-reduce assembles the vector
   return 0;
+}
+
+int32_t cae_expander_chain(const int32_t* chain, int32_t chain_len, int32_t num_templates, const int32_t* node_count,
+                           const int32_t* pod_count, const double* waste_score, uint8_t* best_mask) {
+  if (!chain || !node_count || !pod_count || !waste_score || num_templates < 0) return -2;
+  return run_expander_chain(chain, chain_len, num_templates, node_count, pod_count, waste_score, best_mask);
 }
 
 int32_t cae_get_stats(cae_engine* h, cae_stats* out) {

@@ -175,6 +175,13 @@ class Engine:
         self._check(self.lib.cae_expander_best(self.h, vp(ch), len(ch), vp(nc), vp(pc), vp(sc), vp(mask), vp(waste)))
         return mask, waste
 
+    def waste_scores(self) -> np.ndarray:
+        """Least-waste score of this rank's template shard from the device-resident result of the last estimate_all
+        (0.0 for the rows of other ranks: a sum all-reduce of float64[T] assembles the vector)."""
+        waste = np.zeros(self.enc.T, np.float64)
+        self._check(self.lib.cae_waste_scores(self.h, waste.ctypes.data_as(C.c_void_p)))
+        return waste
+
     def filter_schedulable(self, pod_order: Sequence[int], hint_node=None, sim_class=None, class_ctrl=None, node_ok=None,
                            last_index: int = 0, break_on_failure: bool = False):
         """HintingSimulator.TrySchedulePods on the cluster snapshot of the last load.  Returns (assigned[P] cluster node
@@ -217,6 +224,21 @@ class Engine:
         n = C.c_size_t(0)
         p = self.lib.cae_device_buffer(self.h, which, C.byref(n))
         return int(p or 0), int(n.value)
+
+
+def expander_chain(chain: Sequence[int], node_count, pod_count, waste) -> np.ndarray:
+    """The expander filter chain on the host (cae_expander_chain): needs the library, not a GPU."""
+    lib = capi.load_engine_lib()
+    ch = np.asarray(chain, np.int32)
+    nc = np.ascontiguousarray(node_count, np.int32)
+    pc = np.ascontiguousarray(pod_count, np.int32)
+    w = np.ascontiguousarray(waste, np.float64)
+    mask = np.zeros(len(nc), np.uint8)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.cae_expander_chain(vp(ch), len(ch), len(nc), vp(nc), vp(pc), vp(w), vp(mask))
+    if rc != 0:
+        raise EngineError("cae_expander_chain status %d: %s" % (rc, (lib.cae_last_error() or b"").decode()))
+    return mask
 
 
 def unpack_bits(bits: np.ndarray, P: int) -> np.ndarray:

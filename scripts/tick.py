@@ -26,7 +26,7 @@ def main():
     args = ap.parse_args()
     rank, world, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
-    if world > 1:   # torchrun: templates sharded over the ranks, ONE all-reduce of int32[2T] (node_count | pod_count)
+    if world > 1:   # torchrun: templates sharded over the ranks; all-reduce of int32[2T] (node_count | pod_count) + float64[T] (waste)
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
@@ -48,7 +48,7 @@ def main():
         t0 = time.perf_counter()
         eng.load(enc)
         t1 = time.perf_counter()
-        nc, pc, sched, order = eng.estimate_all(caps, copy=False)
+        nc, pc, sched, order = eng.estimate_all(caps, want_sched=dist is None or args.check > 0, copy=False)
         if dist is not None:
             if counts_t is None:
                 ptr, nbytes = eng.device_buffer(1)
@@ -56,15 +56,19 @@ def main():
                 class _Wrap:
                     __cuda_array_interface__ = {"shape": (2 * enc.T,), "typestr": "<i4", "data": (ptr, False), "version": 3}
                 counts_t = torch.as_tensor(_Wrap(), device="cuda")
-            dist.all_reduce(counts_t)
+            waste_t = torch.from_numpy(eng.waste_scores()).cuda()   # own rows, 0.0 elsewhere (before the counts are summed)
+            dist.all_reduce(counts_t)                                # int32[2T]: node_count | pod_count
+            dist.all_reduce(waste_t)                                 # float64[T]: exactly one non-zero contribution per row
             torch.cuda.synchronize()
             both = counts_t.cpu().numpy()
             nc, pc = both[:enc.T].copy(), both[enc.T:].copy()
-            sched_full = torch.from_numpy(np.ascontiguousarray(sched)).cuda()
-            dist.all_reduce(sched_full)          # [T][E] rows of foreign templates are zero: the expander needs them all
-            sched = sched_full.cpu().numpy()
         t2 = time.perf_counter()
-        mask, waste = eng.expander_best([0, 1, 2], nc, pc, sched if dist is not None else None)
+        if dist is not None:
+            from kubernetes_autoscaler_b200.engine import expander_chain
+            waste = waste_t.cpu().numpy()
+            mask = expander_chain([0, 1, 2], nc, pc, waste)
+        else:
+            mask, waste = eng.expander_best([0, 1, 2], nc, pc)
         t3 = time.perf_counter()
         st = eng.stats()
         rows.append({"load_ms": 1e3 * (t1 - t0), "estimate_wall_ms": 1e3 * (t2 - t1), "estimate_dev_ms": st.estimate_ms,

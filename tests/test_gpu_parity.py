@@ -51,6 +51,9 @@ def _check_estimate(eng, oracle, enc, caps):
         assert np.array_equal(waste, owaste)  # float64, bit-identical
         mask2, waste2 = eng.expander_best(chain, nc, pc)   # device-resident result of the estimate just run
         assert np.array_equal(mask2, omask) and np.array_equal(waste2, owaste)
+        from kubernetes_autoscaler_b200.engine import expander_chain   # the two halves used when templates are sharded
+        assert np.array_equal(eng.waste_scores(), owaste)
+        assert np.array_equal(expander_chain(chain, nc, pc, owaste), omask)
     return nc, pc
 
 

@@ -36,7 +36,14 @@ def _worker(rank, world, port, out_dir):
     # pack: templates sharded, zero-filled int32[2T] all-reduced
     tb, te = shard_templates(enc.T, rank, world)
     caps = np.full(enc.T, 50, np.int32)
-    nc, pc, _, _, _ = pyoracle.estimate_all(enc, caps, t_range=(tb, te))
+    nc, pc, sched, _, _ = pyoracle.estimate_all(enc, caps, t_range=(tb, te))
+    # expander: least-waste scores of the own templates, 0.0 elsewhere; a float64 sum all-reduce assembles them exactly
+    full_nc, full_pc, full_sched = np.zeros(enc.T, np.int32), np.zeros(enc.T, np.int32), np.zeros((enc.T, enc.E), np.int32)
+    full_nc[tb:te], full_pc[tb:te], full_sched[tb:te] = nc, pc, sched
+    _, own_waste = pyoracle.expander(enc, [0], full_nc, full_pc, full_sched)
+    waste = torch.zeros(enc.T, dtype=torch.float64)
+    waste[tb:te] = torch.from_numpy(own_waste[tb:te])
+    dist.all_reduce(waste)
     counts = torch.zeros(2 * enc.T, dtype=torch.int32)
     counts[tb:te] = torch.from_numpy(nc)
     counts[enc.T + tb:enc.T + te] = torch.from_numpy(pc)
@@ -46,6 +53,7 @@ def _worker(rank, world, port, out_dir):
     if rank == 0:
         np.save(os.path.join(out_dir, "hist.npy"), hist.numpy())
         np.save(os.path.join(out_dir, "counts.npy"), counts.numpy())
+        np.save(os.path.join(out_dir, "waste.npy"), waste.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -68,8 +76,16 @@ def test_two_rank_gloo_assembles_the_single_rank_result(tmp_path, oracle):
     want, _ = oracle.feasibility_dense(enc)
     assert np.array_equal(np.load(tmp_path / "hist.npy"), (want == 0).sum(axis=1))
     caps = np.full(enc.T, 50, np.int32)
-    nc, pc, _, _, _ = oracle.estimate_all(enc, caps)
+    nc, pc, sched, _, _ = oracle.estimate_all(enc, caps)
     assert np.array_equal(np.load(tmp_path / "counts.npy"), np.concatenate([nc, pc]))
+    # the sharded expander: all-reduced waste vector is bit-identical, and the host chain (cae_expander_chain, no GPU
+    # needed) picks the same options as the single-rank expander
+    from kubernetes_autoscaler_b200.engine import expander_chain
+    waste = np.load(tmp_path / "waste.npy")
+    for chain in ([0], [0, 1, 2], [2, 0], [1]):
+        omask, owaste = oracle.expander(enc, chain, nc, pc, sched)
+        assert np.array_equal(waste, owaste)
+        assert np.array_equal(expander_chain(chain, nc, pc, waste), omask), chain
     # word-aligned shards: bit rows concatenate into the full matrix
     full = np.concatenate([np.load(tmp_path / ("bits%d.npy" % r)) for r in range(world)], axis=1)
     assert np.array_equal(np.unpackbits(full, axis=1, bitorder="little")[:, :enc.P].astype(bool), want == 0)
