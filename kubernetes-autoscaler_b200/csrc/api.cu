@@ -759,7 +759,10 @@ int32_t cae_filter_schedulable(cae_engine* h, const int32_t* pod_order, int32_t 
   }
   cudaSetDevice(e->cfg.device);
   const int P = e->P, N = e->N;
-  if (last_index_in < 0 || (N > 0 && last_index_in >= N)) last_index_in = 0;
+  // plugin_runner.go:81 scans from (lastIndex + i) % len: a lastIndex left by a longer node list wraps, and stays as it is
+  // until a scan places a pod (:123)
+  const int32_t last_index_raw = last_index_in;
+  last_index_in = N > 0 ? (int32_t)((((int64_t)last_index_in % N) + N) % N) : 0;
   // runs: consecutive pods of the order with the same spec and similarity class and no hint
   std::vector<int32_t> run_off;
   for (int k = 0; k < n_pods; ++k) {
@@ -831,7 +834,7 @@ int32_t cae_filter_schedulable(cae_engine* h, const int32_t* pod_order, int32_t 
   cudaEventRecord(e->ev0, e->stream);
   if (runs > 0 && cae::launch_filter(e, f)) return -1;
   cudaEventRecord(e->ev1, e->stream);
-  int32_t out[4] = {last_index_in, 0, 0, 0}, status = 0;
+  int32_t out[4] = {last_index_raw, 0, 0, 0}, status = 0;
   if (P) CAE_CUDA(cudaMemcpyAsync(assigned_node, e->d_fm_blob + o_asg, (size_t)P * 4, cudaMemcpyDeviceToHost, e->stream));
   if (runs > 0) {
     CAE_CUDA(cudaMemcpyAsync(out, e->d_fm_blob + o_out, sizeof(out), cudaMemcpyDeviceToHost, e->stream));
@@ -842,7 +845,7 @@ int32_t cae_filter_schedulable(cae_engine* h, const int32_t* pod_order, int32_t 
   cudaEventElapsedTime(&ms, e->ev0, e->ev1);
   e->stats.estimate_ms = ms;
   if (status) { cae::set_error("placement log overflow in the filter pass"); return 1; }
-  if (last_index_out) *last_index_out = out[0];
+  if (last_index_out) *last_index_out = out[3] ? out[0] : last_index_raw;
   if (overflowing_controllers) *overflowing_controllers = out[1];
   return 0;
 }

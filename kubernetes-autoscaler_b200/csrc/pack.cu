@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(PACK_WARPS * 32, PACK_MIN_BLOCKS) pack_kernel(
     const int max_nodes = (!FM && p.max_nodes) ? p.max_nodes[t] : 0;
     const int col_new = N + p.T + t;  // universe column of the sanitized template
     int n_new = 0, nodes_with_pods = 0, pods_total = 0, last_index = FM ? p.fm_last_index : 0, log_n = 0;
-    bool new_nodes_available = !FM, cl_init = false, overflow = false, fm_stop = false;
+    bool new_nodes_available = !FM, cl_init = false, overflow = false, fm_stop = false, fm_moved = false;
     const int n_groups = FM ? p.fm_runs : p.order_n[t];
 
     // ---- shared helpers -----------------------------------------------------------------------
@@ -759,6 +759,7 @@ __global__ void __launch_bounds__(PACK_WARPS * 32, PACK_MIN_BLOCKS) pack_kernel(
                 if (hit >= 0) {
                   place(hit);
                   last_index = (hit + 1) % len;
+                  fm_moved = true;
                   where = hit;
                 } else {
                   run_failed = true;
@@ -878,7 +879,7 @@ __global__ void __launch_bounds__(PACK_WARPS * 32, PACK_MIN_BLOCKS) pack_kernel(
       over = wsum(over);
       if (lane == 0) {
         hdr[0] = stamp_ctr; hdr[1] = gver_ctr;
-        p.fm_out[0] = last_index; p.fm_out[1] = over; p.fm_out[2] = pods_total;
+        p.fm_out[0] = last_index; p.fm_out[1] = over; p.fm_out[2] = pods_total; p.fm_out[3] = fm_moved ? 1 : 0;
         if (overflow && p.status) atomicExch(p.status, 1);
       }
     } else if (lane == 0) {

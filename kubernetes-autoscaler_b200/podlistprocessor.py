@@ -123,8 +123,7 @@ class HintingSimulator:
     def _run(self, x: TryScheduleInputs, breakOnFailure: bool):
         eng = self.engine or shared_engine()
         eng.load(x.enc)
-        return eng.filter_schedulable(x.order, x.hint, x.sim_class, x.class_ctrl, x.node_ok,
-                                      self.last_index if self.last_index < len(x.cluster) else 0, breakOnFailure)
+        return eng.filter_schedulable(x.order, x.hint, x.sim_class, x.class_ctrl, x.node_ok, self.last_index, breakOnFailure)
 
     def TrySchedulePods(self, cluster_snapshot: Sequence[NodeInfo], pods: Sequence[Pod],
                         isNodeAcceptable: Callable[[NodeInfo], bool] = ScheduleAnywhere, breakOnFailure: bool = False,

@@ -17,8 +17,7 @@ class OracleSimulator(plp.HintingSimulator):
 
     def _run(self, x, breakOnFailure):
         from oracle import pyoracle
-        return pyoracle.filter_schedulable(x.enc, x.order, x.hint, x.sim_class, x.class_ctrl, x.node_ok,
-                                           self.last_index if self.last_index < len(x.cluster) else 0, breakOnFailure)
+        return pyoracle.filter_schedulable(x.enc, x.order, x.hint, x.sim_class, x.class_ctrl, x.node_ok, self.last_index, breakOnFailure)
 
 
 def _ready_node(name, cpu, mem):
@@ -241,7 +240,7 @@ def _both(gpu_engine, cluster, pods, hints=None, ok=plp.ScheduleAnywhere, brk=Fa
 def test_gpu_filter_semantics(gpu_engine, scn):
     _, cluster, pods = scn
     for brk in (False, True):
-        for li in (0, len(cluster) - 1):
+        for li in (0, len(cluster) - 1, 2 * len(cluster) + 1):   # a lastIndex left by a longer list wraps (plugin_runner.go:81)
             _both(gpu_engine, cluster, pods, brk=brk, last_index=li)
     _both(gpu_engine, cluster, pods, hints={pods[-1].name: cluster[-1].node.name, pods[0].name: cluster[0].node.name})
     _both(gpu_engine, cluster, pods, ok=lambda ni: ni.node.name != cluster[0].node.name)
@@ -261,3 +260,79 @@ def test_gpu_filter_synthetic(gpu_engine):
         got = gpu_engine.filter_schedulable(order)
         assert np.array_equal(got[0], want[0])
         assert got[1:] == want[1:]
+
+
+# ---- scale-down consumer: RemovalSimulator.SimulateNodeRemoval (simulator/cluster_test.go:46-230) ------------------------
+def _removal_cases():
+    from kubernetes_autoscaler_b200.objects import BuildTestNode as N
+    def rs(p):
+        p.owner_uid, p.owner_kind = "rs", "ReplicaSet"
+        return p
+    def topo(name):
+        p = rs(BuildTestPod(name, 100, 100000, WithLabels({"app": "topo-app"})))
+        p.topology_spread = [TopologySpreadConstraint(1, "kubernetes.io/hostname", LabelSelector({"app": "topo-app"}), min_domains=2)]
+        return p
+    def tnode(name):
+        n = N(name, 1000, 2000000)
+        n.labels = {"kubernetes.io/hostname": name}
+        return n
+    def mk():
+        empty = NodeInfo(N("n1", 1000, 2000000))
+        drainable = NodeInfo(N("n2", 1000, 2000000), [rs(BuildTestPod("p1", 100, 100000)), rs(BuildTestPod("p2", 100, 100000))])
+        nondrain = NodeInfo(N("n3", 1000, 2000000), [BuildTestPod("p3", 100, 100000)])
+        full = NodeInfo(N("n4", 1000, 2000000), [BuildTestPod("p4", 1000, 100000)])
+        t1 = NodeInfo(tnode("topo-n1"), [topo("p5")])
+        t2 = NodeInfo(tnode("topo-n2"), [topo("p6"), BuildTestPod("blocker1", 100, 100000)])
+        t3 = NodeInfo(tnode("topo-n3"), [topo("p7"), BuildTestPod("blocker2", 100, 100000)])
+        return dict(empty=empty, drainable=drainable, nondrain=nondrain, full=full, t1=t1, t2=t2, t3=t3)
+    return mk, [
+        ("just an empty node, should be removed", ["empty"], "n1", ("remove", [])),
+        ("just a drainable node, but nowhere for pods to go to", ["drainable"], "n2", ("unremovable", "NoPlaceToMovePods")),
+        ("drainable node, and a mostly empty node that can take its pods", ["drainable", "nondrain"], "n2", ("remove", ["p1", "p2"])),
+        ("drainable node, and a full node that cannot fit anymore pods", ["drainable", "full"], "n2", ("unremovable", "NoPlaceToMovePods")),
+        ("4 nodes, 1 empty, 1 drainable", ["empty", "drainable", "full", "nondrain"], "n1", ("remove", [])),
+        ("topology spread constraint test - one node should be removable", ["t1", "t2", "t3"], "topo-n1", ("remove", ["p5"])),
+        ("candidate not in clusterSnapshot should be marked unremovable", [], "n5", ("unremovable", "NoNodeInfo")),
+    ]
+
+
+def _run_removal_case(make_sim, case):
+    from kubernetes_autoscaler_b200.removal import RemovalSimulator
+    mk, _ = _removal_cases()
+    _, names, node_name, want = case
+    nodes = mk()
+    cluster = [nodes[n] for n in names]
+    r = RemovalSimulator(cluster, False, schedulingSimulator=make_sim())
+    to_remove, unremovable = r.SimulateNodeRemoval(node_name, {ni.node.name: True for ni in cluster})
+    if want[0] == "remove":
+        assert unremovable is None and to_remove.node.name == node_name
+        assert [p.name for p in to_remove.pods_to_reschedule] == want[1]
+    else:
+        assert to_remove is None and unremovable.reason == want[1] and unremovable.node.name == node_name
+
+
+REMOVAL_CASES = _removal_cases()[1]
+
+
+@pytest.mark.parametrize("case", REMOVAL_CASES, ids=[c[0] for c in REMOVAL_CASES])
+def test_oracle_simulate_node_removal_kat(case):
+    _run_removal_case(OracleSimulator, case)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", REMOVAL_CASES, ids=[c[0] for c in REMOVAL_CASES])
+def test_gpu_simulate_node_removal_kat(gpu_engine, case):
+    _run_removal_case(lambda: plp.HintingSimulator(gpu_engine), case)
+
+
+def test_removal_persists_successful_simulations():
+    from kubernetes_autoscaler_b200.removal import RemovalSimulator
+    mk, _ = _removal_cases()
+    nodes = mk()
+    cluster = [nodes["drainable"], nodes["nondrain"], nodes["empty"]]
+    r = RemovalSimulator(cluster, True, schedulingSimulator=OracleSimulator())
+    to_remove, _ = r.SimulateNodeRemoval("n2", {"n1": True, "n3": True})
+    assert to_remove is not None and [ni.node.name for ni in cluster] == ["n3", "n1"]
+    assert sorted(p.name for ni in cluster for p in ni.pods) == ["p1", "p2", "p3"]
+    # hints of the persisted simulation steer the next one (the pods would go back to where they were placed)
+    assert r.schedulingSimulator.hints.Get(("default", "p1")) in ("n1", "n3")

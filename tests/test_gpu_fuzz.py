@@ -178,7 +178,7 @@ def _filter_scenario(seed):
     hints = {p.name: rng.choice(cluster).node.name for p in pods if rng.random() < 0.15}
     namespaces = [Namespace("other", {"team": "a"})] if rng.random() < 0.5 else []
     banned = {ni.node.name for ni in cluster if rng.random() < 0.15} if rng.random() < 0.3 else set()
-    return cluster, pods, hints, namespaces, banned, rng.random() < 0.2, rng.randrange(len(cluster))
+    return cluster, pods, hints, namespaces, banned, rng.random() < 0.2, rng.randrange(2 * len(cluster))
 
 
 @pytest.mark.parametrize("block", range(4))
