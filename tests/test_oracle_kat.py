@@ -127,3 +127,51 @@ def test_capacity_thresholds(oracle):
     assert oracle.sng_capacity_limit(True, [5, 10, 100], [5, 10, 100]) == -1
     assert oracle.sng_capacity_limit(True, [5, 10, 100, 0], [10, 11, 111, 5]) == -1
     assert oracle.sng_capacity_limit(False, [10], [5]) == 0
+
+
+# simulator/clustersnapshot/predicate/plugin_runner_test.go:43-196 (TestRunFiltersOnNode, default scheduler config):
+# (scheduled pods on n1000, test pod, failing plugin or None)
+def _runner_cases():
+    from kubernetes_autoscaler_b200.objects import BuildTestNode, WithNodeNamesAffinity
+    p450, p600, p8000, p500 = (BuildTestPod("p450", 450, 500000), BuildTestPod("p600", 600, 500000),
+                               BuildTestPod("p8000", 8000, 0), BuildTestPod("p500", 500, 500000))
+    aff = BuildTestPod("pod_with_affinity", 500, 500, WithNodeNamesAffinity("n1000"))
+    bad_aff = BuildTestPod("pod_with_affinity", 500, 500, WithNodeNamesAffinity("non-existing-node"))
+    n1000 = lambda pods: NodeInfo(BuildTestNode("n1000", 1000, 2000000), pods)
+    FIT, PREFILTER = 7, 1   # CAE_R_FIT ("NodeResourcesFit": Insufficient cpu), CAE_R_PREFILTER_NODEAFFINITY ("PreFilter filtered the Node out")
+    return [
+        ("default - other pod - insuficient cpu (:85)", n1000([p450]), p600, FIT),
+        ("default - other pod - ok (:95)", n1000([p450]), p500, 0),
+        ("default - empty - insuficient cpu (:102)", n1000([]), p8000, FIT),
+        ("default - empty - ok (:112)", n1000([]), p600, 0),
+        ("default - affinity on existing node - ok (:121)", n1000([]), aff, 0),
+        ("default - affinity on non-existing node - error (:128)", n1000([]), bad_aff, PREFILTER),
+    ]
+
+
+RUNNER_CASES = _runner_cases()
+
+
+@pytest.mark.parametrize("case", RUNNER_CASES, ids=[c[0] for c in RUNNER_CASES])
+def test_run_filters_on_node_kat(oracle, case):
+    """The node under test is the 'template' (CheckPredicates on a node that joined the snapshot); its scheduled pods are the
+    NodeInfo's pods."""
+    _, node, pod, want = case
+    enc = encode([], [node], [makePodEquivalenceGroup(pod, 1)])
+    reasons, _ = oracle.feasibility_dense(enc)
+    assert int(reasons[0][0]) == want
+
+
+# plugin_runner_test.go:198-294 (TestRunFilterUntilPassingNode, default config): nodes n1000, n2000
+@pytest.mark.parametrize("cpu,expected", [(900, {"n1000", "n2000"}), (1900, {"n2000"}), (2100, set())],
+                         ids=["default - small pod - no error (:231)", "default - medium pod - no error (:237)",
+                              "default - large pod - insufficient cpu (:243)"])
+def test_run_filters_until_passing_node_kat(oracle, cpu, expected):
+    from kubernetes_autoscaler_b200.objects import BuildTestNode
+    cluster = [NodeInfo(BuildTestNode("n1000", 1000, 2000000)), NodeInfo(BuildTestNode("n2000", 2000, 2000000))]
+    enc = encode(cluster, [], [makePodEquivalenceGroup(BuildTestPod("p", cpu, 1000), 1)])
+    assigned, _, _ = oracle.filter_schedulable(enc, [0])
+    if expected:
+        assert cluster[int(assigned[0])].node.name in expected
+    else:
+        assert int(assigned[0]) == -1
