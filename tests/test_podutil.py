@@ -53,3 +53,13 @@ def test_build_pod_groups_limit_per_controller():
     ds = BuildTestPod("ds", 1, 1)
     ds.owner_uid, ds.owner_kind = "d", "DaemonSet"
     assert [len(g.pods) for g in build_pod_groups([ds, ds])] == [1, 1]
+
+
+def test_build_pod_groups_ignores_daemonsets():
+    """core/scaleup/equivalence/groups_test.go:170-187: DaemonSet-owned pods are never grouped."""
+    from kubernetes_autoscaler_b200.objects import BuildTestPod
+    from kubernetes_autoscaler_b200.podutil import build_pod_groups
+    pods = [BuildTestPod("p1", 3000, 200000), BuildTestPod("p2", 3000, 200000)]
+    for p in pods:
+        p.owner_uid, p.owner_kind = "12345678-1234-1234-1234-123456789012", "DaemonSet"
+    assert len(build_pod_groups(pods)) == 2
