@@ -438,7 +438,8 @@ static int do_load(Engine* e, const cae_objects* o) {
       dev_alloc(e, &e->d_chunk_done, (size_t)std::max(e->Twp / FEAS_TW, 1), true) || dev_alloc(e, &e->d_group_reason, (size_t)std::max(T, 1) * std::max(e->E, 1)) ||
       dev_alloc(e, &e->d_counts2, (size_t)2 * std::max(T, 1), true) || dev_alloc(e, &e->d_sched, (size_t)std::max(T, 1) * std::max(e->E, 1), true) ||
       dev_alloc(e, &e->d_order, (size_t)std::max(T, 1) * std::max(e->E, 1)) || dev_alloc(e, &e->d_order_n, (size_t)std::max(T, 1), true) ||
-      dev_alloc(e, &e->d_max_nodes, (size_t)std::max(T, 1), true) || dev_alloc(e, &e->d_work_counter, 4, true) ||
+      dev_alloc(e, &e->d_max_nodes, (size_t)std::max(T, 1), true) || dev_alloc(e, &e->d_tmpl_cost, (size_t)std::max(T, 1), true) ||
+      dev_alloc(e, &e->d_perm, (size_t)std::max(T, 1)) || dev_alloc(e, &e->d_work_counter, 4, true) ||
       dev_alloc(e, &e->d_act_dim, CAE_MAX_RES))
     return -1;
   e->d_score = nullptr;
@@ -546,6 +547,7 @@ int32_t cae_create(const cae_config* cfg, cae_engine** out) {
   cudaEventCreate(&e->ev1);
   { const char* v = getenv("CAE_K1_BITSLICE"); e->force_bitslice = v && v[0] == '1'; }
   { const char* v = getenv("CAE_K1_WARPS"); if (v && atoi(v) == 8) e->k1_warps = 8; }
+  { const char* v = getenv("CAE_PACK_LPT"); e->pack_lpt = v && v[0] == '1'; }
   { const char* v = getenv("CAE_PACK_WARPS_PER_SM"); if (v && atoi(v) >= 1 && atoi(v) <= 64) e->pack_warps_per_sm = atoi(v); }
   *out = reinterpret_cast<cae_engine*>(e);
   return 0;

@@ -105,6 +105,9 @@ struct Engine {
   uint8_t lut_word[CAE_MAX_RES] = {0}, lut_shift[CAE_MAX_RES] = {0};
   uint32_t lut_mask[CAE_MAX_RES] = {0};
   uint32_t* d_rlut = nullptr;             // [lut_rows][Twp]
+  bool pack_lpt = false;                  // CAE_PACK_LPT=1: hand templates to the estimator warps longest first (experimental, off)
+  long long* d_tmpl_cost = nullptr;       // [T] pods in the schedulable groups of a template (order kernel)
+  int32_t* d_perm = nullptr;              // [T] work order of the pack
   int pack_warps_per_sm = 20;             // resident estimator warps per SM (CAE_PACK_WARPS_PER_SM)
   int k1_warps = 16;                      // warps per thread block of the LUT variant (CAE_K1_WARPS=8|16)
   bool force_bitslice = false;            // CAE_K1_BITSLICE=1: always take the bit-sliced comparator (tests)

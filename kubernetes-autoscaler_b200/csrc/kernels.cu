@@ -137,12 +137,15 @@ int launch_port_conflicts(Engine* e, int num_port_lists) {
 // ------------------------------------------------------------------------------------------------
 __global__ void order_kernel(DevObjects o, int E, int T, int N, int t_begin, int n_sort,
                              const uint8_t* __restrict__ group_reason, double* __restrict__ score_out,
-                             int32_t* __restrict__ order, int32_t* __restrict__ order_n) {
+                             int32_t* __restrict__ order, int32_t* __restrict__ order_n, long long* __restrict__ tmpl_cost) {
   extern __shared__ unsigned char smem_raw[];
+  __shared__ unsigned long long s_cost;   // pods in this template's schedulable groups: the pack's work estimate
   double* s_key = reinterpret_cast<double*>(smem_raw);
   int32_t* s_idx = reinterpret_cast<int32_t*>(s_key + n_sort);
   const int t = t_begin + blockIdx.x;
   if (t >= T) return;
+  if (threadIdx.x == 0) s_cost = 0ull;
+  __syncthreads();
   const int node = N + t;
   const int64_t acpu = o.node_alloc[(size_t)node * R + CAE_RES_CPU], amem = o.node_alloc[(size_t)node * R + CAE_RES_MEM];
   const bool use_cpu = o.node_has_alloc_cpu[node] && acpu > 0, use_mem = o.node_has_alloc_mem[node] && amem > 0;
@@ -157,6 +160,7 @@ __global__ void order_kernel(DevObjects o, int E, int T, int N, int t_begin, int
       if (use_mem) sc = __dadd_rn(sc, __ddiv_rn(__ll2double_rn(o.ps_req[(size_t)spec * R + CAE_RES_MEM]), __ll2double_rn(amem)));
       idx = g;
       if (score_out) score_out[(size_t)t * E + g] = sc;
+      if (tmpl_cost) atomicAdd(&s_cost, (unsigned long long)(o.group_off[g + 1] - o.group_off[g]));
     }
     s_key[g] = sc;
     s_idx[g] = idx;
@@ -191,6 +195,7 @@ __global__ void order_kernel(DevObjects o, int E, int T, int N, int t_begin, int
     while (lo < hi) { int mid = (lo + hi) >> 1; if (s_idx[mid] != INT_MAX) lo = mid + 1; else hi = mid; }
     n = lo;
     order_n[t] = n;
+    if (tmpl_cost) tmpl_cost[t] = (long long)s_cost;
   }
 }
 
@@ -203,7 +208,7 @@ int launch_order(Engine* e) {
   if (smem > 200 * 1024) { set_error("too many pod groups for the in-smem orderer"); return 1; }
   CAE_CUDA(cudaFuncSetAttribute(order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   order_kernel<<<nt, 256, smem, e->stream>>>(e->dobj, e->E, e->T, e->N, e->t_begin, n_sort, e->d_group_reason,
-                                              e->d_score, e->d_order, e->d_order_n);
+                                              e->d_score, e->d_order, e->d_order_n, e->pack_lpt ? e->d_tmpl_cost : nullptr);
   e->stats.kernel_launches++;
   CAE_KERNEL_OK();
   return 0;

@@ -25,7 +25,9 @@
 // list is the N cluster nodes, pods arrive as runs of consecutive identical pods in the caller's order and
 // every pod is placed with the per-pod loop (hint first, then SchedulePodOnAnyNodeMatching from lastIndex),
 // with the SimilarPodsScheduling shortcut (similar_pods.go:59-104).
+#include <algorithm>
 #include <climits>
+#include <vector>
 
 #include "engine.h"
 
@@ -35,6 +37,7 @@ struct PackParams {
   int E, T, N, U, t_begin, t_end, cap, has_dyn, dstride, log_cap, nblk;
   size_t bmax_off;
   const int32_t *order, *order_n;
+  const int32_t* perm;     // work order of the templates (NULL = index order)
   const uint8_t* pre_code;
   const int32_t *spec_sc, *spec_dc;
   const int64_t* tmpl_free;  // [A][T]
@@ -124,7 +127,10 @@ __global__ void __launch_bounds__(PACK_WARPS * 32, PACK_MIN_BLOCKS) pack_kernel(
 
   for (;;) {
     int t = 0;
-    if (lane == 0) t = p.t_begin + atomicAdd(p.work_counter, 1);
+    if (lane == 0) {
+      const int i = atomicAdd(p.work_counter, 1);
+      t = i >= p.t_end - p.t_begin ? p.t_end : (p.perm ? p.perm[i] : p.t_begin + i);
+    }
     t = __shfl_sync(0xffffffffu, t, 0);
     if (t >= p.t_end) break;
 
@@ -977,6 +983,17 @@ int launch_pack(Engine* e) {
   p.scratch = static_cast<unsigned char*>(e->d_pack_scratch);
   p.scratch_per_warp = per_warp;
   CAE_CUDA(cudaMemsetAsync(e->d_work_counter, 0, sizeof(int32_t) * 2, e->stream));
+  if (e->pack_lpt) {   // longest processing time first: fewer idle SMs while the last templates finish
+    std::vector<long long> cost(nt);
+    CAE_CUDA(cudaMemcpyAsync(cost.data(), e->d_tmpl_cost + e->t_begin, sizeof(long long) * nt, cudaMemcpyDeviceToHost, e->stream));
+    CAE_CUDA(cudaStreamSynchronize(e->stream));
+    std::vector<int32_t> perm(nt);
+    for (int i = 0; i < nt; ++i) perm[i] = e->t_begin + i;
+    std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) { return cost[a - e->t_begin] > cost[b - e->t_begin]; });
+    CAE_CUDA(cudaMemcpyAsync(e->d_perm, perm.data(), sizeof(int32_t) * nt, cudaMemcpyHostToDevice, e->stream));
+    CAE_CUDA(cudaStreamSynchronize(e->stream));   // perm lives on this stack frame
+    p.perm = e->d_perm;
+  }
   launch_pack_any<false>(e->A, blocks, e->stream, e->dobj, e->dyn, p);
   e->stats.kernel_launches++;
   CAE_KERNEL_OK();

@@ -357,3 +357,17 @@ def test_dense_many_distinct_requests(eng, oracle):
     groups = [makePodEquivalenceGroup(BuildTestPod("p%d" % i, 100 + i, (64 + (i * 7) % 1500) << 20), 1) for i in range(1301)]
     enc = encode(cluster, templates, groups)
     _check_dense(eng, oracle, enc)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("CAE_TEST_EXPERIMENTAL") != "1",
+                    reason="CAE_PACK_LPT is an unmeasured, default-off work order (written after the round's GPU budget ran out)")
+def test_pack_longest_first_order(oracle, monkeypatch):
+    """CAE_PACK_LPT=1 only permutes the order in which templates are handed to warps: results must not change."""
+    from kubernetes_autoscaler_b200.engine import Engine
+    monkeypatch.setenv("CAE_PACK_LPT", "1")
+    e = Engine(device=0)
+    try:
+        for enc in (synth.generate(2, pods=6_000, templates=96), synth.generate(3, pods=3_000, templates=70, cluster_nodes=40)):
+            _check_estimate(e, oracle, enc, np.full(enc.T, 1000))
+    finally:
+        e.close()
