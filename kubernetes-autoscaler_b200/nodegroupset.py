@@ -12,7 +12,7 @@ engine is the exemplar feasibility matrix (``ScaleUpSimulation.schedulable_pod_g
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Sequence
 
 from .estimator import NodeGroupInfo
 
