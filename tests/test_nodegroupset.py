@@ -56,3 +56,90 @@ def test_compute_similar_node_groups():
     assert ComputeSimilarNodeGroups("d", ["a"], sched) == []                      # nothing schedulable on the main group
     assert ComputeSimilarNodeGroups("a", ["b"], sched, balance_similar_node_groups=False) == []
     assert ComputeSimilarNodeGroups("a", ["b"], sched, zero_or_max_node_scaling=True) == []
+
+
+# ---- processors/nodegroupset/compare_nodegroups_test.go:41-197 ----------------------------------------------------------------
+from kubernetes_autoscaler_b200.nodegroupset import CreateGenericNodeInfoComparator, FindSimilarNodeGroups  # noqa: E402
+from kubernetes_autoscaler_b200.objects import BuildTestNode, BuildTestPod, NodeInfo  # noqa: E402
+from kubernetes_autoscaler_b200.snapshotz import quantity_value  # noqa: E402
+
+
+def _similar(n1, n2, want, pods1=(), pods2=(), extra=()):
+    cmp = CreateGenericNodeInfoComparator(extra)
+    assert cmp(NodeInfo(n1, list(pods1)), NodeInfo(n2, list(pods2))) is want
+
+
+def test_identical_nodes_similar():
+    _similar(BuildTestNode("node1", 1000, 2000), BuildTestNode("node2", 1000, 2000), True)
+
+
+def test_nodes_similar_various_requirements():
+    n1 = BuildTestNode("node1", 1000, 2000)
+    n2 = BuildTestNode("node2", 1000, 2000)
+    n2.capacity["cpu"] = 1001                                   # different CPU capacity
+    _similar(n1, n2, False)
+    n3 = BuildTestNode("node3", 1000, 2000)
+    n3.allocatable["cpu"] = 999                                 # slightly different allocatable
+    _similar(n1, n3, True)
+    n4 = BuildTestNode("node4", 1000, 2000)
+    n4.allocatable["cpu"] = 500                                 # significantly different allocatable
+    _similar(n1, n4, False)
+    n5 = BuildTestNode("node5", 1000, 2000)
+    n5.capacity["nvidia.com/gpu"] = n5.allocatable["nvidia.com/gpu"] = 1   # one with GPU, one without
+    _similar(n1, n5, False)
+
+
+def test_nodes_similar_various_requirements_and_pods():
+    n1, p1 = BuildTestNode("node1", 1000, 2000), BuildTestPod("pod1", 500, 1000)
+    n2 = BuildTestNode("node2", 1000, 2000)
+    n2.allocatable["cpu"], n2.allocatable["memory"] = 500, 1000  # different allocatable, but same free
+    _similar(n1, n2, False, [p1], [])
+    _similar(n1, BuildTestNode("node3", 1000, 2000), True, [p1], [BuildTestPod("pod3", 500, 1000)])
+    n4 = BuildTestNode("node4", 1000, 2000)
+    n4.allocatable["cpu"] = 999                                 # similar allocatable, similar pods
+    _similar(n1, n4, True, [p1], [BuildTestPod("pod4", 501, 1001)])
+
+
+def test_nodes_similar_various_memory_requirements():
+    n1 = BuildTestNode("node1", 1000, 1000)
+    n2 = BuildTestNode("node2", 1000, 1000)
+    n2.capacity["memory"] = int(1000 - (1000 * 0.015) + 1)
+    _similar(n1, n2, True)
+    n3 = BuildTestNode("node3", 1000, 1000)
+    n3.capacity["memory"] = int(1000 - (1000 * 0.015) - 1)
+    _similar(n1, n3, False)
+
+
+@pytest.mark.parametrize("q1,q2,q3", [("16116152Ki", "15944120Ki", "16438475Ki"), ("259970052Ki", "257217528Ki", "265169453Ki")],
+                         ids=["m5.xlarge", "m5.16xlarge"])
+def test_nodes_similar_large_memory(q1, q2, q3):
+    n1 = BuildTestNode("node1", 1000, quantity_value(q1))
+    _similar(n1, BuildTestNode("node2", 1000, quantity_value(q2)), True)    # another zone's instance of the same type
+    _similar(n1, BuildTestNode("node3", 1000, quantity_value(q3)), False)   # q1 * 1.02
+
+
+def test_nodes_similar_various_labels():
+    extra = ["example.com/ready"]
+    n1, n2 = BuildTestNode("node1", 1000, 2000), BuildTestNode("node2", 1000, 2000)
+    n1.labels.update({"test-label": "test-value", "character": "winnie the pooh"})
+    n2.labels["test-label"] = "test-value"
+    _similar(n1, n2, False, extra=extra)                        # missing character label
+    n2.labels["character"] = "winnie the pooh"
+    _similar(n1, n2, True, extra=extra)
+    n1.labels["kubernetes.io/hostname"], n2.labels["kubernetes.io/hostname"] = "node1", "node2"
+    _similar(n1, n2, True, extra=extra)
+    n1.labels["failure-domain.beta.kubernetes.io/zone"], n2.labels["failure-domain.beta.kubernetes.io/zone"] = "mars-olympus-mons1-b", "us-houston1-a"
+    _similar(n1, n2, True, extra=extra)
+    n1.labels["beta.kubernetes.io/fluentd-ds-ready"], n2.labels["beta.kubernetes.io/fluentd-ds-ready"] = "true", "false"
+    _similar(n1, n2, True, extra=extra)
+    del n2.labels["beta.kubernetes.io/fluentd-ds-ready"]
+    _similar(n1, n2, True, extra=extra)
+    n1.labels["example.com/ready"], n2.labels["example.com/ready"] = "true", "false"
+    _similar(n1, n2, True, extra=extra)
+
+
+def test_find_similar_node_groups():
+    infos = {"a": NodeInfo(BuildTestNode("ta", 1000, 2000)), "b": NodeInfo(BuildTestNode("tb", 1000, 2000)),
+             "c": NodeInfo(BuildTestNode("tc", 2000, 2000))}
+    assert FindSimilarNodeGroups("a", infos) == ["b"]
+    assert FindSimilarNodeGroups("c", infos) == []
