@@ -167,10 +167,10 @@ class ScaleUpSimulation:
     """All node groups of one autoscaler tick through the engine in one pass."""
 
     def __init__(self, cluster: Sequence[NodeInfo], templates: Dict[str, NodeInfo],
-                 groups: Sequence[PodEquivalenceGroup], engine: Optional[Engine] = None) -> None:
+                 groups: Sequence[PodEquivalenceGroup], engine: Optional[Engine] = None, namespaces=()) -> None:
         self.ids = list(templates.keys())
         self.groups = list(groups)
-        self.enc: EncodedObjects = encode(cluster, [templates[i] for i in self.ids], groups)
+        self.enc: EncodedObjects = encode(cluster, [templates[i] for i in self.ids], groups, namespaces)
         self.engine = engine or shared_engine()
         self.engine.load(self.enc)
 
