@@ -1,0 +1,1014 @@
+// binpack.cu — K3: BinpackingNodeEstimator.Estimate (estimator/binpacking_estimator.go:97-247) on the GPU.
+//
+// One THREAD BLOCK per template (templates are independent simulations; inside one, placement order is
+// sequential by construction), persistent with an atomic work counter over a longest-first work order.
+// A thread owns the nodes j = tid, tid + TPB, ... of the simulation ("thread per node"): the running
+// state of the nodes the estimate adds (free[A] int64, pod slots, used host ports, has-pods flag) lives
+// in SHARED memory, every per-group pass is one sweep of the block over the open nodes followed by a
+// block reduction; the state of the pre-existing cluster nodes (touched only by the hostname-spread
+// fallback) stays in a per-block global slab.
+//
+// Plain groups (identical pods, no topology spread / inter-pod affinity involvement): CLOSED FORM
+//   * tryToScheduleOnExistingNodes (:141-164): SchedulePodOnAnyNodeMatching scans cyclically from
+//     lastIndex (predicate/plugin_runner.go:81,123), so identical pods are dealt round-robin over the
+//     added nodes with spare capacity k_j: every node gets min(k_j, L), the first `rem` nodes in cyclic
+//     order with k_j > L get one more (L = largest lap count with sum min(k_j, L) <= n).
+//   * tryToScheduleOnNewNodes (:168-247): only the last added node is tried, so each new node takes
+//     min(remaining, k_new) until the limiter denies (:222); an empty last node stops the group (:212);
+//     a pod that fits no fresh node still adds one (:227-240).
+// Hostname-spread groups whose global minimum is PINNED at 0 (one DoNotSchedule constraint on
+// kubernetes.io/hostname counting only the group's own pods, and an eligible empty domain that can never
+// take a pod): the skew rule is then a per-node capacity (maxSkew - self - count) / weight + 1, so the
+// same round-robin closed form applies to the added nodes AND to the fallback of :186-205, which deals
+// the pods the last node refuses for skew over the CLUSTER nodes in cyclic order.
+// Every other dynamic group (dyn.cuh) runs the reference's per-pod loop against incremental counters
+// (copy-on-write over the cluster base counts): per pod one block-wide evaluation of every open node,
+// a block-wide arg-min of the cyclic distance, one placement.
+#include <algorithm>
+#include <climits>
+#include <vector>
+
+#include "engine.h"
+
+namespace cae {
+
+struct BpParams {
+  int E, T, N, U, t_begin, t_end, cap, has_dyn, dstride, log_cap;
+  int win;                 // added nodes resident in shared memory (= cap), 0 when they do not fit
+  const int32_t *order, *order_n;
+  const int32_t* perm;     // work order of the templates
+  const uint8_t* pre_code;
+  const int32_t *spec_sc, *spec_dc;
+  const int64_t* tmpl_free;  // [A][T]
+  const int32_t *tmpl_slots, *max_nodes, *pc_of;
+  const unsigned long long* port_conf;
+  const int64_t* c_free;  // [A][N]
+  const int32_t* c_slots;
+  int act_dim[CAE_MAX_RES];
+  int32_t *node_count, *pod_count, *sched, *work_counter, *status;
+  long long* prof;         // optional [16] counters (CAE_PACK_PROF)
+  unsigned char* scratch;
+  size_t scratch_per_cta;
+};
+
+constexpr int BP_HIST = 256;   // capacities up to this use the histogram; above, a binary search
+
+// description of the dynamic group being placed (shared memory, uniform reads)
+struct GroupDyn {
+  int nq;
+  int qid[DYN_MAX_Q], kind[DYN_MAX_Q], k[DYN_MAX_Q], host[DYN_MAX_Q], Dc[DYN_MAX_Q], tslot[DYN_MAX_Q];
+  int wown[DYN_MAX_Q], self[DYN_MAX_Q], maxskew[DYN_MAX_Q], mindom[DYN_MAX_Q], elig_new[DYN_MAX_Q], dsw[DYN_MAX_Q];
+  int minv[DYN_MAX_Q], nmin[DYN_MAX_Q], ndom[DYN_MAX_Q], tot[DYN_MAX_Q], boff[DYN_MAX_Q];
+  int aff_self;
+};
+
+struct BpShared {
+  GroupDyn wd;
+  int flag[DYN_MAX_Q];        // counters whose minimum must be recomputed
+  long long rl[2][32];
+  int ri[2][32][3];
+  int hist[BP_HIST + 1];      // #nodes per capacity value (closed-form lap count)
+  int t, L, rem, pre_s, log_n, overflow, newly, need_log, mlast;
+};
+
+__device__ __forceinline__ int bp_wsum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ long long bp_wsum_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int bp_wmax(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int bp_wmin(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block reductions: one barrier each.  Two scratch rows alternate (`par`), so a row is rewritten only
+// after every thread has passed the barrier of the reduction in between.
+template <int NW>
+__device__ __forceinline__ void blk_sum_ll_max(BpShared& S, int& par, long long& a, int& b) {
+  a = bp_wsum_ll(a); b = bp_wmax(b);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { S.rl[par][w] = a; S.ri[par][w][0] = b; }
+  __syncthreads();
+  a = bp_wsum_ll(lane < NW ? S.rl[par][lane] : 0ll);
+  b = bp_wmax(lane < NW ? S.ri[par][lane][0] : INT_MIN);
+  par ^= 1;
+}
+template <int NW>
+__device__ __forceinline__ void blk_sum_sum_max(BpShared& S, int& par, int& a, int& b, int& c) {
+  a = bp_wsum(a); b = bp_wsum(b); c = bp_wmax(c);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { S.ri[par][w][0] = a; S.ri[par][w][1] = b; S.ri[par][w][2] = c; }
+  __syncthreads();
+  a = bp_wsum(lane < NW ? S.ri[par][lane][0] : 0);
+  b = bp_wsum(lane < NW ? S.ri[par][lane][1] : 0);
+  c = bp_wmax(lane < NW ? S.ri[par][lane][2] : INT_MIN);
+  par ^= 1;
+}
+template <int NW>
+__device__ __forceinline__ void blk_min_sum(BpShared& S, int& par, int& a, int& b) {
+  a = bp_wmin(a); b = bp_wsum(b);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { S.ri[par][w][0] = a; S.ri[par][w][1] = b; }
+  __syncthreads();
+  a = bp_wmin(lane < NW ? S.ri[par][lane][0] : INT_MAX);
+  b = bp_wsum(lane < NW ? S.ri[par][lane][1] : 0);
+  par ^= 1;
+}
+template <int NW>
+__device__ __forceinline__ long long blk_sum_ll(BpShared& S, int& par, long long a) {
+  a = bp_wsum_ll(a);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) S.rl[par][w] = a;
+  __syncthreads();
+  a = bp_wsum_ll(lane < NW ? S.rl[par][lane] : 0ll);
+  par ^= 1;
+  return a;
+}
+
+#ifndef BP_MIN_CTAS
+#define BP_MIN_CTAS 3
+#endif
+
+template <int A, int TPB>
+__global__ void __launch_bounds__(TPB, BP_MIN_CTAS) binpack_kernel(DevObjects o, DynTables d, BpParams p) {
+  constexpr int NW = TPB / 32;
+  constexpr int A1 = A > 0 ? A : 1;
+  extern __shared__ __align__(16) unsigned char bp_dsm[];
+  __shared__ BpShared S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = p.N, NT = p.N + p.T;
+  const int Neff = p.has_dyn ? N : 0;   // cluster nodes carry run state only when a placement can reach them
+  const int win = p.win;
+  const int Xg = Neff + (win ? 0 : p.cap);
+  // ---- shared window: the nodes this estimate adds ----
+  int64_t* s_free = reinterpret_cast<int64_t*>(bp_dsm);                                        // [A1][win]
+  unsigned long long* s_ports = reinterpret_cast<unsigned long long*>(s_free + (size_t)A1 * win);  // [win]
+  int32_t* s_slots = reinterpret_cast<int32_t*>(s_ports + win);                                // [win]
+  int32_t* s_kc = s_slots + win;                                                               // [win] capacity for the current group
+  int32_t* s_pre = s_kc + win;                                                                 // [win] ordered prefix (final-lap ranks)
+  uint8_t* s_sched = reinterpret_cast<uint8_t*>(s_pre + win);                                  // [win] node holds a scheduled pod
+  // ---- global slab: cluster nodes (and the added nodes when they do not fit the window) ----
+  unsigned char* slab = p.scratch + (size_t)blockIdx.x * p.scratch_per_cta;
+  int32_t* hdr = reinterpret_cast<int32_t*>(slab);   // version counter survives across launches
+  int64_t* g_free = reinterpret_cast<int64_t*>(slab + 16);                                     // [A1][Xg]
+  unsigned long long* g_ports = reinterpret_cast<unsigned long long*>(g_free + (size_t)A1 * Xg);
+  int32_t* g_slots = reinterpret_cast<int32_t*>(g_ports + Xg);
+  int32_t* g_kc = g_slots + Xg;
+  int32_t* g_pre = g_kc + Xg;
+  int32_t* wcnt = g_pre + Xg;                                                                  // [DYN_MAX_Q][dstride]
+  int32_t* wpres = wcnt + (size_t)DYN_MAX_Q * p.dstride;
+  int32_t* wver = wpres + (size_t)DYN_MAX_Q * p.dstride;                                       // slot version
+  int32_t* logbuf = wver + (size_t)DYN_MAX_Q * p.dstride;                                      // [log_cap][3]
+  uint8_t* g_sched = reinterpret_cast<uint8_t*>(logbuf + (size_t)p.log_cap * 3);               // [Xg]
+
+  auto fr = [&](int a, int x) -> int64_t& { return (win && x >= Neff) ? s_free[a * win + (x - Neff)] : g_free[(size_t)a * Xg + x]; };
+  auto po = [&](int x) -> unsigned long long& { return (win && x >= Neff) ? s_ports[x - Neff] : g_ports[x]; };
+  auto sl_ = [&](int x) -> int32_t& { return (win && x >= Neff) ? s_slots[x - Neff] : g_slots[x]; };
+  auto kc = [&](int x) -> int32_t& { return (win && x >= Neff) ? s_kc[x - Neff] : g_kc[x]; };
+  auto pr = [&](int x) -> int32_t& { return (win && x >= Neff) ? s_pre[x - Neff] : g_pre[x]; };
+  auto sch = [&](int x) -> uint8_t& { return (win && x >= Neff) ? s_sched[x - Neff] : g_sched[x]; };
+
+  GroupDyn& wd = S.wd;
+  int par = 0;                 // block-uniform parity of the reduction scratch
+  int gver_ctr = hdr[1] + 1;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) {
+      const int i = atomicAdd(p.work_counter, 1);
+      S.t = i >= p.t_end - p.t_begin ? p.t_end : (p.perm ? p.perm[i] : p.t_begin + i);
+      S.log_n = 0; S.overflow = 0;
+    }
+    __syncthreads();
+    const int t = S.t;
+    if (t >= p.t_end) break;
+
+    int64_t tfree[A1];
+#pragma unroll
+    for (int a = 0; a < A; ++a) tfree[a] = p.tmpl_free[(size_t)a * p.T + t];
+    const int tslots = p.tmpl_slots[t];
+    const int max_nodes = p.max_nodes ? p.max_nodes[t] : 0;
+    const int col_new = N + p.T + t;  // universe column of the sanitized template
+    int n_new = 0, nodes_with_pods = 0, pods_total = 0, last_index = 0;
+    bool new_nodes_available = true, cl_init = false;
+    const int n_groups = p.order_n[t];
+
+    auto log_append = [&](int x, int spec, int cnt) {  // any thread
+      const int idx = atomicAdd(&S.log_n, 1);
+      if (idx < p.log_cap) { logbuf[idx * 3] = x; logbuf[idx * 3 + 1] = spec; logbuf[idx * 3 + 2] = cnt; }
+      else S.overflow = 1;
+    };
+
+    // Identical pods dealt round-robin over `cnt` nodes (node i of the range has capacity capfn(i), cyclic
+    // scan order starts at node s): closed form of repeated SchedulePodOnAnyNodeMatching calls.
+    // applyfn(i, m) books m pods on node i and returns 1 when the node held no scheduled pod before.
+    // Returns pods placed, nodes newly holding pods, cyclic distance from s of the node that took the LAST pod.
+    auto round_robin = [&](int cnt, int s, int npods, auto capfn, auto kcref, auto preref, auto applyfn,
+                           int& got, int& newly, int& last_dist) {
+      got = 0; newly = 0; last_dist = -1;
+      for (int i = tid; i <= BP_HIST; i += TPB) S.hist[i] = 0;
+      __syncthreads();
+      long long total = 0;
+      int kmax = 0;
+      for (int base = 0; base < cnt; base += TPB) {
+        const int i = base + tid;
+        int k = 0;
+        if (i < cnt) { k = capfn(i); kcref(i) = k; total += k; kmax = max(kmax, k); }
+        // histogram of the capacities: lanes with the same value elect one writer
+        const bool cntd = k > 0 && k <= BP_HIST;
+        const unsigned peers = __match_any_sync(0xffffffffu, cntd ? k : 0);
+        if (cntd && lane == __ffs(peers) - 1) atomicAdd(&S.hist[k], __popc(peers));
+      }
+      blk_sum_ll_max<NW>(S, par, total, kmax);
+      if (total <= 0) return;
+      int L, rem;
+      if (total <= npods) { L = kmax; rem = 0; }
+      else if (kmax <= BP_HIST) {
+        // f(L) = sum_j min(k_j, L) = sum_{l <= L} G(l), G(l) = #{k_j >= l}: two warp scans over the histogram
+        if (warp == 0) {
+          constexpr int PB = BP_HIST / 32;
+          int c[PB], G[PB];
+          int lane_tot = 0;
+#pragma unroll
+          for (int i = 0; i < PB; ++i) { c[i] = S.hist[lane * PB + i + 1]; lane_tot += c[i]; }
+          int suf = lane_tot;   // inclusive suffix sum over lanes
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_down_sync(0xffffffffu, suf, off);
+            if (lane + off < 32) suf += v;
+          }
+          int run = suf - lane_tot, gsum = 0;   // counts of the lanes above
+#pragma unroll
+          for (int i = PB - 1; i >= 0; --i) { run += c[i]; G[i] = run; gsum += run; }
+          int pre = gsum;       // inclusive prefix sum over lanes
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, pre, off);
+            if (lane >= off) pre += v;
+          }
+          int f = pre - gsum, cn = 0, fbest = 0;
+#pragma unroll
+          for (int i = 0; i < PB; ++i) {
+            f += G[i];          // f(lane * PB + i + 1)
+            if (f <= npods) { ++cn; fbest = f; }
+          }
+          cn = bp_wsum(cn);     // f is strictly increasing up to kmax and f(kmax) = total > npods
+          fbest = bp_wmax(fbest);
+          if (lane == 0) { S.L = cn; S.rem = npods - fbest; }
+        }
+        __syncthreads();
+        L = S.L; rem = S.rem;
+      } else {
+        int lo = 0, hi = kmax;  // f(lo) <= npods < f(hi)
+        long long flo = 0;
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          long long f = 0;
+          for (int i = tid; i < cnt; i += TPB) f += min(kcref(i), mid);
+          f = blk_sum_ll<NW>(S, par, f);
+          if (f <= npods) { lo = mid; flo = f; } else hi = mid;
+        }
+        L = lo;
+        rem = (int)(npods - flo);
+      }
+      // final lap: the first `rem` nodes in cyclic order from s with k > L take one more
+      int pre_s = 0, tot_extra = 0;
+      if (rem > 0) {
+        int basecnt = 0;
+        for (int base = 0; base < cnt; base += TPB) {
+          const int i = base + tid;
+          const bool ex = i < cnt && kcref(i) > L;
+          const unsigned m = __ballot_sync(0xffffffffu, ex);
+          if (lane == 0) S.ri[par][warp][0] = __popc(m);
+          __syncthreads();
+          const int v = lane < NW ? S.ri[par][lane][0] : 0;
+          int inc = v;          // inclusive scan over the warps' counts
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc += u;
+          }
+          const int wpre = __shfl_sync(0xffffffffu, inc - v, warp);
+          const int all = __shfl_sync(0xffffffffu, inc, 31);
+          if (i < cnt) {
+            const int pj = basecnt + wpre + __popc(m & ((1u << lane) - 1));
+            preref(i) = pj;
+            if (i == s) S.pre_s = pj;
+          }
+          basecnt += all;
+          par ^= 1;
+        }
+        __syncthreads();
+        pre_s = S.pre_s;
+        tot_extra = basecnt;
+      }
+      for (int i = tid; i < cnt; i += TPB) {
+        const int k = kcref(i);
+        if (k <= 0) continue;
+        bool extra = false;
+        if (rem > 0 && k > L) {
+          int rank = preref(i) - pre_s;
+          if (i < s) rank += tot_extra;
+          extra = rank < rem;
+        }
+        const int mj = min(k, L) + (extra ? 1 : 0);
+        if (mj > 0) {
+          newly += applyfn(i, mj);
+          got += mj;
+          // the pod placed last sits at the furthest position served in the final lap
+          if (rem > 0 ? extra : (k >= L)) { int dd = i - s; if (dd < 0) dd += cnt; last_dist = max(last_dist, dd); }
+        }
+      }
+      blk_sum_sum_max<NW>(S, par, got, newly, last_dist);
+    };
+
+    for (int gi = 0; gi < n_groups; ++gi) {
+      const int g = p.order[(size_t)t * p.E + gi];
+      const int pb = o.group_off[g];
+      int n = o.group_off[g + 1] - pb;
+      const int spec = o.pend_spec[pb];
+      int64_t req[A1];
+#pragma unroll
+      for (int a = 0; a < A; ++a) req[a] = o.ps_req[(size_t)spec * R + p.act_dim[a]];
+      const int sc = p.spec_sc[spec];
+      const int dc = p.has_dyn ? p.spec_dc[spec] : 0;
+      const bool static_new = (p.pre_code[(size_t)sc * p.U + col_new] & 0x0F) == 0;
+      const int plist = o.ps_port_list[spec];
+      const bool has_ports = o.port_off[plist + 1] > o.port_off[plist];
+      const unsigned long long pconf = has_ports ? p.port_conf[plist] : 0ull;  // port sets this pod collides with
+      const unsigned long long pbit = has_ports ? (1ull << p.pc_of[plist]) : 0ull;
+      const bool feeds = p.has_dyn && d.group_feeds[g];
+      int placed = 0;
+
+      // spare capacity of node x for this pod by NodePorts + NodeResourcesFit alone (pod slots, free resources)
+      auto res_cap = [&](int x, int want) -> int {
+        int k = min(sl_(x), want);
+        if (k > 0 && (po(x) & pconf)) k = 0;
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+          if (req[a] > 0 && k > 0) {
+            const int64_t f = fr(a, x);
+            if (f < req[a]) k = 0;
+            else if (f < (int64_t)k * req[a]) k = (int)(f / req[a]);
+          }
+        }
+        if (has_ports) k = min(k, 1);
+        return k;
+      };
+      // ForceAddPod x m on node x (owner thread); returns 1 when the node held no scheduled pod before
+      auto book = [&](int x, int m) -> int {
+#pragma unroll
+        for (int a = 0; a < A; ++a) if (req[a] > 0) fr(a, x) -= (int64_t)m * req[a];
+        sl_(x) -= m;
+        po(x) |= pbit;
+        int nw = 0;
+        if (!sch(x)) { sch(x) = 1; nw = 1; }
+        if (feeds) log_append(x, spec, m);
+        return nw;
+      };
+      // capacity of a FRESH node by NodePorts + NodeResourcesFit (DaemonSet port conflicts are part of static_new)
+      auto fresh_cap = [&](int want) -> int {
+        int k = 0;
+        if (static_new) {
+          k = min(tslots, want);
+#pragma unroll
+          for (int a = 0; a < A; ++a) {
+            if (req[a] > 0 && k > 0) {
+              if (tfree[a] < req[a]) k = 0;
+              else if (tfree[a] < (int64_t)k * req[a]) k = (int)(tfree[a] / req[a]);
+            }
+          }
+          if (has_ports) k = min(k, 1);
+        }
+        return k;
+      };
+      // tryToScheduleOnNewNodes in closed form: every new node takes min(remaining, k_new) pods (k_new <= 0: the node
+      // is added, the pod still fails on it, :235-240).  `one`: add a single node only (permission is asked once).
+      auto add_new_nodes = [&](int k_new, bool one) {
+        long long allowed = max_nodes < 0 ? 0 : (max_nodes == 0 ? (long long)INT_MAX : max((long long)max_nodes - n_new, 0ll));
+        if (allowed > p.cap - n_new) allowed = p.cap - n_new;
+        int add, fill = 0;
+        if (k_new <= 0 || one) {
+          add = allowed >= 1 ? 1 : 0;
+          if (allowed < 1) new_nodes_available = false;   // PermissionToAddNode denied (:222)
+          if (k_new > 0) fill = min(n, add * k_new);
+        } else {
+          const long long need = ((long long)n + k_new - 1) / k_new;
+          if (need > allowed) { add = (int)allowed; new_nodes_available = false; }
+          else add = (int)need;
+          fill = (int)min((long long)n, (long long)add * k_new);
+        }
+        for (int i = tid; i < add; i += TPB) {
+          const int x = Neff + n_new + i;
+          const int mj = k_new <= 0 ? 0 : min(k_new, fill - i * k_new);
+#pragma unroll
+          for (int a = 0; a < A; ++a) fr(a, x) = tfree[a] - (req[a] > 0 ? (int64_t)mj * req[a] : 0);
+          sl_(x) = tslots - mj;
+          po(x) = mj > 0 ? pbit : 0ull;
+          sch(x) = mj > 0;
+          if (feeds && mj > 0) log_append(x, spec, mj);
+        }
+        if (k_new > 0) { nodes_with_pods += add; placed += fill; n -= fill; }
+        n_new += add;
+        __syncthreads();
+      };
+
+      if (dc == 0) {
+        // ======================= plain group: closed form =======================================
+        if (n_new > 0 && static_new) {
+          const int s = last_index >= N ? last_index - N : 0;  // first added node in cyclic scan order
+          int got, newly, last_dist;
+          round_robin(n_new, s, n,
+                      [&](int i) { return res_cap(Neff + i, n); },
+                      [&](int i) -> int32_t& { return kc(Neff + i); },
+                      [&](int i) -> int32_t& { return pr(Neff + i); },
+                      [&](int i, int m) { return book(Neff + i, m); }, got, newly, last_dist);
+          placed += got;
+          nodes_with_pods += newly;
+          n -= got;
+          if (last_dist >= 0) {
+            int jl = s + last_dist;
+            if (jl >= n_new) jl -= n_new;
+            last_index = (N + jl + 1) % (N + n_new);
+          }
+          __syncthreads();
+        }
+        if (n > 0 && new_nodes_available) {
+          // after the pass above no added node (the last one included) can take this pod any more
+          const bool stop = (n_new > 0) && !sch(Neff + n_new - 1);  // last node still empty (:212)
+          if (!stop) add_new_nodes(fresh_cap(n), false);
+        }
+      } else {
+        // ======================= dynamic group ===================================================
+        const bool host_spread = o.ps_hostname_spread[spec] != 0;
+        const int gver = ++gver_ctr;      // version of this group's working counters (lazy copy-on-write)
+        // ---- describe the group's counters ----
+        __syncthreads();
+        if (tid == 0) {
+          int nq = 0;
+          for (int q = d.dc_q_off[dc]; q < d.dc_q_off[dc + 1]; ++q) {
+            if (!d.q_active[q]) continue;
+            const int k = d.q_k[q], kind = d.q_kind[q];
+            wd.qid[nq] = q; wd.kind[nq] = kind; wd.k[nq] = k; wd.host[nq] = d.is_host[k]; wd.Dc[nq] = d.Dc[k];
+            const int td = d.dom[(size_t)k * NT + N + t];
+            wd.tslot[nq] = td < 0 ? -1 : (td < d.Dc[k] ? td : d.Dc[k]);
+            wd.wown[nq] = d.q_wown[q]; wd.self[nq] = d.q_self[q];
+            wd.maxskew[nq] = kind == Q_PTS ? o.pts_max_skew[d.q_p0[q]] : 0;
+            wd.mindom[nq] = kind == Q_PTS ? o.pts_min_domains[d.q_p0[q]] : 0;
+            wd.elig_new[nq] = d.elig[(size_t)q * p.U + col_new];
+            wd.dsw[nq] = d.ds_w[(size_t)q * p.T + t];
+            wd.tot[nq] = d.base_tot[q];
+            wd.boff[nq] = d.q_base_off[q];
+            wd.minv[nq] = d.st_min1[q]; wd.nmin[nq] = d.st_nmin[q]; wd.ndom[nq] = d.st_ndom[q];
+            S.flag[nq] = 0;
+            ++nq;
+          }
+          wd.nq = nq;
+          wd.aff_self = d.dc_aff_self[dc];
+          S.need_log = 0;
+        }
+        __syncthreads();
+        const int nq = wd.nq;
+        auto slot_of = [&](int q, int x) -> int {
+          if (x < Neff) return d.dom[(size_t)wd.k[q] * NT + x];
+          if (wd.host[q]) return wd.Dc[q] + 1 + (x - Neff);
+          return wd.tslot[q];
+        };
+        auto elig_of = [&](int q, int x) -> bool {
+          return x < Neff ? d.elig[(size_t)wd.qid[q] * p.U + x] != 0 : wd.elig_new[q] != 0;
+        };
+        // Working counters are copy-on-write over the cluster base counts: a slot is valid only when its
+        // version equals this group's, otherwise it reads as its default (base count for cluster domains,
+        // DaemonSet weight for the fresh hostname domain of an added node, 0 for a template-only value).
+        auto def_cnt = [&](int q, int sl) -> int {
+          const int Dc = wd.Dc[q];
+          return sl < Dc ? d.base_cnt[wd.boff[q] + sl] : (sl == Dc ? 0 : (wd.elig_new[q] ? wd.dsw[q] : 0));
+        };
+        auto def_pres = [&](int q, int sl) -> int {
+          const int Dc = wd.Dc[q];
+          return sl < Dc ? d.base_pres[wd.boff[q] + sl] : (sl == Dc ? 0 : (wd.elig_new[q] ? 1 : 0));
+        };
+        auto rd_cnt = [&](int q, int sl) -> int {
+          const size_t o2 = (size_t)q * p.dstride + sl;
+          if (wver[o2] == gver) return wcnt[o2];
+          return def_cnt(q, sl);
+        };
+        auto rd_pres = [&](int q, int sl) -> int {
+          const size_t o2 = (size_t)q * p.dstride + sl;
+          if (wver[o2] == gver) return wpres[o2];
+          return def_pres(q, sl);
+        };
+        auto wr = [&](int q, int sl, int c, int prs) {  // single thread
+          const size_t o2 = (size_t)q * p.dstride + sl;
+          wcnt[o2] = c; wpres[o2] = prs; wver[o2] = gver;
+        };
+        // min / #domains over the present domains of a spread counter (block-wide; ends with a barrier)
+        auto recompute = [&](int q) {
+          const int len = wd.Dc[q] + 1 + (wd.host[q] ? n_new : 0);
+          int mn = INT_MAX, nd = 0;
+          for (int i = tid; i < len; i += TPB) if (rd_pres(q, i) > 0) { mn = min(mn, rd_cnt(q, i)); ++nd; }
+          blk_min_sum<NW>(S, par, mn, nd);
+          int nm = 0, zero = 0;
+          for (int i = tid; i < len; i += TPB) if (rd_pres(q, i) > 0 && rd_cnt(q, i) == mn) ++nm;
+          blk_min_sum<NW>(S, par, zero, nm);
+          if (tid == 0) { wd.minv[q] = mn; wd.nmin[q] = nm; wd.ndom[q] = nd; S.flag[q] = 0; }
+          __syncthreads();
+        };
+        auto run_flagged = [&]() {   // after a barrier: recompute the counters thread 0 flagged
+          for (int q = 0; q < nq; ++q) if (S.flag[q]) recompute(q);
+        };
+        // ---- seed: nodes added so far (O(1) per counter) ----
+        if (tid == 0) {
+          int need_log = 0;
+          for (int q = 0; q < nq; ++q) {
+            if (wd.elig_new[q] && n_new > 0) {
+              const int dsw = wd.dsw[q];
+              if (wd.host[q]) {  // n_new fresh hostname domains, each holding the DaemonSet weight
+                wd.tot[q] += n_new * dsw;
+                if (wd.kind[q] == Q_PTS) {
+                  wd.ndom[q] += n_new;
+                  if (dsw < wd.minv[q]) { wd.minv[q] = dsw; wd.nmin[q] = n_new; }
+                  else if (dsw == wd.minv[q]) wd.nmin[q] += n_new;
+                }
+              } else if (wd.tslot[q] >= 0) {  // all added nodes share the template's value of this key
+                const int sl = wd.tslot[q];
+                const int c0 = rd_cnt(q, sl), p0 = rd_pres(q, sl), c1 = c0 + n_new * dsw;
+                wr(q, sl, c1, p0 + n_new);
+                wd.tot[q] += n_new * dsw;
+                if (wd.kind[q] == Q_PTS && p0 == 0) {
+                  wd.ndom[q] += 1;
+                  if (c1 < wd.minv[q]) { wd.minv[q] = c1; wd.nmin[q] = 1; }
+                  else if (c1 == wd.minv[q]) wd.nmin[q] += 1;
+                }
+                if (wd.kind[q] == Q_PTS && p0 > 0 && dsw > 0) S.flag[q] = 1;
+              }
+            }
+            if (d.q_nfeed[wd.qid[q]] - (wd.wown[q] > 0 ? 1 : 0) > 0) need_log = 1;
+          }
+          S.need_log = need_log;
+        }
+        __syncthreads();
+        run_flagged();
+        const bool need_log = S.need_log != 0;
+        // ---- then the run's placement log if other groups feed us ----
+        if (need_log && S.log_n > 0) {
+          const int nlog = min(S.log_n, p.log_cap);
+          for (int q = 0; q < nq; ++q) {
+            const int qid = wd.qid[q];
+            // Pass 1 materialises the touched copy-on-write slots with their defaults (identical values from
+            // every thread), pass 2 stamps the version and adds the weights atomically.
+            int touched = 0;
+            long long dt = 0;
+            for (int i = tid; i < nlog; i += TPB) {
+              const int x = logbuf[i * 3];
+              const int w = d.wmat[(size_t)qid * d.S + logbuf[i * 3 + 1]];
+              if (w == 0 || !elig_of(q, x)) continue;
+              const int sl = slot_of(q, x);
+              if (sl < 0) continue;
+              const size_t o2 = (size_t)q * p.dstride + sl;
+              if (wver[o2] != gver) { wcnt[o2] = def_cnt(q, sl); wpres[o2] = def_pres(q, sl); }
+              touched = 1;
+              dt += w * logbuf[i * 3 + 2];
+            }
+            __syncthreads();
+            for (int i = tid; i < nlog; i += TPB) {
+              const int x = logbuf[i * 3];
+              const int w = d.wmat[(size_t)qid * d.S + logbuf[i * 3 + 1]];
+              if (w == 0 || !elig_of(q, x)) continue;
+              const int sl = slot_of(q, x);
+              if (sl < 0) continue;
+              const size_t o2 = (size_t)q * p.dstride + sl;
+              wver[o2] = gver;
+              atomicAdd(&wcnt[o2], w * logbuf[i * 3 + 2]);
+            }
+            blk_sum_ll_max<NW>(S, par, dt, touched);
+            if (tid == 0) wd.tot[q] += (int)dt;
+            __syncthreads();
+            if (touched > 0 && wd.kind[q] == Q_PTS) recompute(q);
+          }
+        }
+
+        auto ensure_cluster = [&]() {  // run state of the cluster nodes, needed once a fallback can place onto them
+          if (cl_init) return;
+          for (int x = tid; x < N; x += TPB) {
+#pragma unroll
+            for (int a = 0; a < A; ++a) g_free[(size_t)a * Xg + x] = p.c_free[(size_t)a * N + x];
+            g_slots[x] = p.c_slots[x];
+            g_ports[x] = 0ull;
+            g_sched[x] = 0;
+          }
+          cl_init = true;
+          __syncthreads();
+        };
+
+        // ---- hostname spread with the global minimum pinned at 0: closed form ----
+        bool fast = false;
+        if (nq == 1 && wd.kind[0] == Q_PTS && wd.host[0] && !need_log && wd.minv[0] == 0) {
+          const int w0 = wd.wown[0], self0 = wd.self[0], ms0 = wd.maxskew[0], boff0 = wd.boff[0], k0 = wd.k[0], qid0 = wd.qid[0];
+          // skew capacity of a node whose domain holds c matching pods and counts placements iff `counted`
+          auto skew_cap = [&](int c, bool counted) -> int {
+            if (c + self0 > ms0) return 0;                       // filtering.go:352 with minMatchNum = 0
+            if (!counted || w0 == 0) return INT_MAX;
+            return (ms0 - self0 - c) / w0 + 1;
+          };
+          bool caps_done = false;
+          // capacities of the cluster nodes for this pod (static filters, ports, resources, skew) -> kc[x];
+          // returns "a present empty domain exists whose only eligible node can never take this pod"
+          auto cluster_caps = [&]() -> bool {
+            ensure_cluster();
+            int blocked = 0;
+            for (int x = tid; x < N; x += TPB) {
+              int k = 0;
+              const bool stat_ok = (p.pre_code[(size_t)sc * p.U + x] & 0x0F) == 0 && !o.node_unschedulable[x];
+              const int rc = stat_ok ? res_cap(x, n) : 0;
+              const int dm = d.dom[(size_t)k0 * NT + x];
+              const bool el = d.elig[(size_t)qid0 * p.U + x] != 0;
+              if (dm >= 0) {
+                const int c = d.base_cnt[boff0 + dm];
+                if (rc > 0) k = min(rc, skew_cap(c, el));
+                if (el && c == 0 && rc == 0 && d.base_pres[boff0 + dm] == 1) blocked = 1;
+              }
+              g_kc[x] = k;
+            }
+            long long z = 0;
+            blk_sum_ll_max<NW>(S, par, z, blocked);
+            caps_done = true;
+            return blocked > 0;
+          };
+          if (w0 == 0 || wd.nmin[0] > n) fast = true;
+          else if (N > 0) fast = cluster_caps();
+          if (fast) {
+            const int c_new = wd.elig_new[0] ? wd.dsw[0] : 0;
+            const int S_new = skew_cap(c_new, wd.elig_new[0] != 0);
+            int m_last = 0;   // pods of this group on the last added node
+            // ---- tryToScheduleOnExistingNodes ----
+            if (n_new > 0 && static_new && S_new > 0) {
+              if (tid == 0) S.mlast = 0;
+              const int s = last_index >= N ? last_index - N : 0;
+              const int lastj = n_new - 1;
+              int got, newly, last_dist;
+              round_robin(n_new, s, n,
+                          [&](int i) { return min(res_cap(Neff + i, n), S_new); },
+                          [&](int i) -> int32_t& { return kc(Neff + i); },
+                          [&](int i) -> int32_t& { return pr(Neff + i); },
+                          [&](int i, int m) { if (i == lastj) S.mlast = m; return book(Neff + i, m); }, got, newly, last_dist);
+              placed += got;
+              nodes_with_pods += newly;
+              n -= got;
+              if (last_dist >= 0) {
+                int jl = s + last_dist;
+                if (jl >= n_new) jl -= n_new;
+                last_index = (N + jl + 1) % (N + n_new);
+              }
+              __syncthreads();
+              m_last = S.mlast;
+            }
+            // the pods the last node refuses for skew go to the cluster nodes in cyclic order (:186-205)
+            auto cluster_phase = [&]() {
+              if (N == 0) return;
+              if (!caps_done) cluster_caps();
+              const int s = last_index < N ? last_index : 0;
+              int got, newly, last_dist;
+              round_robin(N, s, n,
+                          [&](int i) { return g_kc[i]; },
+                          [&](int i) -> int32_t& { return g_kc[i]; },
+                          [&](int i) -> int32_t& { return g_pre[i]; },
+                          [&](int i, int m) { return book(i, m); }, got, newly, last_dist);
+              placed += got;
+              nodes_with_pods += newly;
+              n -= got;
+              if (last_dist >= 0) {
+                int jl = s + last_dist;
+                if (jl >= N) jl -= N;
+                last_index = jl + 1;   // < N + n_new: the list holds at least one added node here
+              }
+              __syncthreads();
+            };
+            // ---- tryToScheduleOnNewNodes ----
+            if (n > 0 && new_nodes_available) {
+              bool cluster_done = false;
+              if (n_new > 0) {
+                // why the last node refuses the next pod (default plugin order): static, ports, fit, then skew
+                const int xl = Neff + n_new - 1;
+                bool skew = static_new && !(po(xl) & pconf) && sl_(xl) >= 1;
+#pragma unroll
+                for (int a = 0; a < A; ++a) skew = skew && !(req[a] > 0 && req[a] > fr(a, xl));
+                skew = skew && (c_new + (wd.elig_new[0] ? m_last * w0 : 0) + self0 > ms0);
+                if (skew && host_spread) { cluster_phase(); cluster_done = true; }
+              }
+              if (n > 0) {
+                const bool stop = (n_new > 0) && !sch(Neff + n_new - 1);  // last node still empty (:212)
+                if (!stop) {
+                  const int k_res = fresh_cap(n);
+                  const int k_new = min(k_res, S_new);
+                  // a full fresh node refuses the next pod for skew iff the skew capacity binds before ports / fit
+                  const bool fresh_skew = k_new > 0 && S_new < fresh_cap(INT_MAX);
+                  if (k_new > 0 && fresh_skew && host_spread && !cluster_done) {
+                    add_new_nodes(k_new, true);        // the first fresh node fills ...
+                    if (n > 0 && new_nodes_available) {
+                      cluster_phase();                 // ... then the fallback drains the cluster nodes ...
+                      if (n > 0) add_new_nodes(k_new, false);   // ... and further nodes take the rest
+                    }
+                  } else add_new_nodes(k_new, false);
+                }
+              }
+            }
+          }
+        }
+        if (!fast) {
+        // ======================= per-pod loop on incremental counters =============================
+        // RunFilterPlugins on node x (default plugin order), per thread
+        auto eval = [&](int x) -> int {
+          const int col = x < Neff ? x : col_new;
+          const int code = p.pre_code[(size_t)sc * p.U + col] & 0x0F;
+          if (code) return code;
+          if (po(x) & pconf) return CAE_R_NODE_PORTS;
+          bool fail = sl_(x) < 1;
+#pragma unroll
+          for (int a = 0; a < A; ++a) fail |= (req[a] > 0 && req[a] > fr(a, x));
+          if (fail) return CAE_R_FIT;
+          bool aff_any = false, pods_exist = true;
+          long long aff_tot = 0;
+          for (int q = 0; q < nq; ++q) {
+            const int kind = wd.kind[q];
+            const int sl = slot_of(q, x);
+            const int c = sl >= 0 ? rd_cnt(q, sl) : 0;
+            if (kind == Q_PTS) {  // podtopologyspread/filtering.go:314-359
+              if (sl < 0) return CAE_R_PTS_MISSING_LABEL;
+              const long long minm = wd.ndom[q] < wd.mindom[q] ? 0 : wd.minv[q];
+              if ((long long)c + wd.self[q] - minm > wd.maxskew[q]) return CAE_R_PTS_SKEW;
+            } else if (kind == Q_AFF) {  // interpodaffinity/filtering.go:382-408
+              aff_any = true;
+              if (sl < 0) return CAE_R_IPA_AFFINITY;
+              if (c <= 0) pods_exist = false;
+              aff_tot += wd.tot[q];
+            } else {
+              if (aff_any) {
+                if (!pods_exist && !(aff_tot == 0 && wd.aff_self)) return CAE_R_IPA_AFFINITY;
+                aff_any = false;
+              }
+              if (sl >= 0 && c > 0) return kind == Q_ANTI ? CAE_R_IPA_ANTI_AFFINITY : CAE_R_IPA_EXISTING_ANTI_AFFINITY;
+            }
+          }
+          if (aff_any && !pods_exist && !(aff_tot == 0 && wd.aff_self)) return CAE_R_IPA_AFFINITY;
+          return CAE_R_OK;
+        };
+        // ForceAddPod on node x (uniform x) + counter upkeep
+        auto place = [&](int x) {
+          __syncthreads();   // every thread has finished evaluating against the old state
+          if (tid == 0) {
+            S.newly = !sch(x);
+#pragma unroll
+            for (int a = 0; a < A; ++a) if (req[a] > 0) fr(a, x) -= req[a];
+            sl_(x) -= 1;
+            po(x) |= pbit;
+            sch(x) = 1;
+            for (int q = 0; q < nq; ++q) {
+              const int w = wd.wown[q];
+              if (w == 0 || !elig_of(q, x)) continue;
+              const int sl = slot_of(q, x);
+              if (sl < 0) continue;
+              const int old = rd_cnt(q, sl), prs = rd_pres(q, sl);
+              wr(q, sl, old + w, prs);
+              wd.tot[q] += w;
+              if (wd.kind[q] == Q_PTS && old == wd.minv[q]) {
+                if (--wd.nmin[q] == 0) S.flag[q] = 1;
+              }
+            }
+            if (feeds) log_append(x, spec, 1);
+          }
+          __syncthreads();
+          if (S.newly) ++nodes_with_pods;
+          run_flagged();
+          ++placed;
+          --n;
+        };
+        // addNewNodeToSnapshot (:249-265): a sanitized copy of the template joins the list
+        auto add_node = [&]() {
+          const int x = Neff + n_new;
+          __syncthreads();
+          if (tid == 0) {
+#pragma unroll
+            for (int a = 0; a < A; ++a) fr(a, x) = tfree[a];
+            sl_(x) = tslots;
+            po(x) = 0ull;
+            sch(x) = 0;
+            for (int q = 0; q < nq; ++q) {
+              const int en = wd.elig_new[q], dsw = wd.dsw[q];
+              const int sl = slot_of(q, x);
+              const bool pts = wd.kind[q] == Q_PTS;
+              if (wd.host[q]) {  // a brand-new hostname domain (its default already reads dsw / present)
+                if (en) {
+                  wd.tot[q] += dsw;
+                  if (pts) {
+                    wd.ndom[q] += 1;
+                    if (dsw < wd.minv[q]) { wd.minv[q] = dsw; wd.nmin[q] = 1; }
+                    else if (dsw == wd.minv[q]) wd.nmin[q] += 1;
+                  }
+                }
+              } else if (en && sl >= 0) {
+                const int c0 = rd_cnt(q, sl), p0 = rd_pres(q, sl);
+                wr(q, sl, c0 + dsw, p0 + 1);
+                wd.tot[q] += dsw;
+                if (pts && p0 == 0) {
+                  wd.ndom[q] += 1;
+                  if (c0 + dsw < wd.minv[q]) { wd.minv[q] = c0 + dsw; wd.nmin[q] = 1; }
+                  else if (c0 + dsw == wd.minv[q]) wd.nmin[q] += 1;
+                }
+                if (pts && p0 > 0 && dsw > 0) S.flag[q] = 1;
+              }
+            }
+          }
+          n_new += 1;       // recompute() below must see the new node's hostname domain
+          __syncthreads();
+          run_flagged();
+        };
+
+        // ---- tryToScheduleOnExistingNodes: per pod, first passing added node in cyclic order ----
+        while (n > 0 && n_new > 0) {
+          const int s = last_index >= N ? last_index - N : 0;
+          int best = INT_MAX, zero = 0;
+          for (int j = tid; j < n_new; j += TPB)
+            if (eval(Neff + j) == CAE_R_OK) { int dd = j - s; if (dd < 0) dd += n_new; best = min(best, dd); }
+          blk_min_sum<NW>(S, par, best, zero);
+          if (best == INT_MAX) break;  // first pod that fits nowhere ends this phase for the group (:158)
+          int found = s + best;
+          if (found >= n_new) found -= n_new;
+          place(Neff + found);
+          last_index = (N + found + 1) % (N + n_new);
+        }
+        // ---- tryToScheduleOnNewNodes ----
+        while (n > 0 && new_nodes_available) {
+          bool found = false;
+          if (n_new > 0) {
+            const int xl = Neff + n_new - 1;
+            const int r = eval(xl);
+            if (r == CAE_R_OK) { place(xl); found = true; }
+            else if (host_spread && r == CAE_R_PTS_SKEW) {
+              // SchedulePodOnAnyNodeMatching(name != lastNodeName) (:190-205): whole list, cyclic from lastIndex
+              ensure_cluster();
+              const int len = N + n_new, lastpos = N + n_new - 1;
+              int best = INT_MAX, zero = 0;
+              for (int idx = tid; idx < len; idx += TPB) {
+                if (idx == lastpos) continue;
+                if (idx < N && o.node_unschedulable[idx]) continue;   // plugin_runner.go:92-94
+                const int x = idx < N ? idx : Neff + (idx - N);
+                if (eval(x) == CAE_R_OK) { int dd = idx - last_index; if (dd < 0) dd += len; best = min(best, dd); }
+              }
+              blk_min_sum<NW>(S, par, best, zero);
+              if (best != INT_MAX) {
+                int hit = last_index + best;
+                if (hit >= len) hit -= len;
+                place(hit < N ? hit : Neff + (hit - N));
+                last_index = (hit + 1) % len;
+                found = true;
+              }
+            }
+          }
+          if (!found) {
+            if (n_new > 0 && !sch(Neff + n_new - 1)) break;  // last node still empty (:212)
+            const bool permit = !(max_nodes < 0 || (max_nodes > 0 && n_new >= max_nodes)) && n_new < p.cap;
+            if (!permit) { new_nodes_available = false; break; }  // (:222)
+            add_node();
+            if (eval(Neff + n_new - 1) != CAE_R_OK) break;  // (:238-240)
+            place(Neff + n_new - 1);
+          }
+        }
+        }  // !fast
+      }
+      pods_total += placed;
+      if (tid == 0) p.sched[(size_t)t * p.E + g] = placed;
+      __syncthreads();
+    }
+    if (tid == 0) {
+      p.node_count[t] = nodes_with_pods;
+      p.pod_count[t] = pods_total;
+      if (S.overflow && p.status) atomicExch(p.status, 1);
+    }
+  }
+  if (tid == 0) hdr[1] = gver_ctr;
+}
+
+// work order of the estimator blocks: templates by decreasing cost (pods in their schedulable groups), ties by index
+__global__ void lpt_rank_kernel(const long long* __restrict__ cost, int t_begin, int nt, int32_t* __restrict__ perm) {
+  __shared__ long long tile[256];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long mine = i < nt ? cost[t_begin + i] : 0;
+  int rank = 0;
+  for (int base = 0; base < nt; base += 256) {
+    const int j = base + threadIdx.x;
+    tile[threadIdx.x] = j < nt ? cost[t_begin + j] : LLONG_MIN;
+    __syncthreads();
+    const int lim = min(256, nt - base);
+    for (int k = 0; k < lim; ++k) {
+      const long long c = tile[k];
+      rank += (c > mine) || (c == mine && base + k < i);
+    }
+    __syncthreads();
+  }
+  if (i < nt) perm[rank] = t_begin + i;
+}
+
+template <int A>
+static int launch_binpack_a(Engine* e, int blocks_wanted, size_t smem, const BpParams& p, int* blocks_out, bool query_only) {
+  auto kern = binpack_kernel<A, 256>;
+  CAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CAE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+  if (per_sm < 1) { set_error("binpack_kernel does not fit an SM"); return -1; }
+  const int blocks = std::max(1, std::min(blocks_wanted, per_sm * e->sm_count));
+  *blocks_out = blocks;
+  if (query_only) return 0;
+  kern<<<blocks, 256, smem, e->stream>>>(e->dobj, e->dyn, p);
+  return 0;
+}
+
+static int launch_binpack_any(Engine* e, int blocks_wanted, size_t smem, const BpParams& p, int* blocks_out, bool query_only) {
+  switch (e->A) {
+    case 0: return launch_binpack_a<0>(e, blocks_wanted, smem, p, blocks_out, query_only);
+    case 1: return launch_binpack_a<1>(e, blocks_wanted, smem, p, blocks_out, query_only);
+    case 2: return launch_binpack_a<2>(e, blocks_wanted, smem, p, blocks_out, query_only);
+    case 3: return launch_binpack_a<3>(e, blocks_wanted, smem, p, blocks_out, query_only);
+    case 4: return launch_binpack_a<4>(e, blocks_wanted, smem, p, blocks_out, query_only);
+    case 5: return launch_binpack_a<5>(e, blocks_wanted, smem, p, blocks_out, query_only);
+    case 6: return launch_binpack_a<6>(e, blocks_wanted, smem, p, blocks_out, query_only);
+    case 7: return launch_binpack_a<7>(e, blocks_wanted, smem, p, blocks_out, query_only);
+    default: return launch_binpack_a<8>(e, blocks_wanted, smem, p, blocks_out, query_only);
+  }
+}
+
+int launch_binpack(Engine* e) {
+  const int nt = e->t_end - e->t_begin;
+  if (nt <= 0) return 0;
+  BpParams p{};
+  p.E = e->E; p.T = e->T; p.N = e->N; p.U = e->U;
+  p.has_dyn = e->has_dynamic ? 1 : 0;
+  for (int a = 0; a < CAE_MAX_RES; ++a) p.act_dim[a] = e->act_dim[a];
+  p.order = e->d_order; p.order_n = e->d_order_n; p.pre_code = e->d_pre_code; p.spec_sc = e->d_spec_sc; p.spec_dc = e->d_spec_dc;
+  p.tmpl_free = e->d_tmpl_free; p.tmpl_slots = e->d_tmpl_slots; p.max_nodes = e->d_max_nodes;
+  p.pc_of = e->d_pc_of; p.port_conf = e->d_port_conf; p.c_free = e->d_c_free; p.c_slots = e->d_c_slots;
+  p.node_count = e->d_counts2; p.pod_count = e->d_counts2 + e->T; p.sched = e->d_sched;
+  p.work_counter = e->d_work_counter; p.status = e->d_work_counter + 1;
+  p.t_begin = e->t_begin; p.t_end = e->t_end;
+  // node capacity of a simulation: the largest limiter cap, or (unlimited) one node per pod + 1
+  // (every added node but possibly one holds >= 1 pod)
+  const int cap = std::max(1, std::min(e->P + 1, e->pack_cap));
+  p.cap = cap;
+  const int A1 = std::max(e->A, 1);
+  const int Neff = p.has_dyn ? e->N : 0;
+  // shared window for the added nodes: per node A1 x int64 free + ports + slots + capacity + prefix + flag
+  const size_t node_bytes = (size_t)A1 * 8 + 8 + 4 + 4 + 4 + 1;
+  size_t smem = ((size_t)cap * node_bytes + 15) & ~(size_t)15;
+  const size_t smem_limit = (size_t)e->smem_optin > 4096 ? (size_t)e->smem_optin - 4096 : 0;   // static part + reserve
+  if (smem <= smem_limit) p.win = cap; else { p.win = 0; smem = 0; }
+  const size_t Xg = (size_t)Neff + (p.win ? 0 : cap);
+  int dmax = 1;
+  for (int k = 0; k < e->dyn.K; ++k) dmax = std::max(dmax, e->dyn.Dc[k] + 1 + (e->dyn.is_host[k] ? cap : 0));
+  p.dstride = p.has_dyn ? dmax : 1;
+  p.log_cap = p.has_dyn ? (int)std::min<size_t>(4 * ((size_t)Neff + cap) + 1024, (size_t)1 << 24) : 1;
+  size_t per_cta = 16 + Xg * ((size_t)A1 * 8 + 8 + 4 + 4 + 4) + (size_t)3 * DYN_MAX_Q * p.dstride * 4 + (size_t)p.log_cap * 12 + Xg;
+  per_cta = (per_cta + 255) & ~(size_t)255;
+  p.scratch_per_cta = per_cta;
+  int blocks = 0;
+  if (launch_binpack_any(e, nt, smem, p, &blocks, true)) return -1;
+  const size_t budget = (size_t)24 << 30;  // keep the slabs within 24 GiB of the 180 GB HBM
+  if (per_cta * blocks > budget) blocks = (int)std::max<size_t>(1, budget / per_cta);
+  const size_t need = per_cta * blocks;
+  const size_t sig = per_cta * 1000003u + Xg * 10007u + (size_t)p.dstride * 101u + (size_t)p.log_cap * 7u + (size_t)A1 + 0x9000000000ull;
+  if (need > e->pack_scratch_bytes) {
+    if (e->d_pack_scratch) cudaFree(e->d_pack_scratch);
+    e->d_pack_scratch = nullptr;
+    e->pack_scratch_bytes = 0;
+    CAE_CUDA(cudaMalloc(&e->d_pack_scratch, need));
+    e->pack_scratch_bytes = need;
+    e->pack_layout_sig = 0;
+  }
+  if (sig != e->pack_layout_sig) {  // slot versions are only meaningful within one slab layout
+    CAE_CUDA(cudaMemsetAsync(e->d_pack_scratch, 0, need, e->stream));
+    e->pack_layout_sig = sig;
+  }
+  p.scratch = static_cast<unsigned char*>(e->d_pack_scratch);
+  CAE_CUDA(cudaMemsetAsync(e->d_work_counter, 0, sizeof(int32_t) * 2, e->stream));
+  // longest processing time first: the heaviest templates start first, the tail of the pass is made of light ones
+  lpt_rank_kernel<<<(nt + 255) / 256, 256, 0, e->stream>>>(e->d_tmpl_cost, e->t_begin, nt, e->d_perm);
+  e->stats.kernel_launches++;
+  p.perm = e->d_perm;
+  int launched = 0;
+  if (launch_binpack_any(e, blocks, smem, p, &launched, false)) return -1;
+  e->stats.kernel_launches++;
+  CAE_KERNEL_OK();
+  return 0;
+}
+
+}  // namespace cae

@@ -157,6 +157,8 @@ struct Engine {
   std::vector<int64_t> h_cap_cpu, h_cap_mem;  // per template
   int num_podspecs = 0;
   int sm_count = 148;
+  int smem_optin = 227 * 1024;             // opt-in shared memory per thread block
+  bool pack_v1 = false;                   // CAE_PACK_V1=1: the round-1 warp-per-template estimator (A/B measurements only)
 };
 
 // kernels.cu
@@ -169,7 +171,8 @@ int launch_port_conflicts(Engine* e, int num_port_lists);
 int launch_feasibility(Engine* e, bool want_reasons);
 int launch_group_feasibility(Engine* e);
 int launch_order(Engine* e);
-int launch_pack(Engine* e);
+int launch_pack(Engine* e);      // round-1 estimator kernel (pack.cu): kept for A/B runs and the filter pass
+int launch_binpack(Engine* e);   // K3: block-per-template estimator (binpack.cu)
 struct FilterLaunch {
   int runs, n_pods, last_index, break_on_failure, nctrl;
   const int32_t *run_off, *pods, *hint, *cls, *class_ctrl;

@@ -208,7 +208,7 @@ int launch_order(Engine* e) {
   if (smem > 200 * 1024) { set_error("too many pod groups for the in-smem orderer"); return 1; }
   CAE_CUDA(cudaFuncSetAttribute(order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   order_kernel<<<nt, 256, smem, e->stream>>>(e->dobj, e->E, e->T, e->N, e->t_begin, n_sort, e->d_group_reason,
-                                              e->d_score, e->d_order, e->d_order_n, e->pack_lpt ? e->d_tmpl_cost : nullptr);
+                                              e->d_score, e->d_order, e->d_order_n, e->d_tmpl_cost);
   e->stats.kernel_launches++;
   CAE_KERNEL_OK();
   return 0;
