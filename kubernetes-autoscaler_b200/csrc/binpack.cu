@@ -26,6 +26,8 @@
 // a block-wide arg-min of the cyclic distance, one placement.
 #include <algorithm>
 #include <climits>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "engine.h"
@@ -71,26 +73,14 @@ struct BpShared {
   int t, L, rem, pre_s, log_n, overflow, newly, need_log, mlast;
 };
 
-__device__ __forceinline__ int bp_wsum(int v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
+__device__ __forceinline__ int bp_wsum(int v) { return __reduce_add_sync(0xffffffffu, v); }   // REDUX: one instruction
 __device__ __forceinline__ long long bp_wsum_ll(long long v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ int bp_wmax(int v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-__device__ __forceinline__ int bp_wmin(int v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
+__device__ __forceinline__ int bp_wmax(int v) { return __reduce_max_sync(0xffffffffu, v); }
+__device__ __forceinline__ int bp_wmin(int v) { return __reduce_min_sync(0xffffffffu, v); }
 
 // Block reductions: one barrier each.  Two scratch rows alternate (`par`), so a row is rewritten only
 // after every thread has passed the barrier of the reduction in between.
@@ -113,6 +103,28 @@ __device__ __forceinline__ void blk_sum_sum_max(BpShared& S, int& par, int& a, i
   a = bp_wsum(lane < NW ? S.ri[par][lane][0] : 0);
   b = bp_wsum(lane < NW ? S.ri[par][lane][1] : 0);
   c = bp_wmax(lane < NW ? S.ri[par][lane][2] : INT_MIN);
+  par ^= 1;
+}
+// a: sum of per-thread values each <= clampv (<= 2^26), clamped to clampv after every stage; b: max; c: sum
+template <int NW>
+__device__ __forceinline__ void blk_csum_max_sum(BpShared& S, int& par, int clampv, int& a, int& b, int& c) {
+  a = min(bp_wsum(a), clampv); b = bp_wmax(b); c = bp_wsum(c);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { S.ri[par][w][0] = a; S.ri[par][w][1] = b; S.ri[par][w][2] = c; }
+  __syncthreads();
+  a = min(bp_wsum(lane < NW ? S.ri[par][lane][0] : 0), clampv);
+  b = bp_wmax(lane < NW ? S.ri[par][lane][1] : INT_MIN);
+  c = bp_wsum(lane < NW ? S.ri[par][lane][2] : 0);
+  par ^= 1;
+}
+template <int NW>
+__device__ __forceinline__ void blk_sum_max(BpShared& S, int& par, int& a, int& b) {
+  a = bp_wsum(a); b = bp_wmax(b);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { S.ri[par][w][0] = a; S.ri[par][w][1] = b; }
+  __syncthreads();
+  a = bp_wsum(lane < NW ? S.ri[par][lane][0] : 0);
+  b = bp_wmax(lane < NW ? S.ri[par][lane][1] : INT_MIN);
   par ^= 1;
 }
 template <int NW>
@@ -140,8 +152,28 @@ __device__ __forceinline__ long long blk_sum_ll(BpShared& S, int& par, long long
 #define BP_MIN_CTAS 3
 #endif
 
-template <int A, int TPB>
-__global__ void __launch_bounds__(TPB, BP_MIN_CTAS) binpack_kernel(DevObjects o, DynTables d, BpParams p) {
+// floor(f / r) for f >= r > 0 with a quotient below 2^31: one double division + an exact +-1 correction
+// (|double error| < 2^-20 of the quotient), instead of the ~100-instruction 64-bit integer division
+__device__ __forceinline__ int bp_div(int64_t f, int64_t r) {
+  long long q = (long long)(__ll2double_rn(f) / __ll2double_rn(r));
+  if (q * r > f) --q;
+  else if ((q + 1) * r <= f) ++q;
+  return (int)q;
+}
+
+// the same with a precomputed float reciprocal of r, for quotients below `kbound` <= 2^20: the float estimate is
+// within 1 of the true quotient (relative error < 2^-21), the correction makes it exact
+__device__ __forceinline__ int bp_div_f(int64_t f, int64_t r, float rinv, int kbound) {
+  if (kbound > (1 << 20)) return bp_div(f, r);
+  int q = (int)(__ll2float_rz(f) * rinv);
+  const long long qr = (long long)q * r;
+  if (qr > f) --q;
+  else if (qr + r <= f) ++q;
+  return q;
+}
+
+template <int A, int TPB, bool WIN>
+__global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(DevObjects o, DynTables d, BpParams p) {
   constexpr int NW = TPB / 32;
   constexpr int A1 = A > 0 ? A : 1;
   extern __shared__ __align__(16) unsigned char bp_dsm[];
@@ -172,15 +204,31 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS) binpack_kernel(DevObjects o,
   int32_t* logbuf = wver + (size_t)DYN_MAX_Q * p.dstride;                                      // [log_cap][3]
   uint8_t* g_sched = reinterpret_cast<uint8_t*>(logbuf + (size_t)p.log_cap * 3);               // [Xg]
 
-  auto fr = [&](int a, int x) -> int64_t& { return (win && x >= Neff) ? s_free[a * win + (x - Neff)] : g_free[(size_t)a * Xg + x]; };
-  auto po = [&](int x) -> unsigned long long& { return (win && x >= Neff) ? s_ports[x - Neff] : g_ports[x]; };
-  auto sl_ = [&](int x) -> int32_t& { return (win && x >= Neff) ? s_slots[x - Neff] : g_slots[x]; };
-  auto kc = [&](int x) -> int32_t& { return (win && x >= Neff) ? s_kc[x - Neff] : g_kc[x]; };
-  auto pr = [&](int x) -> int32_t& { return (win && x >= Neff) ? s_pre[x - Neff] : g_pre[x]; };
-  auto sch = [&](int x) -> uint8_t& { return (win && x >= Neff) ? s_sched[x - Neff] : g_sched[x]; };
+  // added node j (shared window, or the slab behind the cluster nodes when the window does not fit)
+  auto afr = [&](int a, int j) -> int64_t& { if constexpr (WIN) return s_free[a * win + j]; else return g_free[(size_t)a * Xg + Neff + j]; };
+  auto apo = [&](int j) -> unsigned long long& { if constexpr (WIN) return s_ports[j]; else return g_ports[Neff + j]; };
+  auto asl = [&](int j) -> int32_t& { if constexpr (WIN) return s_slots[j]; else return g_slots[Neff + j]; };
+  auto akc = [&](int j) -> int32_t& { if constexpr (WIN) return s_kc[j]; else return g_kc[Neff + j]; };
+  auto apr = [&](int j) -> int32_t& { if constexpr (WIN) return s_pre[j]; else return g_pre[Neff + j]; };
+  auto asch = [&](int j) -> uint8_t& { if constexpr (WIN) return s_sched[j]; else return g_sched[Neff + j]; };
+  // cluster node x < Neff
+  auto cfr = [&](int a, int x) -> int64_t& { return g_free[(size_t)a * Xg + x]; };
+  auto cpo = [&](int x) -> unsigned long long& { return g_ports[x]; };
+  auto csl = [&](int x) -> int32_t& { return g_slots[x]; };
+  auto csch = [&](int x) -> uint8_t& { return g_sched[x]; };
+  // any node of the simulation, x < Neff: cluster, else added node x - Neff (per-pod loop only)
+  auto fr = [&](int a, int x) -> int64_t& { return x >= Neff ? afr(a, x - Neff) : cfr(a, x); };
+  auto po = [&](int x) -> unsigned long long& { return x >= Neff ? apo(x - Neff) : cpo(x); };
+  auto sl_ = [&](int x) -> int32_t& { return x >= Neff ? asl(x - Neff) : csl(x); };
+  auto sch = [&](int x) -> uint8_t& { return x >= Neff ? asch(x - Neff) : csch(x); };
 
   GroupDyn& wd = S.wd;
   int par = 0;                 // block-uniform parity of the reduction scratch
+  // CAE_PACK_PROF=1: cycles per phase / event counts, thread 0 of every block, summed over the launch
+  long long prof_t0 = 0;
+#define BP_PROF_BEGIN() do { if (p.prof && tid == 0) prof_t0 = clock64(); } while (0)
+#define BP_PROF_END(slot) do { if (p.prof && tid == 0) atomicAdd((unsigned long long*)&p.prof[slot], (unsigned long long)(clock64() - prof_t0)); } while (0)
+#define BP_PROF_COUNT(slot, v) do { if (p.prof && tid == 0) atomicAdd((unsigned long long*)&p.prof[slot], (unsigned long long)(v)); } while (0)
   int gver_ctr = hdr[1] + 1;
 
   for (;;) {
@@ -193,6 +241,7 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS) binpack_kernel(DevObjects o,
     __syncthreads();
     const int t = S.t;
     if (t >= p.t_end) break;
+    const long long prof_tmpl0 = (p.prof && tid == 0) ? clock64() : 0;
 
     int64_t tfree[A1];
 #pragma unroll
@@ -217,24 +266,41 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS) binpack_kernel(DevObjects o,
     auto round_robin = [&](int cnt, int s, int npods, auto capfn, auto kcref, auto preref, auto applyfn,
                            int& got, int& newly, int& last_dist) {
       got = 0; newly = 0; last_dist = -1;
-      for (int i = tid; i <= BP_HIST; i += TPB) S.hist[i] = 0;
-      __syncthreads();
-      long long total = 0;
-      int kmax = 0;
-      for (int base = 0; base < cnt; base += TPB) {
-        const int i = base + tid;
-        int k = 0;
-        if (i < cnt) { k = capfn(i); kcref(i) = k; total += k; kmax = max(kmax, k); }
-        // histogram of the capacities: lanes with the same value elect one writer
-        const bool cntd = k > 0 && k <= BP_HIST;
-        const unsigned peers = __match_any_sync(0xffffffffu, cntd ? k : 0);
-        if (cntd && lane == __ffs(peers) - 1) atomicAdd(&S.hist[k], __popc(peers));
+      // pass 1: capacities; their sum only matters up to npods + 1, so it travels as a clamped 32-bit value
+      const int clampv = npods < (1 << 26) ? npods + 1 : (1 << 26);
+      int total = 0, kmax = 0, npos = 0;
+      for (int i = tid; i < cnt; i += TPB) {
+        const int k = capfn(i);
+        kcref(i) = k;
+        total = min(total + min(k, clampv), clampv);
+        kmax = max(kmax, k);
+        npos += k > 0;
       }
-      blk_sum_ll_max<NW>(S, par, total, kmax);
+      blk_csum_max_sum<NW>(S, par, clampv, total, kmax, npos);
       if (total <= 0) return;
       int L, rem;
-      if (total <= npods) { L = kmax; rem = 0; }
+      bool exact = npods < (1 << 26);   // the clamped sum decides total <= npods
+      if (!exact) {
+        long long t2 = 0;
+        for (int i = tid; i < cnt; i += TPB) t2 += kcref(i);
+        t2 = blk_sum_ll<NW>(S, par, t2);
+        total = t2 <= npods ? (int)t2 : INT_MAX;
+      }
+      if (total <= npods) { L = kmax; rem = 0; got = total; }            // every node takes its full capacity
+      else if (npos >= npods) { L = 0; rem = npods; got = npods; }       // one pod each on the first npods nodes with room
       else if (kmax <= BP_HIST) {
+        got = npods;
+        // histogram of the capacities: lanes with the same value elect one writer
+        for (int i = tid; i <= BP_HIST; i += TPB) S.hist[i] = 0;
+        __syncthreads();
+        for (int base = 0; base < cnt; base += TPB) {
+          const int i = base + tid;
+          const int k = i < cnt ? kcref(i) : 0;
+          const bool cntd = k > 0;
+          const unsigned peers = __match_any_sync(0xffffffffu, cntd ? k : 0);
+          if (cntd && lane == __ffs(peers) - 1) atomicAdd(&S.hist[k], __popc(peers));
+        }
+        __syncthreads();
         // f(L) = sum_j min(k_j, L) = sum_{l <= L} G(l), G(l) = #{k_j >= l}: two warp scans over the histogram
         if (warp == 0) {
           constexpr int PB = BP_HIST / 32;
@@ -270,6 +336,7 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS) binpack_kernel(DevObjects o,
         __syncthreads();
         L = S.L; rem = S.rem;
       } else {
+        got = npods;
         int lo = 0, hi = kmax;  // f(lo) <= npods < f(hi)
         long long flo = 0;
         while (hi - lo > 1) {
@@ -325,12 +392,11 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS) binpack_kernel(DevObjects o,
         const int mj = min(k, L) + (extra ? 1 : 0);
         if (mj > 0) {
           newly += applyfn(i, mj);
-          got += mj;
           // the pod placed last sits at the furthest position served in the final lap
           if (rem > 0 ? extra : (k >= L)) { int dd = i - s; if (dd < 0) dd += cnt; last_dist = max(last_dist, dd); }
         }
       }
-      blk_sum_sum_max<NW>(S, par, got, newly, last_dist);
+      blk_sum_max<NW>(S, par, newly, last_dist);
     };
 
     for (int gi = 0; gi < n_groups; ++gi) {
@@ -341,6 +407,9 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS) binpack_kernel(DevObjects o,
       int64_t req[A1];
 #pragma unroll
       for (int a = 0; a < A; ++a) req[a] = o.ps_req[(size_t)spec * R + p.act_dim[a]];
+      float rinv[A1];
+#pragma unroll
+      for (int a = 0; a < A; ++a) rinv[a] = req[a] > 0 ? __frcp_rn(__ll2float_rn(req[a])) : 0.f;
       const int sc = p.spec_sc[spec];
       const int dc = p.has_dyn ? p.spec_dc[spec] : 0;
       const bool static_new = (p.pre_code[(size_t)sc * p.U + col_new] & 0x0F) == 0;
@@ -352,28 +421,40 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS) binpack_kernel(DevObjects o,
       int placed = 0;
 
       // spare capacity of node x for this pod by NodePorts + NodeResourcesFit alone (pod slots, free resources)
-      auto res_cap = [&](int x, int want) -> int {
-        int k = min(sl_(x), want);
-        if (k > 0 && (po(x) & pconf)) k = 0;
+      auto res_cap_of = [&](auto frf, int slots, unsigned long long ports, int want) -> int {
+        int k = min(slots, want);
+        if (k > 0 && (ports & pconf)) k = 0;
 #pragma unroll
         for (int a = 0; a < A; ++a) {
           if (req[a] > 0 && k > 0) {
-            const int64_t f = fr(a, x);
+            const int64_t f = frf(a);
             if (f < req[a]) k = 0;
-            else if (f < (int64_t)k * req[a]) k = (int)(f / req[a]);
+            else if (f < (int64_t)k * req[a]) k = bp_div_f(f, req[a], rinv[a], k);
           }
         }
         if (has_ports) k = min(k, 1);
         return k;
       };
+      auto res_cap_a = [&](int j, int want) -> int { return res_cap_of([&](int a) { return afr(a, j); }, asl(j), has_ports ? apo(j) : 0ull, want); };
+      auto res_cap_c = [&](int x, int want) -> int { return res_cap_of([&](int a) { return cfr(a, x); }, csl(x), has_ports ? cpo(x) : 0ull, want); };
       // ForceAddPod x m on node x (owner thread); returns 1 when the node held no scheduled pod before
-      auto book = [&](int x, int m) -> int {
+      auto book_a = [&](int j, int m) -> int {
 #pragma unroll
-        for (int a = 0; a < A; ++a) if (req[a] > 0) fr(a, x) -= (int64_t)m * req[a];
-        sl_(x) -= m;
-        po(x) |= pbit;
+        for (int a = 0; a < A; ++a) if (req[a] > 0) afr(a, j) -= (int64_t)m * req[a];
+        asl(j) -= m;
+        if (has_ports) apo(j) |= pbit;
         int nw = 0;
-        if (!sch(x)) { sch(x) = 1; nw = 1; }
+        if (!asch(j)) { asch(j) = 1; nw = 1; }
+        if (feeds) log_append(Neff + j, spec, m);
+        return nw;
+      };
+      auto book_c = [&](int x, int m) -> int {
+#pragma unroll
+        for (int a = 0; a < A; ++a) if (req[a] > 0) cfr(a, x) -= (int64_t)m * req[a];
+        csl(x) -= m;
+        if (has_ports) cpo(x) |= pbit;
+        int nw = 0;
+        if (!csch(x)) { csch(x) = 1; nw = 1; }
         if (feeds) log_append(x, spec, m);
         return nw;
       };
@@ -386,7 +467,7 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS) binpack_kernel(DevObjects o,
           for (int a = 0; a < A; ++a) {
             if (req[a] > 0 && k > 0) {
               if (tfree[a] < req[a]) k = 0;
-              else if (tfree[a] < (int64_t)k * req[a]) k = (int)(tfree[a] / req[a]);
+              else if (tfree[a] < (int64_t)k * req[a]) k = bp_div_f(tfree[a], req[a], rinv[a], k);
             }
           }
           if (has_ports) k = min(k, 1);
@@ -410,14 +491,14 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS) binpack_kernel(DevObjects o,
           fill = (int)min((long long)n, (long long)add * k_new);
         }
         for (int i = tid; i < add; i += TPB) {
-          const int x = Neff + n_new + i;
+          const int j = n_new + i;
           const int mj = k_new <= 0 ? 0 : min(k_new, fill - i * k_new);
 #pragma unroll
-          for (int a = 0; a < A; ++a) fr(a, x) = tfree[a] - (req[a] > 0 ? (int64_t)mj * req[a] : 0);
-          sl_(x) = tslots - mj;
-          po(x) = mj > 0 ? pbit : 0ull;
-          sch(x) = mj > 0;
-          if (feeds && mj > 0) log_append(x, spec, mj);
+          for (int a = 0; a < A; ++a) afr(a, j) = tfree[a] - (req[a] > 0 ? (int64_t)mj * req[a] : 0);
+          asl(j) = tslots - mj;
+          apo(j) = mj > 0 ? pbit : 0ull;
+          asch(j) = mj > 0;
+          if (feeds && mj > 0) log_append(Neff + j, spec, mj);
         }
         if (k_new > 0) { nodes_with_pods += add; placed += fill; n -= fill; }
         n_new += add;
@@ -426,14 +507,16 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS) binpack_kernel(DevObjects o,
 
       if (dc == 0) {
         // ======================= plain group: closed form =======================================
+        BP_PROF_COUNT(8, 1);
+        BP_PROF_BEGIN();
         if (n_new > 0 && static_new) {
           const int s = last_index >= N ? last_index - N : 0;  // first added node in cyclic scan order
           int got, newly, last_dist;
           round_robin(n_new, s, n,
-                      [&](int i) { return res_cap(Neff + i, n); },
-                      [&](int i) -> int32_t& { return kc(Neff + i); },
-                      [&](int i) -> int32_t& { return pr(Neff + i); },
-                      [&](int i, int m) { return book(Neff + i, m); }, got, newly, last_dist);
+                      [&](int i) { return res_cap_a(i, n); },
+                      [&](int i) -> int32_t& { return akc(i); },
+                      [&](int i) -> int32_t& { return apr(i); },
+                      [&](int i, int m) { return book_a(i, m); }, got, newly, last_dist);
           placed += got;
           nodes_with_pods += newly;
           n -= got;
@@ -444,16 +527,20 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS) binpack_kernel(DevObjects o,
           }
           __syncthreads();
         }
+        BP_PROF_END(0);
+        BP_PROF_BEGIN();
         if (n > 0 && new_nodes_available) {
           // after the pass above no added node (the last one included) can take this pod any more
-          const bool stop = (n_new > 0) && !sch(Neff + n_new - 1);  // last node still empty (:212)
+          const bool stop = (n_new > 0) && !asch(n_new - 1);  // last node still empty (:212)
           if (!stop) add_new_nodes(fresh_cap(n), false);
         }
+        BP_PROF_END(1);
       } else {
         // ======================= dynamic group ===================================================
         const bool host_spread = o.ps_hostname_spread[spec] != 0;
         const int gver = ++gver_ctr;      // version of this group's working counters (lazy copy-on-write)
         // ---- describe the group's counters ----
+        BP_PROF_BEGIN();
         __syncthreads();
         if (tid == 0) {
           int nq = 0;
@@ -612,7 +699,9 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS) binpack_kernel(DevObjects o,
           __syncthreads();
         };
 
+        BP_PROF_END(2);
         // ---- hostname spread with the global minimum pinned at 0: closed form ----
+        BP_PROF_BEGIN();
         bool fast = false;
         if (nq == 1 && wd.kind[0] == Q_PTS && wd.host[0] && !need_log && wd.minv[0] == 0) {
           const int w0 = wd.wown[0], self0 = wd.self[0], ms0 = wd.maxskew[0], boff0 = wd.boff[0], k0 = wd.k[0], qid0 = wd.qid[0];
@@ -631,7 +720,7 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS) binpack_kernel(DevObjects o,
             for (int x = tid; x < N; x += TPB) {
               int k = 0;
               const bool stat_ok = (p.pre_code[(size_t)sc * p.U + x] & 0x0F) == 0 && !o.node_unschedulable[x];
-              const int rc = stat_ok ? res_cap(x, n) : 0;
+              const int rc = stat_ok ? res_cap_c(x, n) : 0;
               const int dm = d.dom[(size_t)k0 * NT + x];
               const bool el = d.elig[(size_t)qid0 * p.U + x] != 0;
               if (dm >= 0) {
@@ -644,6 +733,7 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS) binpack_kernel(DevObjects o,
             long long z = 0;
             blk_sum_ll_max<NW>(S, par, z, blocked);
             caps_done = true;
+            BP_PROF_COUNT(14, 1);
             return blocked > 0;
           };
           if (w0 == 0 || wd.nmin[0] > n) fast = true;
@@ -659,10 +749,10 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS) binpack_kernel(DevObjects o,
               const int lastj = n_new - 1;
               int got, newly, last_dist;
               round_robin(n_new, s, n,
-                          [&](int i) { return min(res_cap(Neff + i, n), S_new); },
-                          [&](int i) -> int32_t& { return kc(Neff + i); },
-                          [&](int i) -> int32_t& { return pr(Neff + i); },
-                          [&](int i, int m) { if (i == lastj) S.mlast = m; return book(Neff + i, m); }, got, newly, last_dist);
+                          [&](int i) { return min(res_cap_a(i, n), S_new); },
+                          [&](int i) -> int32_t& { return akc(i); },
+                          [&](int i) -> int32_t& { return apr(i); },
+                          [&](int i, int m) { if (i == lastj) S.mlast = m; return book_a(i, m); }, got, newly, last_dist);
               placed += got;
               nodes_with_pods += newly;
               n -= got;
@@ -677,6 +767,7 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS) binpack_kernel(DevObjects o,
             // the pods the last node refuses for skew go to the cluster nodes in cyclic order (:186-205)
             auto cluster_phase = [&]() {
               if (N == 0) return;
+              BP_PROF_COUNT(15, 1);
               if (!caps_done) cluster_caps();
               const int s = last_index < N ? last_index : 0;
               int got, newly, last_dist;
@@ -684,7 +775,7 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS) binpack_kernel(DevObjects o,
                           [&](int i) { return g_kc[i]; },
                           [&](int i) -> int32_t& { return g_kc[i]; },
                           [&](int i) -> int32_t& { return g_pre[i]; },
-                          [&](int i, int m) { return book(i, m); }, got, newly, last_dist);
+                          [&](int i, int m) { return book_c(i, m); }, got, newly, last_dist);
               placed += got;
               nodes_with_pods += newly;
               n -= got;
@@ -700,15 +791,15 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS) binpack_kernel(DevObjects o,
               bool cluster_done = false;
               if (n_new > 0) {
                 // why the last node refuses the next pod (default plugin order): static, ports, fit, then skew
-                const int xl = Neff + n_new - 1;
-                bool skew = static_new && !(po(xl) & pconf) && sl_(xl) >= 1;
+                const int jl = n_new - 1;
+                bool skew = static_new && !(apo(jl) & pconf) && asl(jl) >= 1;
 #pragma unroll
-                for (int a = 0; a < A; ++a) skew = skew && !(req[a] > 0 && req[a] > fr(a, xl));
+                for (int a = 0; a < A; ++a) skew = skew && !(req[a] > 0 && req[a] > afr(a, jl));
                 skew = skew && (c_new + (wd.elig_new[0] ? m_last * w0 : 0) + self0 > ms0);
                 if (skew && host_spread) { cluster_phase(); cluster_done = true; }
               }
               if (n > 0) {
-                const bool stop = (n_new > 0) && !sch(Neff + n_new - 1);  // last node still empty (:212)
+                const bool stop = (n_new > 0) && !asch(n_new - 1);  // last node still empty (:212)
                 if (!stop) {
                   const int k_res = fresh_cap(n);
                   const int k_new = min(k_res, S_new);
@@ -726,7 +817,9 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS) binpack_kernel(DevObjects o,
             }
           }
         }
+        if (fast) { BP_PROF_END(4); BP_PROF_COUNT(9, 1); }
         if (!fast) {
+        BP_PROF_COUNT(10, 1);
         // ======================= per-pod loop on incremental counters =============================
         // RunFilterPlugins on node x (default plugin order), per thread
         auto eval = [&](int x) -> int {
@@ -836,7 +929,9 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS) binpack_kernel(DevObjects o,
         };
 
         // ---- tryToScheduleOnExistingNodes: per pod, first passing added node in cyclic order ----
+        BP_PROF_BEGIN();
         while (n > 0 && n_new > 0) {
+          BP_PROF_COUNT(12, 1);
           const int s = last_index >= N ? last_index - N : 0;
           int best = INT_MAX, zero = 0;
           for (int j = tid; j < n_new; j += TPB)
@@ -848,8 +943,11 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS) binpack_kernel(DevObjects o,
           place(Neff + found);
           last_index = (N + found + 1) % (N + n_new);
         }
+        BP_PROF_END(5);
+        BP_PROF_BEGIN();
         // ---- tryToScheduleOnNewNodes ----
         while (n > 0 && new_nodes_available) {
+          BP_PROF_COUNT(13, 1);
           bool found = false;
           if (n_new > 0) {
             const int xl = Neff + n_new - 1;
@@ -885,12 +983,15 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS) binpack_kernel(DevObjects o,
             place(Neff + n_new - 1);
           }
         }
+        BP_PROF_END(6);
+        BP_PROF_COUNT(11, placed);
         }  // !fast
       }
       pods_total += placed;
       if (tid == 0) p.sched[(size_t)t * p.E + g] = placed;
       __syncthreads();
     }
+    if (p.prof && tid == 0) atomicAdd((unsigned long long*)&p.prof[7], (unsigned long long)(clock64() - prof_tmpl0));
     if (tid == 0) {
       p.node_count[t] = nodes_with_pods;
       p.pod_count[t] = pods_total;
@@ -920,18 +1021,26 @@ __global__ void lpt_rank_kernel(const long long* __restrict__ cost, int t_begin,
   if (i < nt) perm[rank] = t_begin + i;
 }
 
-template <int A>
-static int launch_binpack_a(Engine* e, int blocks_wanted, size_t smem, const BpParams& p, int* blocks_out, bool query_only) {
-  auto kern = binpack_kernel<A, 256>;
+template <int A, int TPB>
+static int launch_binpack_at(Engine* e, int blocks_wanted, size_t smem, const BpParams& p, int* blocks_out, bool query_only) {
+  auto kern = p.win ? binpack_kernel<A, TPB, true> : binpack_kernel<A, TPB, false>;
   CAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  CAE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+  CAE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, smem));
   if (per_sm < 1) { set_error("binpack_kernel does not fit an SM"); return -1; }
   const int blocks = std::max(1, std::min(blocks_wanted, per_sm * e->sm_count));
   *blocks_out = blocks;
   if (query_only) return 0;
-  kern<<<blocks, 256, smem, e->stream>>>(e->dobj, e->dyn, p);
+  kern<<<blocks, TPB, smem, e->stream>>>(e->dobj, e->dyn, p);
   return 0;
+}
+template <int A>
+static int launch_binpack_a(Engine* e, int blocks_wanted, size_t smem, const BpParams& p, int* blocks_out, bool query_only) {
+  if constexpr (A == 3) {   // experiment: CAE_BP_TPB=128
+    static const int tpb = getenv("CAE_BP_TPB") ? atoi(getenv("CAE_BP_TPB")) : 256;
+    if (tpb == 128) return launch_binpack_at<A, 128>(e, blocks_wanted, smem, p, blocks_out, query_only);
+  }
+  return launch_binpack_at<A, 256>(e, blocks_wanted, smem, p, blocks_out, query_only);
 }
 
 static int launch_binpack_any(Engine* e, int blocks_wanted, size_t smem, const BpParams& p, int* blocks_out, bool query_only) {
@@ -1004,10 +1113,26 @@ int launch_binpack(Engine* e) {
   lpt_rank_kernel<<<(nt + 255) / 256, 256, 0, e->stream>>>(e->d_tmpl_cost, e->t_begin, nt, e->d_perm);
   e->stats.kernel_launches++;
   p.perm = e->d_perm;
+  static const bool want_prof = getenv("CAE_PACK_PROF") != nullptr;
+  long long* d_prof = nullptr;
+  if (want_prof) {
+    CAE_CUDA(cudaMalloc(&d_prof, sizeof(long long) * 16));
+    CAE_CUDA(cudaMemsetAsync(d_prof, 0, sizeof(long long) * 16, e->stream));
+    p.prof = d_prof;
+  }
   int launched = 0;
   if (launch_binpack_any(e, blocks, smem, p, &launched, false)) return -1;
   e->stats.kernel_launches++;
   CAE_KERNEL_OK();
+  if (want_prof) {
+    long long h[16];
+    CAE_CUDA(cudaMemcpyAsync(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
+    CAE_CUDA(cudaStreamSynchronize(e->stream));
+    cudaFree(d_prof);
+    fprintf(stderr, "binpack prof: blocks=%d smem=%zu win=%d cycles{plain_rr=%lld plain_new=%lld dyn_setup=%lld fast=%lld genA=%lld genB=%lld template=%lld} "
+            "counts{plain=%lld fast=%lld generic=%lld generic_pods=%lld genA_iters=%lld genB_iters=%lld cluster_caps=%lld cluster_phase=%lld}\n",
+            launched, smem, p.win, h[0], h[1], h[2], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11], h[12], h[13], h[14], h[15]);
+  }
   return 0;
 }
 
