@@ -437,7 +437,7 @@ static int do_load(Engine* e, const cae_objects* o) {
       dev_alloc(e, &e->d_fit_count, (size_t)std::max(T, 1), true) || dev_alloc(e, &e->d_fit_acc, (size_t)std::max(T, 1), true) ||
       dev_alloc(e, &e->d_chunk_done, (size_t)std::max(e->Twp / FEAS_TW, 1), true) || dev_alloc(e, &e->d_group_reason, (size_t)std::max(T, 1) * std::max(e->E, 1)) ||
       dev_alloc(e, &e->d_counts2, (size_t)2 * std::max(T, 1), true) || dev_alloc(e, &e->d_sched, (size_t)std::max(T, 1) * std::max(e->E, 1), true) ||
-      dev_alloc(e, &e->d_order, (size_t)std::max(T, 1) * std::max(e->E, 1)) || dev_alloc(e, &e->d_order_n, (size_t)std::max(T, 1), true) ||
+      dev_alloc(e, &e->d_order, (size_t)std::max(T, 1) * std::max(e->E, 1)) || dev_alloc(e, &e->d_grec, (size_t)std::max(e->E, 1)) || dev_alloc(e, &e->d_order_n, (size_t)std::max(T, 1), true) ||
       dev_alloc(e, &e->d_max_nodes, (size_t)std::max(T, 1), true) || dev_alloc(e, &e->d_tmpl_cost, (size_t)std::max(T, 1), true) ||
       dev_alloc(e, &e->d_perm, (size_t)std::max(T, 1)) || dev_alloc(e, &e->d_work_counter, 4, true) ||
       dev_alloc(e, &e->d_act_dim, CAE_MAX_RES))
@@ -468,6 +468,7 @@ static int do_load(Engine* e, const cae_objects* o) {
   }
   if (launch_post_bits(e)) return -1;
   if (launch_expand_pods(e)) return -1;
+  if (launch_group_records(e)) return -1;
   cudaEventRecord(e->ev1, e->stream);
   lt.mark("launches");
   CAE_CUDA(cudaStreamSynchronize(e->stream));
@@ -665,6 +666,8 @@ int32_t cae_estimate_all(cae_engine* h, const int32_t* max_nodes, int32_t* node_
   if (sched_count && E) CAE_CUDA(cudaMemcpyAsync(sched_count, e->d_sched, sizeof(int32_t) * (size_t)T * E, cudaMemcpyDeviceToHost, e->stream));
   if (order && E) CAE_CUDA(cudaMemcpyAsync(order, e->d_order, sizeof(int32_t) * (size_t)T * E, cudaMemcpyDeviceToHost, e->stream));
   CAE_CUDA(cudaStreamSynchronize(e->stream));
+  if (order && E)   // the device rows carry a flag bit per entry (ORDER_NOT_ON_FRESH); padding stays -1
+    for (size_t i = 0, nn = (size_t)T * E; i < nn; ++i) if (order[i] >= 0) order[i] &= ~cae::ORDER_NOT_ON_FRESH;
   float ms = 0;
   cudaEventElapsedTime(&ms, e->ev0, e->ev1);
   e->stats.estimate_ms = ms;

@@ -38,6 +38,7 @@ struct BpParams {
   int E, T, N, U, t_begin, t_end, cap, has_dyn, dstride, log_cap;
   int win;                 // added nodes resident in shared memory (= cap), 0 when they do not fit
   const int32_t *order, *order_n;
+  const GroupRec* grec;    // [E] one record per pending pod group
   const int32_t* perm;     // work order of the templates
   const uint8_t* pre_code;
   const int32_t *spec_sc, *spec_dc;
@@ -65,6 +66,7 @@ struct GroupDyn {
 };
 
 struct BpShared {
+  GroupRec rec[2];            // record of the current group / the next one (in flight)
   GroupDyn wd;
   int flag[DYN_MAX_Q];        // counters whose minimum must be recomputed
   long long rl[2][32];
@@ -151,6 +153,13 @@ __device__ __forceinline__ long long blk_sum_ll(BpShared& S, int& par, long long
 #ifndef BP_MIN_CTAS
 #define BP_MIN_CTAS 3
 #endif
+
+__device__ __forceinline__ void bp_cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem_src));
+}
+__device__ __forceinline__ void bp_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void bp_cp_async_wait() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // floor(f / r) for f >= r > 0 with a quotient below 2^31: one double division + an exact +-1 correction
 // (|double error| < 2^-20 of the quotient), instead of the ~100-instruction 64-bit integer division
@@ -399,25 +408,39 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
       blk_sum_max<NW>(S, par, newly, last_dist);
     };
 
+    // Group records travel one group ahead: warp 0 copies the next group's record into shared memory with cp.async
+    // while the block works on the current one; the order row is read two entries ahead.
+    const int32_t* order_row = p.order + (size_t)t * p.E;
+    auto fetch_rec = [&](int graw, int buf) {
+      if (warp == 0) {
+        if (lane < 9) bp_cp_async16(reinterpret_cast<char*>(&S.rec[buf]) + lane * 16,
+                                    reinterpret_cast<const char*>(p.grec + (graw & ~ORDER_NOT_ON_FRESH)) + lane * 16);
+        bp_cp_async_commit();
+      }
+    };
+    int ord_cur = n_groups > 0 ? order_row[0] : 0, ord_next = n_groups > 1 ? order_row[1] : 0;
+    if (n_groups > 0) fetch_rec(ord_cur, 0);
+    if (warp == 0) bp_cp_async_wait();
+    __syncthreads();
+
     for (int gi = 0; gi < n_groups; ++gi) {
-      const int g = p.order[(size_t)t * p.E + gi];
-      const int pb = o.group_off[g];
-      int n = o.group_off[g + 1] - pb;
-      const int spec = o.pend_spec[pb];
+      const GroupRec& rc = S.rec[gi & 1];
+      if (gi + 1 < n_groups) fetch_rec(ord_next, (gi + 1) & 1);
+      const int ord_next2 = gi + 2 < n_groups ? order_row[gi + 2] : 0;
+      const int g = ord_cur & ~ORDER_NOT_ON_FRESH;
+      int n = rc.n;
+      const int spec = rc.spec;
       int64_t req[A1];
-#pragma unroll
-      for (int a = 0; a < A; ++a) req[a] = o.ps_req[(size_t)spec * R + p.act_dim[a]];
       float rinv[A1];
 #pragma unroll
-      for (int a = 0; a < A; ++a) rinv[a] = req[a] > 0 ? __frcp_rn(__ll2float_rn(req[a])) : 0.f;
-      const int sc = p.spec_sc[spec];
-      const int dc = p.has_dyn ? p.spec_dc[spec] : 0;
-      const bool static_new = (p.pre_code[(size_t)sc * p.U + col_new] & 0x0F) == 0;
-      const int plist = o.ps_port_list[spec];
-      const bool has_ports = o.port_off[plist + 1] > o.port_off[plist];
-      const unsigned long long pconf = has_ports ? p.port_conf[plist] : 0ull;  // port sets this pod collides with
-      const unsigned long long pbit = has_ports ? (1ull << p.pc_of[plist]) : 0ull;
-      const bool feeds = p.has_dyn && d.group_feeds[g];
+      for (int a = 0; a < A; ++a) { req[a] = rc.req[a]; rinv[a] = rc.rinv[a]; }
+      const int sc = rc.sc;
+      const int dc = rc.dc;
+      const bool static_new = !(ord_cur & ORDER_NOT_ON_FRESH);
+      const bool has_ports = (rc.flags & GREC_HAS_PORTS) != 0;
+      const unsigned long long pconf = rc.pconf;  // port sets this pod collides with
+      const unsigned long long pbit = rc.pbit;
+      const bool feeds = (rc.flags & GREC_FEEDS) != 0;
       int placed = 0;
 
       // spare capacity of node x for this pod by NodePorts + NodeResourcesFit alone (pod slots, free resources)
@@ -537,7 +560,7 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
         BP_PROF_END(1);
       } else {
         // ======================= dynamic group ===================================================
-        const bool host_spread = o.ps_hostname_spread[spec] != 0;
+        const bool host_spread = (rc.flags & GREC_HOST_SPREAD) != 0;
         const int gver = ++gver_ctr;      // version of this group's working counters (lazy copy-on-write)
         // ---- describe the group's counters ----
         BP_PROF_BEGIN();
@@ -989,7 +1012,10 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
       }
       pods_total += placed;
       if (tid == 0) p.sched[(size_t)t * p.E + g] = placed;
+      if (warp == 0) bp_cp_async_wait();   // the next group's record has landed
       __syncthreads();
+      ord_cur = ord_next;
+      ord_next = ord_next2;
     }
     if (p.prof && tid == 0) atomicAdd((unsigned long long*)&p.prof[7], (unsigned long long)(clock64() - prof_tmpl0));
     if (tid == 0) {
@@ -1064,7 +1090,7 @@ int launch_binpack(Engine* e) {
   p.E = e->E; p.T = e->T; p.N = e->N; p.U = e->U;
   p.has_dyn = e->has_dynamic ? 1 : 0;
   for (int a = 0; a < CAE_MAX_RES; ++a) p.act_dim[a] = e->act_dim[a];
-  p.order = e->d_order; p.order_n = e->d_order_n; p.pre_code = e->d_pre_code; p.spec_sc = e->d_spec_sc; p.spec_dc = e->d_spec_dc;
+  p.order = e->d_order; p.order_n = e->d_order_n; p.grec = e->d_grec; p.pre_code = e->d_pre_code; p.spec_sc = e->d_spec_sc; p.spec_dc = e->d_spec_dc;
   p.tmpl_free = e->d_tmpl_free; p.tmpl_slots = e->d_tmpl_slots; p.max_nodes = e->d_max_nodes;
   p.pc_of = e->d_pc_of; p.port_conf = e->d_port_conf; p.c_free = e->d_c_free; p.c_slots = e->d_c_slots;
   p.node_count = e->d_counts2; p.pod_count = e->d_counts2 + e->T; p.sched = e->d_sched;

@@ -18,6 +18,20 @@ constexpr int FEAS_TW = 16;                // template words per thread block of
 
 void set_error(const std::string& msg);
 
+// Everything the estimator needs to know about a pending pod group, gathered once per load so that a thread block
+// fetches ONE contiguous record per group (cp.async, one group ahead) instead of chasing five dependent tables.
+struct alignas(16) GroupRec {
+  int32_t n, spec, sc, dc;            // pods, pod spec, static class, dynamic class (0 = plain)
+  uint32_t flags;                     // GREC_*
+  int32_t pad[3];
+  unsigned long long pconf, pbit;     // host-port sets the pod collides with / the bit of its own set
+  int64_t req[CAE_MAX_RES];           // request per ACTIVE resource dim
+  float rinv[CAE_MAX_RES];            // 1 / req (0 when the dim is not requested)
+};
+static_assert(sizeof(GroupRec) == 144, "GroupRec is fetched as nine 16-byte chunks");
+enum : uint32_t { GREC_HAS_PORTS = 1u, GREC_FEEDS = 2u, GREC_HOST_SPREAD = 4u };
+constexpr int ORDER_NOT_ON_FRESH = 1 << 30;   // order entry flag: the group's static filters fail on the SANITIZED template
+
 #define CAE_CUDA(expr)                                                                        \
   do {                                                                                        \
     cudaError_t _e = (expr);                                                                  \
@@ -129,6 +143,7 @@ struct Engine {
   int32_t* d_sched = nullptr;             // [T][E]
   int32_t* d_order = nullptr;             // [T][E]
   int32_t* d_order_n = nullptr;           // [T]
+  GroupRec* d_grec = nullptr;             // [E]
   double* d_score = nullptr;              // [T][E]
   int32_t* d_max_nodes = nullptr;         // [T]
   int32_t* d_pc_of = nullptr;             // [num_port_lists] compact id of a pending pod's port list, -1 otherwise
@@ -171,6 +186,7 @@ int launch_port_conflicts(Engine* e, int num_port_lists);
 int launch_feasibility(Engine* e, bool want_reasons);
 int launch_group_feasibility(Engine* e);
 int launch_order(Engine* e);
+int launch_group_records(Engine* e);     // GroupRec[E] (after the class / counter tables of a load)
 int launch_pack(Engine* e);      // round-1 estimator kernel (pack.cu): kept for A/B runs and the filter pass
 int launch_binpack(Engine* e);   // K3: block-per-template estimator (binpack.cu)
 struct FilterLaunch {

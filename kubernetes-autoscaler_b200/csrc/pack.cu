@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(PACK_WARPS * 32, PACK_MIN_BLOCKS) pack_kernel(
     };
 
     for (int gi = 0; gi < n_groups; ++gi) {
-      const int g = FM ? 0 : p.order[(size_t)t * p.E + gi];
+      const int g = FM ? 0 : (p.order[(size_t)t * p.E + gi] & ~ORDER_NOT_ON_FRESH);
       const int pb = FM ? p.fm_run_off[gi] : o.group_off[g];
       int n = (FM ? p.fm_run_off[gi + 1] : o.group_off[g + 1]) - pb;
       const int spec = o.pend_spec[FM ? p.fm_pods[pb] : pb];
