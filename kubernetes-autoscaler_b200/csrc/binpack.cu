@@ -723,35 +723,115 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
         };
 
         BP_PROF_END(2);
-        // ---- hostname spread with the global minimum pinned at 0: closed form ----
+        // ---- capacity form: every counter of the group is either a per-node capacity or a budget ----
+        // Hostname counters (each node is its own domain): a spread constraint whose global minimum is pinned at 0
+        // admits (maxSkew - self - count) / weight + 1 pods on a node, an anti-affinity / existing-anti-affinity
+        // counter one pod (none if the domain already holds a match).  Counters on any other key see ONE domain for
+        // all added nodes (the template's value), so they bound the number of pods the group can place at all.
+        // Then the per-pod loop of the reference is the round-robin closed form over capacities, cut at the budget.
         BP_PROF_BEGIN();
         bool fast = false;
-        if (nq == 1 && wd.kind[0] == Q_PTS && wd.host[0] && !need_log && wd.minv[0] == 0) {
-          const int w0 = wd.wown[0], self0 = wd.self[0], ms0 = wd.maxskew[0], boff0 = wd.boff[0], k0 = wd.k[0], qid0 = wd.qid[0];
-          // skew capacity of a node whose domain holds c matching pods and counts placements iff `counted`
-          auto skew_cap = [&](int c, bool counted) -> int {
-            if (c + self0 > ms0) return 0;                       // filtering.go:352 with minMatchNum = 0
-            if (!counted || w0 == 0) return INT_MAX;
-            return (ms0 - self0 - c) / w0 + 1;
+        {
+          int hp = -1;           // the hostname spread constraint, if any
+          bool any_z = false, ok = true;
+          for (int q = 0; q < nq; ++q) {
+            if (wd.host[q]) {
+              if (wd.kind[q] == Q_PTS) { if (hp >= 0) ok = false; hp = q; }
+              else if (wd.kind[q] == Q_AFF) ok = false;
+            } else any_z = true;
+          }
+          // the fallback of :186-205 places onto cluster nodes, whose other-key domains differ: per-pod loop
+          if (hp >= 0 && (any_z || wd.minv[hp] != 0)) ok = false;
+          // capacity a hostname counter puts on a node whose domain (slot sl, -1 = label missing) holds c matches
+          auto hq_cap = [&](int q, int sl, int c, bool counted) -> int {
+            if (wd.kind[q] == Q_PTS) {
+              if (sl < 0) return 0;                                          // filtering.go:329 missing label
+              if (c + wd.self[q] > wd.maxskew[q]) return 0;                  // filtering.go:352 with minMatchNum = 0
+              if (!counted) return INT_MAX;
+              return (wd.maxskew[q] - wd.self[q] - c) / wd.wown[q] + 1;
+            }
+            if (sl >= 0 && c > 0) return 0;                                  // interpodaffinity/filtering.go:352-379
+            return (counted && sl >= 0) ? 1 : INT_MAX;
           };
+          // caps of node x (any node of the simulation) from the hostname counters, spread and inter-pod apart
+          auto h_caps = [&](int x, int& cap_pts, int& cap_ipa) {
+            cap_pts = INT_MAX; cap_ipa = INT_MAX;
+            for (int q = 0; q < nq; ++q) {
+              if (!wd.host[q]) continue;
+              const int sl = slot_of(q, x);
+              const int c = sl >= 0 ? rd_cnt(q, sl) : 0;
+              const int v = hq_cap(q, sl, c, wd.wown[q] > 0 && elig_of(q, x));
+              if (wd.kind[q] == Q_PTS) cap_pts = v; else cap_ipa = min(cap_ipa, v);
+            }
+          };
+          // a FRESH node reads the defaults of its new hostname domain
+          int Spts_new = INT_MAX, Sipa_new = INT_MAX;
+          for (int q = 0; q < nq; ++q) {
+            if (!wd.host[q]) continue;
+            const int v = hq_cap(q, 0, wd.elig_new[q] ? wd.dsw[q] : 0, wd.wown[q] > 0 && wd.elig_new[q]);
+            if (wd.kind[q] == Q_PTS) Spts_new = v; else Sipa_new = min(Sipa_new, v);
+          }
+          // ---- budget of the other-key counters (uniform: all added nodes sit in the template's domain) ----
+          int B = INT_MAX;
+          if (ok && any_z) {
+            bool aff_any = false, pods_exist = true, aff_missing = false;
+            long long aff_tot = 0;
+            for (int q = 0; q < nq && ok; ++q) {
+              if (wd.host[q]) continue;
+              const int kind = wd.kind[q], sl = wd.tslot[q], w = wd.wown[q];
+              const int c = sl >= 0 ? rd_cnt(q, sl) : 0;
+              const bool counted = w > 0 && wd.elig_new[q] && sl >= 0;
+              if (wd.elig_new[q] && wd.dsw[q] != 0) { ok = false; break; }   // adding a node moves the counter (DaemonSet pods match)
+              if (kind == Q_PTS) {
+                // ANY spread constraint refusing the last node sends a pod that names the hostname key in some constraint
+                // (even a ScheduleAnyway one) through the any-node fallback of :186-205: per-pod loop
+                if (host_spread) { ok = false; break; }
+                if (sl < 0) { B = 0; continue; }
+                const int prs = rd_pres(q, sl), self = wd.self[q], ms = wd.maxskew[q];
+                if (wd.elig_new[q] && prs == 0) { ok = false; break; }         // the domain appears with the first added node
+                long long lim;    // placements pass while count <= lim
+                if (wd.ndom[q] < wd.mindom[q]) lim = (long long)ms - self;                       // minimum treated as 0
+                else if (prs > 0) {
+                  // minimum over the OTHER present domains (constant while this group runs)
+                  if (c > wd.minv[q] || wd.nmin[q] > 1) lim = (long long)wd.minv[q] + ms - self;
+                  else if (wd.ndom[q] == 1) lim = LLONG_MAX;                                     // the only domain: skew 0
+                  else { ok = false; break; }                                                    // unique minimum: needs the runner-up
+                  if (self > ms) lim = -1;
+                } else lim = wd.ndom[q] == 0 ? LLONG_MAX : (long long)wd.minv[q] + ms - self;    // domain not counted at all
+                if (c > lim) B = 0;
+                else if (counted && lim != LLONG_MAX) B = (int)min((long long)B, (lim - c) / w + 1);
+              } else if (kind == Q_AFF) {
+                aff_any = true;
+                if (sl < 0) aff_missing = true;
+                if (c <= 0) pods_exist = false;
+                aff_tot += wd.tot[q];
+              } else {
+                if (sl >= 0 && c > 0) B = 0;
+                else if (counted) B = min(B, 1);
+              }
+            }
+            if (ok && aff_any) {
+              if (aff_missing) B = 0;
+              else if (!pods_exist) { if (aff_tot == 0 && wd.aff_self) ok = false; else B = 0; }   // first-pod escape hatch: per-pod loop
+            }
+          }
           bool caps_done = false;
-          // capacities of the cluster nodes for this pod (static filters, ports, resources, skew) -> kc[x];
-          // returns "a present empty domain exists whose only eligible node can never take this pod"
+          // capacities of the cluster nodes for this pod (static filters, ports, resources, hostname counters) -> kc[x];
+          // returns "a present empty domain of the spread constraint exists whose only eligible node can never take this pod"
           auto cluster_caps = [&]() -> bool {
             ensure_cluster();
             int blocked = 0;
             for (int x = tid; x < N; x += TPB) {
-              int k = 0;
               const bool stat_ok = (p.pre_code[(size_t)sc * p.U + x] & 0x0F) == 0 && !o.node_unschedulable[x];
               const int rc = stat_ok ? res_cap_c(x, n) : 0;
-              const int dm = d.dom[(size_t)k0 * NT + x];
-              const bool el = d.elig[(size_t)qid0 * p.U + x] != 0;
-              if (dm >= 0) {
-                const int c = d.base_cnt[boff0 + dm];
-                if (rc > 0) k = min(rc, skew_cap(c, el));
-                if (el && c == 0 && rc == 0 && d.base_pres[boff0 + dm] == 1) blocked = 1;
+              int cp, ci;
+              h_caps(x, cp, ci);
+              const int k_other = min(rc, ci);
+              g_kc[x] = min(k_other, cp);
+              if (k_other == 0 && hp >= 0) {
+                const int sl = slot_of(hp, x);
+                if (sl >= 0 && elig_of(hp, x) && rd_cnt(hp, sl) == 0 && rd_pres(hp, sl) == 1) blocked = 1;
               }
-              g_kc[x] = k;
             }
             long long z = 0;
             blk_sum_ll_max<NW>(S, par, z, blocked);
@@ -759,26 +839,35 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
             BP_PROF_COUNT(14, 1);
             return blocked > 0;
           };
-          if (w0 == 0 || wd.nmin[0] > n) fast = true;
-          else if (N > 0) fast = cluster_caps();
-          if (fast) {
-            const int c_new = wd.elig_new[0] ? wd.dsw[0] : 0;
-            const int S_new = skew_cap(c_new, wd.elig_new[0] != 0);
-            int m_last = 0;   // pods of this group on the last added node
+          if (ok && hp >= 0 && !(wd.wown[hp] == 0 || wd.nmin[hp] > n)) ok = N > 0 ? cluster_caps() : false;   // is the minimum pinned?
+          if (ok) {
+            fast = true;
+            const bool uni = !need_log;   // no other group feeds these counters: every added node reads the defaults
+            int b = B;                    // pods the budget still admits
+            int m_last = 0;               // pods of this group on the last added node
+            const int S_new = min(Spts_new, Sipa_new);
             // ---- tryToScheduleOnExistingNodes ----
-            if (n_new > 0 && static_new && S_new > 0) {
+            if (n_new > 0 && static_new && min(n, b) > 0 && (!uni || S_new > 0)) {
               if (tid == 0) S.mlast = 0;
               const int s = last_index >= N ? last_index - N : 0;
-              const int lastj = n_new - 1;
+              const int lastj = n_new - 1, want = min(n, b);
               int got, newly, last_dist;
-              round_robin(n_new, s, n,
-                          [&](int i) { return min(res_cap_a(i, n), S_new); },
+              round_robin(n_new, s, want,
+                          [&](int i) {
+                            const int k = res_cap_a(i, want);
+                            if (k <= 0) return 0;
+                            if (uni) return min(k, S_new);
+                            int cp, ci;
+                            h_caps(Neff + i, cp, ci);
+                            return min(k, min(cp, ci));
+                          },
                           [&](int i) -> int32_t& { return akc(i); },
                           [&](int i) -> int32_t& { return apr(i); },
                           [&](int i, int m) { if (i == lastj) S.mlast = m; return book_a(i, m); }, got, newly, last_dist);
               placed += got;
               nodes_with_pods += newly;
               n -= got;
+              if (b != INT_MAX) b -= got;
               if (last_dist >= 0) {
                 int jl = s + last_dist;
                 if (jl >= n_new) jl -= n_new;
@@ -812,29 +901,40 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
             // ---- tryToScheduleOnNewNodes ----
             if (n > 0 && new_nodes_available) {
               bool cluster_done = false;
-              if (n_new > 0) {
+              if (hp >= 0 && host_spread && n_new > 0) {
                 // why the last node refuses the next pod (default plugin order): static, ports, fit, then skew
                 const int jl = n_new - 1;
                 bool skew = static_new && !(apo(jl) & pconf) && asl(jl) >= 1;
 #pragma unroll
                 for (int a = 0; a < A; ++a) skew = skew && !(req[a] > 0 && req[a] > afr(a, jl));
-                skew = skew && (c_new + (wd.elig_new[0] ? m_last * w0 : 0) + self0 > ms0);
-                if (skew && host_spread) { cluster_phase(); cluster_done = true; }
+                const int c_last = uni ? (wd.elig_new[hp] ? wd.dsw[hp] : 0) : rd_cnt(hp, slot_of(hp, Neff + jl));
+                skew = skew && (c_last + (wd.elig_new[hp] ? m_last * wd.wown[hp] : 0) + wd.self[hp] > wd.maxskew[hp]);
+                if (skew) { cluster_phase(); cluster_done = true; }
               }
               if (n > 0) {
                 const bool stop = (n_new > 0) && !asch(n_new - 1);  // last node still empty (:212)
-                if (!stop) {
-                  const int k_res = fresh_cap(n);
-                  const int k_new = min(k_res, S_new);
-                  // a full fresh node refuses the next pod for skew iff the skew capacity binds before ports / fit
-                  const bool fresh_skew = k_new > 0 && S_new < fresh_cap(INT_MAX);
-                  if (k_new > 0 && fresh_skew && host_spread && !cluster_done) {
+                const int npl = min(n, b);                          // pods the budget still admits
+                if (stop) {
+                } else if (npl == 0) {
+                  add_new_nodes(0, false);             // the node is added, the pod fails on it (:235-240)
+                } else {
+                  const int k_new = min(fresh_cap(npl), S_new);
+                  // a full fresh node refuses the next pod for skew iff the skew capacity binds before ports / fit / inter-pod affinity
+                  const bool fresh_skew = hp >= 0 && k_new > 0 && Spts_new < fresh_cap(INT_MAX) && Spts_new <= Sipa_new;
+                  const int n_all = n;
+                  n = npl;
+                  if (fresh_skew && host_spread && !cluster_done) {
                     add_new_nodes(k_new, true);        // the first fresh node fills ...
                     if (n > 0 && new_nodes_available) {
                       cluster_phase();                 // ... then the fallback drains the cluster nodes ...
                       if (n > 0) add_new_nodes(k_new, false);   // ... and further nodes take the rest
                     }
                   } else add_new_nodes(k_new, false);
+                  const int done = npl - n;
+                  n = n_all - done;
+                  if (b != INT_MAX) b -= done;
+                  // the budget ran out with pods left: the next pod fails on the last node and on one more fresh node
+                  if (k_new > 0 && n > 0 && b == 0 && new_nodes_available && n_new > 0 && asch(n_new - 1)) add_new_nodes(0, false);
                 }
               }
             }
