@@ -70,6 +70,7 @@ struct BpShared {
   GroupDyn wd;
   int flag[DYN_MAX_Q];        // counters whose minimum must be recomputed
   long long rl[2][32];
+  long long rb[2][32][CAE_MAX_RES];   // refresh of the per-template capacity bounds
   int ri[2][32][3];
   int hist[BP_HIST + 1];      // #nodes per capacity value (closed-form lap count)
   int t, L, rem, pre_s, log_n, overflow, newly, need_log, mlast;
@@ -79,6 +80,11 @@ __device__ __forceinline__ int bp_wsum(int v) { return __reduce_add_sync(0xfffff
 __device__ __forceinline__ long long bp_wsum_ll(long long v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ long long bp_wmax_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
 __device__ __forceinline__ int bp_wmax(int v) { return __reduce_max_sync(0xffffffffu, v); }
@@ -260,6 +266,36 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
     const int col_new = N + p.T + t;  // universe column of the sanitized template
     int n_new = 0, nodes_with_pods = 0, pods_total = 0, last_index = 0;
     bool new_nodes_available = true, cl_init = false;
+    // Upper bounds of what ANY added node still has (free only shrinks, so a stale bound stays valid): a group whose
+    // request exceeds them skips its pass over the open nodes; tightened whenever such a pass finds no room at all.
+    int64_t maxfree[A1];
+    int maxslots = INT_MIN;
+#pragma unroll
+    for (int a = 0; a < A; ++a) maxfree[a] = LLONG_MIN;
+    auto refresh_bounds = [&]() {
+      long long mf[A1];
+      int msl = INT_MIN;
+#pragma unroll
+      for (int a = 0; a < A; ++a) mf[a] = LLONG_MIN;
+      for (int j = tid; j < n_new; j += TPB) {
+        msl = max(msl, asl(j));
+#pragma unroll
+        for (int a = 0; a < A; ++a) mf[a] = max(mf[a], (long long)afr(a, j));
+      }
+      msl = bp_wmax(msl);
+#pragma unroll
+      for (int a = 0; a < A; ++a) mf[a] = bp_wmax_ll(mf[a]);
+      if (lane == 0) {
+        S.ri[par][warp][0] = msl;
+#pragma unroll
+        for (int a = 0; a < A; ++a) S.rb[par][warp][a] = mf[a];
+      }
+      __syncthreads();
+      maxslots = bp_wmax(lane < NW ? S.ri[par][lane][0] : INT_MIN);
+#pragma unroll
+      for (int a = 0; a < A; ++a) maxfree[a] = bp_wmax_ll(lane < NW ? S.rb[par][lane][a] : LLONG_MIN);
+      par ^= 1;
+    };
     const int n_groups = p.order_n[t];
 
     auto log_append = [&](int x, int spec, int cnt) {  // any thread
@@ -441,6 +477,9 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
       const unsigned long long pconf = rc.pconf;  // port sets this pod collides with
       const unsigned long long pbit = rc.pbit;
       const bool feeds = (rc.flags & GREC_FEEDS) != 0;
+      bool can_existing = n_new > 0 && static_new && maxslots >= 1;   // some added node may still take this pod
+#pragma unroll
+      for (int a = 0; a < A; ++a) can_existing = can_existing && !(req[a] > 0 && req[a] > maxfree[a]);
       int placed = 0;
 
       // spare capacity of node x for this pod by NodePorts + NodeResourcesFit alone (pod slots, free resources)
@@ -525,6 +564,11 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
         }
         if (k_new > 0) { nodes_with_pods += add; placed += fill; n -= fill; }
         n_new += add;
+        if (add > 0) {
+          maxslots = max(maxslots, tslots);
+#pragma unroll
+          for (int a = 0; a < A; ++a) maxfree[a] = max(maxfree[a], tfree[a]);
+        }
         __syncthreads();
       };
 
@@ -532,7 +576,7 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
         // ======================= plain group: closed form =======================================
         BP_PROF_COUNT(8, 1);
         BP_PROF_BEGIN();
-        if (n_new > 0 && static_new) {
+        if (can_existing) {
           const int s = last_index >= N ? last_index - N : 0;  // first added node in cyclic scan order
           int got, newly, last_dist;
           round_robin(n_new, s, n,
@@ -548,7 +592,7 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
             if (jl >= n_new) jl -= n_new;
             last_index = (N + jl + 1) % (N + n_new);
           }
-          __syncthreads();
+          if (got == 0) refresh_bounds(); else __syncthreads();
         }
         BP_PROF_END(0);
         BP_PROF_BEGIN();
@@ -558,6 +602,8 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
           if (!stop) add_new_nodes(fresh_cap(n), false);
         }
         BP_PROF_END(1);
+      } else if (!new_nodes_available && !can_existing) {
+        // no node may be added any more and no added node has room: every pod of the group fails at once
       } else {
         // ======================= dynamic group ===================================================
         const bool host_spread = (rc.flags & GREC_HOST_SPREAD) != 0;
@@ -847,7 +893,7 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
             int m_last = 0;               // pods of this group on the last added node
             const int S_new = min(Spts_new, Sipa_new);
             // ---- tryToScheduleOnExistingNodes ----
-            if (n_new > 0 && static_new && min(n, b) > 0 && (!uni || S_new > 0)) {
+            if (can_existing && min(n, b) > 0 && (!uni || S_new > 0)) {
               if (tid == 0) S.mlast = 0;
               const int s = last_index >= N ? last_index - N : 0;
               const int lastj = n_new - 1, want = min(n, b);
@@ -873,7 +919,7 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
                 if (jl >= n_new) jl -= n_new;
                 last_index = (N + jl + 1) % (N + n_new);
               }
-              __syncthreads();
+              if (got == 0) refresh_bounds(); else __syncthreads();
               m_last = S.mlast;
             }
             // the pods the last node refuses for skew go to the cluster nodes in cyclic order (:186-205)
@@ -1047,13 +1093,16 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
             }
           }
           n_new += 1;       // recompute() below must see the new node's hostname domain
+          maxslots = max(maxslots, tslots);
+#pragma unroll
+          for (int a = 0; a < A; ++a) maxfree[a] = max(maxfree[a], tfree[a]);
           __syncthreads();
           run_flagged();
         };
 
         // ---- tryToScheduleOnExistingNodes: per pod, first passing added node in cyclic order ----
         BP_PROF_BEGIN();
-        while (n > 0 && n_new > 0) {
+        while (n > 0 && can_existing) {
           BP_PROF_COUNT(12, 1);
           const int s = last_index >= N ? last_index - N : 0;
           int best = INT_MAX, zero = 0;
@@ -1205,7 +1254,7 @@ int launch_binpack(Engine* e) {
   // shared window for the added nodes: per node A1 x int64 free + ports + slots + capacity + prefix + flag
   const size_t node_bytes = (size_t)A1 * 8 + 8 + 4 + 4 + 4 + 1;
   size_t smem = ((size_t)cap * node_bytes + 15) & ~(size_t)15;
-  const size_t smem_limit = (size_t)e->smem_optin > 4096 ? (size_t)e->smem_optin - 4096 : 0;   // static part + reserve
+  const size_t smem_limit = (size_t)e->smem_optin > 9216 ? (size_t)e->smem_optin - 9216 : 0;   // static part + reserve
   if (smem <= smem_limit) p.win = cap; else { p.win = 0; smem = 0; }
   const size_t Xg = (size_t)Neff + (p.win ? 0 : cap);
   int dmax = 1;
