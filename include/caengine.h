@@ -226,13 +226,31 @@ typedef struct cae_objects {
  * ---------------------------------------------------------------------------------------------- */
 typedef struct cae_engine cae_engine;
 
+/* cae_config.flags */
+#define CAE_CFG_PODS_PRESHARDED 1   /* world_size > 1: cae_objects holds ONLY this rank's pending pods (the caller sliced
+                                       pend_spec / group_off); the dense pass covers all of them, the histogram exchange
+                                       still runs over world_size ranks */
+#define CAE_CFG_GATES_REPORTED 2    /* feature_gates is filled in; cae_create answers status 1 when a gate the engine
+                                       hard-codes differs (the caller must then use the stock path) */
+/* cae_config.feature_gates: the scheduler feature gates the path reads (vendor/k8s.io/kubernetes/pkg/scheduler/framework/
+   plugins/feature/feature.go:27-52, read process-globally at plugin construction).  The engine implements:
+   NodeInclusionPolicyInPodTopologySpread ON (podtopologyspread/common.go:43-58), TaintTolerationComparisonOperators OFF
+   (Lt/Gt tolerations, api/core/v1/toleration.go:52-77), DRAExtendedResource OFF (noderesources/fit.go:208);
+   MatchLabelKeysInPodTopologySpread is resolved by the caller when it builds the selectors (either value is accepted). */
+#define CAE_GATE_NODE_INCLUSION_POLICY_IN_PTS 1
+#define CAE_GATE_TAINT_TOLERATION_COMPARISON_OPERATORS 2
+#define CAE_GATE_DRA_EXTENDED_RESOURCE 4
+#define CAE_GATE_MATCH_LABEL_KEYS_IN_PTS 8
+
 typedef struct cae_config {
   int32_t abi_version;
   int32_t device;          /* CUDA device ordinal */
   int32_t rank;            /* this process' shard index (pods for feasibility, templates for estimate) */
   int32_t world_size;      /* number of shards */
   int32_t want_reasons;    /* also produce the dense reason matrix in cae_feasibility */
-  int32_t reserved[11];
+  int32_t flags;           /* CAE_CFG_* */
+  int32_t feature_gates;   /* CAE_GATE_* as utilfeature.DefaultFeatureGate reports them on the Go side (with CAE_CFG_GATES_REPORTED) */
+  int32_t reserved[9];
 } cae_config;
 
 typedef struct cae_stats {

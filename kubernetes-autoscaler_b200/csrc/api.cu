@@ -236,6 +236,7 @@ static int do_load(Engine* e, const cae_objects* o) {
   e->p_end = (int)((int64_t)e->P * (rk + 1) / W);
   e->p_begin = (e->p_begin / 32) * 32;  // word-aligned shards so bit rows concatenate
   if (rk + 1 < W) e->p_end = (e->p_end / 32) * 32;
+  if (e->cfg.flags & CAE_CFG_PODS_PRESHARDED) { e->p_begin = 0; e->p_end = e->P; }   // the caller uploaded its own pod shard only
   e->Pl = e->p_end - e->p_begin;
   e->Plw = (e->Pl + 31) / 32;
   e->t_begin = (int)((int64_t)T * rk / W);
@@ -536,6 +537,14 @@ int32_t cae_create(const cae_config* cfg, cae_engine** out) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cae::set_error("no CUDA device: the engine has no CPU fallback");
     return -1;
+  }
+  if (cfg->flags & CAE_CFG_GATES_REPORTED) {
+    const int32_t g = cfg->feature_gates;
+    if (!(g & CAE_GATE_NODE_INCLUSION_POLICY_IN_PTS) || (g & CAE_GATE_TAINT_TOLERATION_COMPARISON_OPERATORS) || (g & CAE_GATE_DRA_EXTENDED_RESOURCE)) {
+      cae::set_error("feature gates differ from the ones the engine implements (NodeInclusionPolicyInPodTopologySpread on, "
+                     "TaintTolerationComparisonOperators off, DRAExtendedResource off)");
+      return 1;
+    }
   }
   Engine* e = new Engine();
   e->cfg = *cfg;

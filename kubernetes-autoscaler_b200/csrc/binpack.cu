@@ -157,7 +157,7 @@ __device__ __forceinline__ long long blk_sum_ll(BpShared& S, int& par, long long
 }
 
 #ifndef BP_MIN_CTAS
-#define BP_MIN_CTAS 3
+#define BP_MIN_CTAS 4
 #endif
 
 __device__ __forceinline__ void bp_cp_async16(void* smem_dst, const void* gmem_src) {

@@ -405,6 +405,24 @@ class EncodedObjects:
             raise RuntimeError("encoder does not fill ABI fields: %s" % missing)
         self.struct = s
 
+    def slice_pods(self, p_begin: int, p_end: int) -> "EncodedObjects":
+        """The same snapshot with only the pending pods [p_begin, p_end) (groups clipped to the range; every other table is
+        shared): what rank r of a pod-sharded dense pass uploads (CAE_CFG_PODS_PRESHARDED)."""
+        import copy
+        out = copy.copy(self)
+        out.arrays = dict(self.arrays)
+        go = np.clip(self.arrays["group_off"], p_begin, p_end) - p_begin
+        out.arrays["group_off"] = np.ascontiguousarray(go.astype(np.int32))
+        out.arrays["pend_spec"] = np.ascontiguousarray(self.arrays["pend_spec"][p_begin:p_end])
+        s = capi.cae_objects()
+        C.memmove(C.byref(s), C.byref(self.struct), C.sizeof(s))
+        s.num_pending = p_end - p_begin
+        for name, ctype in capi.cae_objects._fields_:
+            if name in ("group_off", "pend_spec"):
+                setattr(s, name, out.arrays[name].ctypes.data_as(ctype))
+        out.struct = s
+        return out
+
     # convenience
     @property
     def P(self) -> int:

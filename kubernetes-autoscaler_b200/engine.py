@@ -63,7 +63,8 @@ def shard_templates(T: int, rank: int, world_size: int) -> Tuple[int, int]:
 
 
 class Engine:
-    def __init__(self, device: int = 0, rank: int = 0, world_size: int = 1, want_reasons: bool = False) -> None:
+    def __init__(self, device: int = 0, rank: int = 0, world_size: int = 1, want_reasons: bool = False,
+                 pods_presharded: bool = False, feature_gates: Optional[int] = None) -> None:
         self.lib = capi.load_engine_lib()
         self.lib.cae_host_alloc.argtypes = [C.c_size_t]
         self.lib.cae_host_alloc.restype = C.c_void_p
@@ -73,6 +74,12 @@ class Engine:
         cfg.abi_version = capi.CONST["CAE_ABI_VERSION"]
         cfg.device, cfg.rank, cfg.world_size, cfg.want_reasons = device, rank, world_size, int(want_reasons)
         self.rank, self.world_size, self.want_reasons = rank, world_size, want_reasons
+        self.pods_presharded = pods_presharded
+        # the scheduler feature gates as the Go side would report them; default = the values the engine implements
+        gates = capi.CONST["CAE_GATE_NODE_INCLUSION_POLICY_IN_PTS"] | capi.CONST["CAE_GATE_MATCH_LABEL_KEYS_IN_PTS"] \
+            if feature_gates is None else int(feature_gates)
+        cfg.flags = capi.CONST["CAE_CFG_GATES_REPORTED"] | (capi.CONST["CAE_CFG_PODS_PRESHARDED"] if pods_presharded else 0)
+        cfg.feature_gates = gates
         h = C.c_void_p()
         self._check(self.lib.cae_create(C.byref(cfg), C.byref(h)))
         self.h = h
@@ -113,6 +120,8 @@ class Engine:
 
     # ---- shards -------------------------------------------------------------------------------
     def pod_shard(self, P: int) -> Tuple[int, int]:
+        if self.pods_presharded:   # the loaded objects hold this rank's pods only
+            return 0, P
         return shard_pods(P, self.rank, self.world_size)
 
     def template_shard(self, T: int) -> Tuple[int, int]:
