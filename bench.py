@@ -1,18 +1,25 @@
 #!/usr/bin/env python
 """bench.py — pod x node predicate evaluations/sec of the dense feasibility pass (BASELINE.json
-metric 1) on config C2: 100 000 pods x 1 000 templates, resources + taints/tolerations.
+metric 1) on config C2: 100 000 pods x 1 000 templates, resources + taints/tolerations,
+and the scale-up decision latency (metric 2) beside it.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 2]
 
 One "step" = one dense pass of the scale-up predicate path over the whole pending-pod batch:
 every pod (not only group exemplars) against every template through the Filter chain.
-  value        : whole-job evals/s with the snapshot already resident in HBM (device time, CUDA events)
-  e2e          : the same through the C-ABI with HOST buffers: cae_load (intern + H2D + class
-                 matrices) + cae_feasibility (kernel + D2H of the bit matrix and counts) per step
-  roofline     : feasibility_kernel's algorithmic bytes / its CUDA-event time vs the measured HBM peak
-  cpu_baseline : the CPU oracle (port of the Go reference) on the box's host cores, same workload
-N > 1 (torchrun): weak scaling — every rank owns 100 000 pods of an N x 100 000-pod snapshot, the
-per-template fit-count histogram int32[T] is all-reduced once per step over NCCL.
+  value            : whole-job evals/s with the snapshot already resident in HBM (device time, CUDA events)
+  e2e              : the same through the C-ABI with HOST buffers: cae_load (intern + H2D + class
+                     matrices) + cae_feasibility (kernel + D2H of the bit matrix and counts) per step
+  roofline         : the dense kernel's algorithmic bytes / its CUDA-event time vs the measured HBM peak
+  cpu_baseline     : the CPU oracle (port of the Go reference) on the box's host cores, same workload
+                     (rows for 1 thread, 4 threads = the reference's default parallelism, and all cores)
+  parity_checked   : the numbers timed were compared with the oracle (and, N > 1, with an NCCL all-reduce
+                     of the per-rank histograms) before the line was printed
+  decision_latency : load -> exemplar feasibility -> order -> Estimate() of every template -> expander
+                     (C3 on one GPU = the headline of metric 2; C4 template-sharded at every N, C5 at N = 8),
+                     with the estimator kernel's roofline and an oracle check of a template slice
+N > 1 (torchrun): weak scaling of the dense pass — every rank owns (and uploads) 100 000 pods of an
+N x 100 000-pod snapshot, the per-template fit-count histogram int32[T] is exchanged once per step.
 """
 import argparse
 import json
@@ -73,6 +80,35 @@ def _peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _host_cores():
+    """Threads this process can really use: the affinity mask, cut by a cgroup CPU quota if one is set."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            quota = int(q) / int(per)
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    if quota:
+        n = max(1, min(n, int(quota)))
+    return n
+
+
+def _config_dict(cfg, P1, T, world):
+    """The SAME dict in the engine's line and the reference arm's line."""
+    return {"workload": "%s; %d pods/GPU x %d templates, splitmix64 seed 0xCA5CA1E0+%d" % (cfg.name, P1, T, cfg.index),
+            "global_pods": P1 * world, "templates": T, "parallelism": "pods sharded x%d" % world,
+            "l2": "flushed between timed iterations (512 MiB memset on the engine's stream)",
+            "timing": "CUDA events on the engine's stream, queued behind the flush + a spin kernel (no host launch latency in the window)"}
+
+
 _W = {}
 
 
@@ -91,13 +127,19 @@ def _worker_run(job):
     return ev, time.perf_counter() - t0
 
 
+def _worker_counts(job):
+    p_range, t_range = job
+    reasons = _W["oracle"].feasibility_dense(_W["enc"], p_range=p_range, t_range=t_range)[0]
+    return t_range[0], (reasons == 0).sum(axis=1).astype(np.int64).tolist()
+
+
 def _worker_decide(job):
-    tb, te, cap = job
+    t, cap = job
     enc = _W["enc"]
     caps = np.full(enc.T, cap, np.int32)
     t0 = time.perf_counter()
-    _W["oracle"].estimate_all(enc, caps, t_range=(tb, te))
-    return time.perf_counter() - t0
+    nc, pc, _, _, ev = _W["oracle"].estimate_all(enc, caps, t_range=(t, t + 1))
+    return {"t": t, "nodes": int(nc[0]), "pods": int(pc[0]), "filter_evals": int(ev), "secs": time.perf_counter() - t0}
 
 
 def _worker_pid(_):
@@ -123,6 +165,165 @@ def _cpu_dense(pool, procs, p_range, t_range):
     return int(sum(r[0] for r in res)), time.perf_counter() - t0
 
 
+def _spread(n, k):
+    return sorted({int(round(i * (n - 1) / max(k - 1, 1))) for i in range(k)})
+
+
+def reference_arm(args, cfg, P1, T, metric):
+    """The reference's own CPU implementation of the path (the C++ port of the Go code: no Go toolchain here)."""
+    import multiprocessing as mp
+    from oracle import pyoracle
+    pyoracle.build()
+    cores = _host_cores()
+    if args.threads:
+        cores = max(1, min(cores, args.threads))
+    ctx = mp.get_context("fork")
+    if args.decision_templates is not None:
+        # metric 2 (SURVEY §8d): SchedulablePodGroups + Estimate per template, one template per job
+        templates = [int(x) for x in args.decision_templates.split(",") if x != ""]
+        with ctx.Pool(min(cores, max(len(templates), 1)), initializer=_worker_init, initargs=(args.config, P1, T)) as pool:
+            t0 = time.perf_counter()
+            rows = pool.map(_worker_decide, [(t, args.cap) for t in templates], chunksize=1)
+            wall = time.perf_counter() - t0
+        per = [r["secs"] for r in rows]
+        print(json.dumps({"impl": "reference", "decision": True, "templates": rows, "wall_s": wall,
+                          "cpu_seconds_per_template": float(np.mean(per)) if per else None, "cores": cores,
+                          "extrapolated_s_all_templates_on_these_cores": float(np.mean(per)) * T / max(min(cores, len(templates)), 1) if per else None,
+                          "kind": "port"}))
+        return
+    if args.counts_slice is not None:
+        # parity leg: per-template fit counts of a template slice over the pods [p_begin, p_end)
+        pb, pe, ts = args.counts_slice.split(":")
+        templates = [int(x) for x in ts.split(",")]
+        with ctx.Pool(min(cores, len(templates)), initializer=_worker_init, initargs=(args.config, P1, T)) as pool:
+            res = dict(pool.map(_worker_counts, [((int(pb), int(pe)), (t, t + 1)) for t in templates], chunksize=1))
+        print(json.dumps({"impl": "reference", "counts": {str(k): v[0] for k, v in res.items()}}))
+        return
+    P = P1
+    t_slice = min(T, 8 * cores)   # bounded sample per step: all pods x a template slice (~0.2 s of work per core)
+    with ctx.Pool(cores, initializer=_worker_init, initargs=(args.config, P1, T)) as pool:
+        _wait_workers(pool, cores)
+        for _ in range(2):
+            _cpu_dense(pool, cores, (0, P), (0, min(T, t_slice)))
+        evals = 0
+        secs = 0.0
+        for s in range(args.steps):
+            tb = (s * t_slice) % max(T - t_slice + 1, 1)
+            ev, dt = _cpu_dense(pool, cores, (0, P), (tb, tb + t_slice))
+            evals += ev
+            secs += dt
+    v = evals / secs
+    sample = "%d pods x %d templates per step (template slice of the full workload), %d steps" % (P, t_slice, args.steps)
+    print(json.dumps({
+        "impl": "reference", "metric": metric, "value": v, "unit": "evals/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": _config_dict(cfg, P1, T, max(args.gpus, 1)),
+        "note": "CPU oracle = C++ port of the Go reference (no Go toolchain in the image); the `l2` / `timing` keys of config describe the engine's arm",
+        "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def _reference_subprocess(extra, timeout=900):
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE")}
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference"] + extra,
+                         capture_output=True, text=True, timeout=timeout, env=env)
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def decision_run(torch, dist, Engine, synth, config, rank, world, local_rank, reps=4, cap=1000, check_templates=8):
+    """One full scale-up decision per rep on `config`: load (intern + H2D + class / counter tables), exemplar feasibility,
+    order, Estimate() of every template (templates sharded over the ranks), one all-reduce of int32[2T] + float64[T],
+    expander chain on the assembled vectors.  Wall time, max over ranks."""
+    enc = synth.generate(config)
+    eng = Engine(device=local_rank, rank=rank, world_size=world)
+    caps = np.full(enc.T, cap, np.int32)
+    counts_t = None
+    rows = []
+    nc = pc = mask = None
+    for rep in range(reps):
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        eng.load(enc)
+        t1 = time.perf_counter()
+        nc, pc, _, _ = eng.estimate_all(caps, want_sched=False, copy=False)
+        t2 = time.perf_counter()
+        if dist is not None:
+            from kubernetes_autoscaler_b200.engine import expander_chain
+            ptr, _ = eng.device_buffer(1)          # node_count | pod_count of this load, on the device
+
+            class _Wrap:
+                __cuda_array_interface__ = {"shape": (2 * enc.T,), "typestr": "<i4", "data": (ptr, False), "version": 3}
+            counts_t = torch.as_tensor(_Wrap(), device="cuda")
+            waste_t = torch.from_numpy(eng.waste_scores()).cuda()   # own rows, 0.0 elsewhere
+            dist.all_reduce(counts_t)                                # int32[2T]: node_count | pod_count
+            dist.all_reduce(waste_t)                                 # float64[T]: one non-zero contribution per row
+            both = counts_t.cpu().numpy()
+            nc, pc = both[:enc.T].copy(), both[enc.T:].copy()
+            mask = expander_chain([0, 1, 2], nc, pc, waste_t.cpu().numpy())
+        else:
+            mask, _ = eng.expander_best([0, 1, 2], nc, pc)         # least-waste, most-pods, least-nodes
+        t3 = time.perf_counter()
+        st = eng.stats()
+        row = [1e3 * (t3 - t0), 1e3 * (t1 - t0), 1e3 * (t2 - t1), st.estimate_ms, 1e3 * (t3 - t2)]
+        if dist is not None:
+            tt = torch.tensor(row, device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            row = [float(x) for x in tt]
+        if rep:
+            rows.append(row)
+    steps = int(eng.stats().estimate_group_steps)
+    if dist is not None:
+        tt = torch.tensor([steps], device="cuda", dtype=torch.int64)
+        dist.all_reduce(tt)
+        steps = int(tt[0])
+    nc, pc = np.array(nc), np.array(pc)
+    eng.close()
+    med = np.median(np.asarray(rows), axis=0)
+    out = {"workload": synth.CONFIGS[config].name + ", node cap %d per template" % cap, "config": config, "n_gpus": world,
+           "ms": float(med[0]), "load_ms": float(med[1]), "estimate_wall_ms": float(med[2]), "estimate_device_ms": float(med[3]),
+           "reduce_and_expander_ms": float(med[4]), "templates_sharded": world > 1,
+           "nodes_total": int(nc.sum()), "pods_scheduled_total": int(pc.sum()), "options_surviving_chain": int(mask.sum()),
+           "group_steps": steps}
+    if rank != 0:
+        return out
+    # ---- estimator kernel roofline: the engine's compulsory HBM traffic (order rows in, per-group records in, per-group
+    #      scheduled counts + two counters out; the node state lives in shared memory) vs the §8(d) model of the per-pod scans
+    E = enc.E
+    alg = enc.T * E * 4 + steps * 144 + enc.T * E * 4 + enc.T * 8
+    peak, peak_src = _peak_hbm()
+    ach = alg / (out["estimate_device_ms"] * 1e-3) / 1e9 * (1.0 if world == 1 else 1.0)
+    out["roofline"] = {"kernel": "binpack_kernel (+ order_kernel, group_reason_kernel in the same window)", "bound": "hbm",
+                       "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                       "algorithmic_bytes": int(alg), "peak_source": peak_src,
+                       "note": "node state is shared-memory resident: the kernel is bound by issue slots / barrier latency per "
+                               "(template, group) step, not by HBM; see profiles/r02_summary.md for the ncu page"}
+    # ---- oracle on a template slice: parity of the timed result + the CPU arm of metric 2 + the §8(d) byte model
+    try:
+        tsel = _spread(enc.T, check_templates)
+        ref = _reference_subprocess(["--config", str(config), "--decision-templates", ",".join(str(t) for t in tsel), "--cap", str(cap)])
+        ok = all(int(nc[r["t"]]) == r["nodes"] and int(pc[r["t"]]) == r["pods"] for r in ref["templates"])
+        out["parity_checked"] = bool(ok)
+        out["parity_templates"] = tsel
+        out["cpu_baseline"] = {k: ref[k] for k in ("cpu_seconds_per_template", "cores", "wall_s", "kind",
+                                                   "extrapolated_s_all_templates_on_these_cores")}
+        ev = float(np.mean([r["filter_evals"] for r in ref["templates"]]))
+        model = enc.T * (E * 320 + ev * 128)
+        out["roofline"]["model_8d"] = {"bytes": model, "definition": "sum_t (E_t x 320 B + filter evaluations of the reference's per-pod "
+                                       "any-node scans x 128 B), evaluations from the oracle's trace on the slice, extrapolated to T templates",
+                                       "effective_GBps": model / (out["estimate_device_ms"] * 1e-3) / 1e9,
+                                       "note": "above the HBM peak = the closed forms never perform those scans"}
+        if not ok:
+            out["parity_error"] = [(r["t"], int(nc[r["t"]]), r["nodes"], int(pc[r["t"]]), r["pods"]) for r in ref["templates"]]
+    except Exception as ex:
+        out["parity_checked"] = False
+        out["parity_error"] = repr(ex)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -132,10 +333,13 @@ def main():
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--pods", type=int, default=None)
     ap.add_argument("--templates", type=int, default=None)
-    ap.add_argument("--decision", action="store_true", help="reference arm: time full scale-up decisions (oracle) instead")
-    ap.add_argument("--no-decision", action="store_true", help="engine arm: skip the secondary decision-latency figure")
+    ap.add_argument("--threads", type=int, default=0, help="reference arm: cap the host processes (0 = all usable cores)")
+    ap.add_argument("--decision-templates", default=None, help="reference arm: time / report full Estimate() of these templates (oracle)")
+    ap.add_argument("--counts-slice", default=None, help="reference arm: pb:pe:t0,t1,.. per-template fit counts (parity leg)")
+    ap.add_argument("--cap", type=int, default=1000)
+    ap.add_argument("--no-decision", action="store_true", help="engine arm: skip the decision-latency figures")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
-                    help="N>1: how the int32[T] fit histogram is reduced: fused P2P atomics in the kernel's last block, or NCCL")
+                    help="N>1: how the int32[T] fit histogram is reduced: fused P2P exchange in the kernel's last block, or NCCL")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -146,58 +350,13 @@ def main():
     cfg = synth.CONFIGS[args.config]
     P1 = args.pods or cfg.pods
     T = args.templates or cfg.templates
-    workload = "%s; %d pods/GPU x %d templates, splitmix64 seed 0xCA5CA1E0+%d" % (cfg.name, P1, T, cfg.index)
     metric = "pod x node predicate evals/sec"
 
     # ------------------------------------------------------------------ reference arm (CPU oracle)
     if args.impl == "reference":
         if rank != 0:
             return
-        import multiprocessing as mp
-        from oracle import pyoracle
-        pyoracle.build()
-        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        P = P1
-        # bounded sample per step: all pods x a template slice (~0.2 s of work per core)
-        t_slice = min(T, 8 * cores)
-        if args.decision:
-            # metric 2: SchedulablePodGroups + Estimate per template, one template per job
-            with mp.get_context("fork").Pool(cores, initializer=_worker_init, initargs=(args.config, P1, T)) as pool:
-                _wait_workers(pool, cores)
-                k = min(T, 2 * cores)
-                t0 = time.perf_counter()
-                per = pool.map(_worker_decide, [(t, t + 1, 1000) for t in range(k)], chunksize=1)
-                wall = time.perf_counter() - t0
-            print(json.dumps({"impl": "reference", "decision": True, "templates_timed": k, "wall_s": wall,
-                              "cpu_seconds_per_template": float(np.mean(per)), "cores": cores,
-                              "extrapolated_s_all_templates": wall * T / k, "kind": "port"}))
-            return
-        with mp.get_context("fork").Pool(cores, initializer=_worker_init, initargs=(args.config, P1, T)) as pool:
-            _wait_workers(pool, cores)
-            for _ in range(2):
-                _cpu_dense(pool, cores, (0, P), (0, min(T, t_slice)))
-            evals = 0
-            secs = 0.0
-            for s in range(args.steps):
-                tb = (s * t_slice) % max(T - t_slice + 1, 1)
-                ev, dt = _cpu_dense(pool, cores, (0, P), (tb, tb + t_slice))
-                evals += ev
-                secs += dt
-
-        class _E:
-            pass
-        enc = _E()
-        enc.P = P
-        v = evals / secs
-        sample = "%d pods x %d templates per step (template slice of the full workload), %d steps" % (enc.P, t_slice, args.steps)
-        print(json.dumps({
-            "impl": "reference", "metric": metric, "value": v, "unit": "evals/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": {"workload": workload, "note": "CPU oracle = C++ port of the Go reference (no Go toolchain in the image)"},
-            "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}))
+        reference_arm(args, cfg, P1, T, metric)
         return
 
     # ------------------------------------------------------------------ engine arm
@@ -212,12 +371,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()
     torch.cuda.set_device(local_rank)
-    from kubernetes_autoscaler_b200.engine import Engine
+    from kubernetes_autoscaler_b200.engine import Engine, shard_pods, unpack_bits
 
-    enc = synth.generate(args.config, pods=P1 * world, templates=T)   # weak scaling: P1 pods per rank
-    eng = Engine(device=local_rank, rank=rank, world_size=world, want_reasons=False)
+    enc_all = synth.generate(args.config, pods=P1 * world, templates=T)   # weak scaling: P1 pods per rank
+    pb, pe = shard_pods(enc_all.P, rank, world)
+    enc = enc_all.slice_pods(pb, pe) if world > 1 else enc_all           # a rank uploads ITS pods only
+    eng = Engine(device=local_rank, rank=rank, world_size=world, want_reasons=False, pods_presharded=world > 1)
     eng.load(enc)
-    pb, pe = eng.pod_shard(enc.P)
     Pl = pe - pb
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
@@ -298,11 +458,49 @@ def main():
     # the histogram (CUDA events on torch's stream), max over ranks
     allreduce_ms = float(np.mean(ar_ms)) if ar_ms else 0.0
     step_ms = kern_ms + allreduce_ms
+    step_stats = [float(np.min(dev_ms)), float(np.median(dev_ms)), float(np.percentile(dev_ms, 99)), float(np.max(dev_ms))]
     if dist is not None:
-        tt = torch.tensor([step_ms, kern_ms], device="cuda", dtype=torch.float64)
+        tt = torch.tensor([step_ms, kern_ms] + step_stats, device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         step_ms, kern_ms = float(tt[0]), float(tt[1])
+        step_stats = [float(x) for x in tt[2:]]
     value = (P1 * world) * T / (step_ms * 1e-3)
+
+    # ---- parity of what was just timed -------------------------------------------------------------------
+    # the result of one more resident step: the fused (or all-reduced) histogram must equal the sum over ranks of the
+    # popcounts of each rank's bit rows; rank 0's rows and counts are compared with the oracle on a template slice
+    parity = {"checked": False}
+    try:
+        step_resident()
+        torch.cuda.synchronize()
+        bits, _, cnt = eng.feasibility()
+        if count_t is not None:
+            dist.all_reduce(count_t)
+            torch.cuda.synchronize()
+            cnt = count_t.cpu().numpy()
+        local = unpack_bits(bits, Pl).sum(axis=1).astype(np.int64)
+        total = local.copy()
+        if dist is not None:
+            tt = torch.from_numpy(local).cuda()
+            dist.all_reduce(tt)                                # NCCL sum of the per-rank histograms
+            total = tt.cpu().numpy()
+        ok_hist = bool(np.array_equal(np.asarray(cnt, np.int64), total))
+        ok_oracle = True
+        tsel = _spread(T, 32)
+        if rank == 0:
+            ref = _reference_subprocess(["--config", str(args.config), "--pods", str(P1 * world), "--templates", str(T),
+                                         "--counts-slice", "%d:%d:%s" % (pb, pe, ",".join(str(t) for t in tsel))], timeout=600)
+            ok_oracle = all(int(local[t]) == int(ref["counts"][str(t)]) for t in tsel)
+        parity = {"checked": bool(ok_hist and ok_oracle), "histogram_equals_sum_of_rank_popcounts": ok_hist,
+                  "rank0_counts_equal_oracle_on_templates": tsel if ok_oracle else False,
+                  "how": "popcount of every rank's bit rows, NCCL all_reduce(sum) across ranks vs the %s histogram; oracle dense pass on rank 0's pods x 32 templates"
+                         % ("fused peer-exchange" if fused else ("NCCL" if world > 1 else "kernel's"))}
+        if dist is not None:
+            tt = torch.tensor([1.0 if parity["checked"] else 0.0], device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MIN)
+            parity["checked"] = bool(tt[0] > 0.5)
+    except Exception as ex:
+        parity = {"checked": False, "error": repr(ex)}
 
     # ---- e2e through the C ABI with host buffers: load (H2D) + pass + D2H of bits/counts ----------
     e2e_ms = []
@@ -329,6 +527,37 @@ def main():
         e2e_step = float(tt[0])
     samples = _clock_sampler_stop(sampler)
 
+    # ---- the dense pass where it is not a launch-latency test: C3 (5 x 10^8 cells) on one GPU ------------
+    dense_large = None
+    if world == 1 and not args.no_decision:
+        try:
+            enc3 = synth.generate(3)
+            eng.load(enc3)
+            ms3 = []
+            for i in range(6):
+                flush_l2()
+                eng.lib.cae_feasibility(eng.h, None, None, None)
+                torch.cuda.synchronize()
+                if i:
+                    ms3.append(eng.stats().feasibility_ms)
+            dense_large = {"workload": synth.CONFIGS[3].name, "cells": enc3.P * enc3.T, "ms": float(np.median(ms3)),
+                           "evals_per_s": enc3.P * enc3.T / (float(np.median(ms3)) * 1e-3)}
+            eng.load(enc)
+        except Exception as ex:
+            dense_large = {"error": repr(ex)}
+    eng.close()
+
+    # ---- metric 2: scale-up decision latency ------------------------------------------------------------
+    decisions = []
+    if not args.no_decision:
+        plan = [3, 4] if world == 1 else ([4, 5] if world >= 8 else [4])
+        for c in plan:
+            try:
+                d = decision_run(torch, dist, Engine, synth, c, rank, world, local_rank)
+            except Exception as ex:
+                d = {"config": c, "error": repr(ex)}
+            decisions.append(d)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -338,77 +567,74 @@ def main():
     # algorithmic bytes of the dense kernel: per pod W packed-rank words + 2 class ids,
     # per template W words, the bit matrix, the fit histogram
     req = enc.arrays["ps_req"][np.unique(enc.arrays["pend_spec"])]
-    bits = 0
+    nbits = 0
     for a in range(req.shape[1]):
         dv = len(np.unique(req[:, a][req[:, a] > 0]))
         if dv:
-            bits += int(dv).bit_length() + 1
-    Wd = max(1, (bits + 31) // 32)
+            nbits += int(dv).bit_length() + 1
+    Wd = max(1, (nbits + 31) // 32)
     alg_bytes = Pl * (4 * Wd + 8) + T * 4 * Wd + Pl * T // 8 + 4 * T
     peak, peak_src = _peak_hbm()
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     traffic = None
+    traffic_src = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload, one `ncu --set full` capture
         tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k1_traffic.json")))
         if args.config == 2 and P1 == 100_000 and T == 1000:
             traffic = int(tj["dram__bytes_read.sum"]) + int(tj["dram__bytes_write.sum"])
+            traffic_src = "profiles/r01_k1_traffic.json (one `ncu --set full` capture of this kernel on this workload; not re-measured in this run)"
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "feasibility_lut_kernel", "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
-                "note": "shuffle / shared-memory issue bound: ~1 bit of compulsory HBM traffic per evaluation (DESIGN.md §K1)"}
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": "feasibility_lut_kernel", "algorithmic_bytes": alg_bytes,
+                "peak_source": peak_src,
+                "note": "the contract's HBM fraction; the kernel needs ~1 bit of DRAM traffic per evaluation and is bound by "
+                        "shared-memory wavefronts + fixed launch latency (see roofline_secondary and DESIGN.md)"}
+    # the kernel's own stated bound: shared-memory wavefronts (ncu l1tex__data_pipe_lsu_wavefronts_mem_shared of the capture above,
+    # 1.356 M per launch on C2) at one wavefront per SM per cycle
+    sm_mhz = None
+    cs = _clocks_summary(samples)
+    if cs.get("sm_mhz"):
+        sm_mhz = cs["sm_mhz"]
+    roofline2 = None
+    if args.config == 2 and P1 == 100_000 and T == 1000 and sm_mhz:
+        wf = 1.356e6
+        floor_us = wf / 148.0 / (sm_mhz * 1e6) * 1e6
+        roofline2 = {"bound": "shared-memory wavefronts", "wavefronts_per_launch": wf, "floor_us": floor_us,
+                     "measured_us": kern_ms * 1e3, "frac": floor_us / (kern_ms * 1e3)}
 
     # ---- CPU baseline: the oracle on this box's cores, bounded sample of the same workload ---------------
-    # (a fresh process: the oracle's worker pool must fork before any CUDA context exists)
+    # (fresh processes: the oracle's worker pool must fork before any CUDA context exists)
     cpu = {"value": None, "unit": "evals/s", "cores": 0, "kind": "port", "sample": "failed"}
     try:
-        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "4",
-                              "--config", str(args.config), "--pods", str(P1), "--templates", str(T)],
-                             capture_output=True, text=True, timeout=600, env={k: v for k, v in os.environ.items()
-                                                                              if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
-        cpu = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        base = ["--steps", "4", "--config", str(args.config), "--pods", str(P1), "--templates", str(T)]
+        cpu = _reference_subprocess(base, timeout=600)["cpu_baseline"]
+        rows = []
+        for th in (1, 4):
+            r = _reference_subprocess(base + ["--threads", str(th), "--steps", "2"], timeout=600)["cpu_baseline"]
+            rows.append({"threads": r["cores"], "value": r["value"]})
+        rows.append({"threads": cpu["cores"], "value": cpu["value"]})
+        cpu["rows"] = rows
+        cpu["note"] = "1 thread = --predicate-parallelism=1 (every reference test), 4 = the reference's default (config/flags/flags.go:234), " \
+                      "all = every core the cgroup grants, templates split across processes"
     except Exception as ex:  # the bench line must still be printed
         cpu["sample"] = "failed: %r" % (ex,)
 
-    # ---- metric 2: scale-up decision latency @ 100k pods x 5k templates (C3), one GPU ---------------------
-    decision = None
-    if world == 1 and not args.no_decision:
-        try:
-            enc3 = synth.generate(3)
-            caps = np.full(enc3.T, 1000, np.int32)
-            ms = []
-            for i in range(4):
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                eng.load(enc3)                                                 # intern + H2D + class / counter tables
-                nc, pc, _, _ = eng.estimate_all(caps, want_sched=False, copy=False)  # exemplar feasibility, order, pack
-                mask, _ = eng.expander_best([0, 1, 2], nc, pc)                 # least-waste, most-pods, least-nodes
-                if i:
-                    ms.append(1e3 * (time.perf_counter() - t0))
-            st = eng.stats()
-            decision = {"workload": synth.CONFIGS[3].name + ", node cap 1000 per template", "ms": float(np.median(ms)),
-                        "estimate_device_ms": st.estimate_ms, "nodes_total": int(nc.sum()), "pods_scheduled_total": int(pc.sum()),
-                        "options_surviving_chain": int(mask.sum()), "cpu_baseline": None}
-            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--decision", "--config", "3"],
-                                 capture_output=True, text=True, timeout=900,
-                                 env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
-            decision["cpu_baseline"] = json.loads(out.stdout.strip().splitlines()[-1])
-        except Exception as ex:
-            decision = {"error": repr(ex)}
-
+    headline_decision = decisions[0] if decisions else None
     print(json.dumps({
         "metric": metric, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": workload, "global_pods": P1 * world, "templates": T, "parallelism": "pods sharded x%d" % world,
-                   "l2": "flushed between timed iterations (512 MiB memset on the engine's stream)",
-                   "timing": "CUDA events on the engine's stream, queued behind the flush + a spin kernel (no host launch latency in the window)"},
+        "config": _config_dict(cfg, P1, T, world),
         "kernel_ms": kern_ms, "allreduce_ms": allreduce_ms,
-        "step_ms_rank0": {"min": float(np.min(dev_ms)), "median": float(np.median(dev_ms)), "max": float(np.max(dev_ms))},
-        "collective": ("none" if world == 1 else ("fused P2P atomics over NVLink (peer memory)" if fused else "NCCL all_reduce int32[T]")), "wall_ms_per_step": float(np.mean(wall_ms)), "clocks": _clocks_summary(samples),
+        "step_ms_max_over_ranks": {"min": step_stats[0], "median": step_stats[1], "p99": step_stats[2], "max": step_stats[3]},
+        "collective": ("none" if world == 1 else ("fused exchange over NVLink peer memory inside the kernel" if fused else "NCCL all_reduce int32[T]")),
+        "wall_ms_per_step": float(np.mean(wall_ms)), "clocks": cs,
         "e2e": {"value": (P1 * world) * T / (e2e_step * 1e-3), "unit": "evals/s", "ms_per_step": e2e_step,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "decision_latency": decision}))
+        "gpu_launches": int(launches), "parity_checked": bool(parity.get("checked")), "parity": parity,
+        "roofline": roofline, "roofline_secondary": roofline2, "cpu_baseline": cpu,
+        "dense_pass_large": dense_large, "decision_latency": headline_decision, "decisions": decisions}))
     if dist is not None:
         dist.destroy_process_group()
 

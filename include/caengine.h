@@ -261,7 +261,8 @@ typedef struct cae_stats {
   double h2d_ms, d2h_ms;
   int64_t h2d_bytes, d2h_bytes;
   int64_t kernel_launches;  /* kernels launched by the engine since creation */
-  int64_t reserved[8];
+  int64_t estimate_group_steps; /* (template, schedulable group) pairs the last cae_estimate_all walked on this rank */
+  int64_t reserved[7];
 } cae_stats;
 
 /* Replaces: estimator.NewBinpackingNodeEstimator / EstimatorBuilder (estimator/estimator.go:59-75). */

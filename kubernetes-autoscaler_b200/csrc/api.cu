@@ -670,11 +670,18 @@ int32_t cae_estimate_all(cae_engine* h, const int32_t* max_nodes, int32_t* node_
   cudaEventRecord(e->ev1, e->stream);
   int32_t pack_status = 0;
   CAE_CUDA(cudaMemcpyAsync(&pack_status, e->d_work_counter + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+  std::vector<int32_t> order_n_host(T);
+  CAE_CUDA(cudaMemcpyAsync(order_n_host.data(), e->d_order_n, sizeof(int32_t) * T, cudaMemcpyDeviceToHost, e->stream));
   if (node_count) CAE_CUDA(cudaMemcpyAsync(node_count, e->d_counts2, sizeof(int32_t) * T, cudaMemcpyDeviceToHost, e->stream));
   if (pod_count) CAE_CUDA(cudaMemcpyAsync(pod_count, e->d_counts2 + T, sizeof(int32_t) * T, cudaMemcpyDeviceToHost, e->stream));
   if (sched_count && E) CAE_CUDA(cudaMemcpyAsync(sched_count, e->d_sched, sizeof(int32_t) * (size_t)T * E, cudaMemcpyDeviceToHost, e->stream));
   if (order && E) CAE_CUDA(cudaMemcpyAsync(order, e->d_order, sizeof(int32_t) * (size_t)T * E, cudaMemcpyDeviceToHost, e->stream));
   CAE_CUDA(cudaStreamSynchronize(e->stream));
+  {
+    int64_t steps = 0;
+    for (int t = e->t_begin; t < e->t_end; ++t) steps += order_n_host[t];
+    e->stats.estimate_group_steps = steps;
+  }
   if (order && E)   // the device rows carry a flag bit per entry (ORDER_NOT_ON_FRESH); padding stays -1
     for (size_t i = 0, nn = (size_t)T * E; i < nn; ++i) if (order[i] >= 0) order[i] &= ~cae::ORDER_NOT_ON_FRESH;
   float ms = 0;
