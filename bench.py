@@ -414,7 +414,7 @@ def main():
     def flush_l2():
         with torch.cuda.stream(estream):
             flush.zero_()                                      # > L2: evicts everything the previous step left
-            torch.cuda._sleep(300_000)                         # ~150 us spin: covers the host's enqueue of the step
+            torch.cuda._sleep(2_000_000)                       # ~1 ms spin: covers the host's enqueue of the step on every rank
             if dist is not None:
                 dist.all_reduce(sync_t)                        # device-side barrier on the engine's stream: the ranks' timed
                                                                # windows open together (a host barrier cannot align queued work)

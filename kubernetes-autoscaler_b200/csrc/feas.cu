@@ -108,6 +108,20 @@ struct K1Args {
   uint8_t* reasons;
 };
 
+__device__ __forceinline__ int k1_ld_acquire_sys(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void k1_red_release_sys(int32_t* p, int v) {
+  asm volatile("red.release.sys.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long k1_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // ---- epilogue shared by both variants -------------------------------------------------------------------
 // s_cnt holds this block's counts for templates t0 .. t0+K1_TCHUNK.  The LAST block of the chunk to arrive
 // publishes fit_count = accumulator and zeroes the accumulator for the next launch.  With a peer exchange
@@ -143,24 +157,23 @@ __device__ __forceinline__ void k1_finish(const K1Args& a, const PeerPush& pp, c
   }
   __syncthreads();
   if (!s_flag) return;
-  // the block that published the LAST chunk owns the complete local histogram: all-gather it
+  // the block that published the LAST chunk owns the complete local histogram: all-gather it.
+  // Chain per step: peer stores -> block barrier -> ONE release-add per peer (cumulative over the barrier, no separate
+  // system fence, no returned value) -> acquire-poll of the own arrival counter (own memory) -> sum.
   __threadfence();
   for (int r = 0; r < pp.world; ++r) {
     int32_t* dst = pp.data[r] + (size_t)pp.rank * Engine::PEER_CAP;
     for (int t = tid; t < a.T; t += nthreads) dst[t] = __ldcg(&a.fit_count[t]);
   }
-  __threadfence_system();
   __syncthreads();
-  if (tid < pp.world) atomicAdd_system(pp.arrive[tid], 1);
+  if (tid < pp.world) k1_red_release_sys(pp.arrive[tid], 1);
   if (tid == 0) {
-    volatile int32_t* arr = pp.arrive[pp.rank];
-    const long long c0 = clock64();
-    int ok = 1;
-    while (*arr < pp.target) {
-      if (clock64() - c0 > 4000000000ll) { ok = 0; break; }  // ~2 s: a peer died; fail instead of hanging the GPU
-      __nanosleep(100);
+    const int32_t* arr = pp.arrive[pp.rank];
+    const unsigned long long t0ns = k1_globaltimer();
+    int ok = 1, spins = 0;
+    while (k1_ld_acquire_sys(arr) < pp.target) {
+      if ((++spins & 1023) == 0 && k1_globaltimer() - t0ns > 2000000000ull) { ok = 0; break; }  // 2 s of wall clock: a peer died; fail instead of hanging the GPU
     }
-    __threadfence_system();
     s_flag = ok;
     if (!ok) atomicExch(pp.status, 1);
     *pp.done_ctr = 0;
@@ -491,6 +504,10 @@ constexpr int K1_LUT_MAX_ROWS = FEAS_LUT_MAX_ROWS;
 
 int launch_feasibility(Engine* e, bool want_reasons) {
   if (e->Pl == 0 || e->Tw == 0) return 0;
+  if (e->peer_world > 1 && e->T > Engine::PEER_CAP) {   // never hand back a local histogram as if it were the global one
+    set_error("fused histogram exchange: more templates than the exchange buffer holds (use the NCCL all-reduce of cae_device_buffer(0))");
+    return 1;
+  }
   const PeerPush pp = peer_push_args(e);
   const K1Args a = k1_args(e);
   if (!e->force_bitslice && e->lut_rows <= K1_LUT_MAX_ROWS) {
