@@ -313,7 +313,7 @@ int32_t cae_estimate_all(cae_engine* e, const int32_t* max_nodes, int32_t* node_
  * node_count > 0).  Replaces: expander.Filter.BestOptions for least-waste / most-pods / least-nodes
  * (expander/waste/waste.go:37-73, mostpods/mostpods.go:33-54, leastnodes/leastnodes.go:35-61) and
  * the chain (expander/factory/chain.go:36-45) up to, not including, the random fallback. */
-enum cae_expander { CAE_EXP_LEAST_WASTE = 0, CAE_EXP_MOST_PODS = 1, CAE_EXP_LEAST_NODES = 2 };
+enum cae_expander { CAE_EXP_LEAST_WASTE = 0, CAE_EXP_MOST_PODS = 1, CAE_EXP_LEAST_NODES = 2, CAE_EXP_PRICE = 3, CAE_EXP_PRIORITY = 4 };
 int32_t cae_expander_best(cae_engine* e, const int32_t* chain, int32_t chain_len,
                           const int32_t* node_count, const int32_t* pod_count,
                           const int32_t* sched_count, /* [T][E]; NULL = use the device-resident result of
@@ -350,6 +350,41 @@ int32_t cae_filter_schedulable(cae_engine* e, const int32_t* pod_order, int32_t 
 int32_t cae_waste_scores(cae_engine* e, double* waste_score /* [T] */);
 int32_t cae_expander_chain(const int32_t* chain, int32_t chain_len, int32_t num_templates, const int32_t* node_count,
                            const int32_t* pod_count, const double* waste_score, uint8_t* best_mask /* [T] */);
+
+/* Price expander (expander/price/price.go:90-183).  The cloud provider's PricingModel and the preferred-node provider
+ * stay on the Go side; the shim evaluates them once per tick into plain vectors, the engine computes the option score
+ *   score = suppressedUnfitness x (NodePrice x nodeCount + stabilization) / (sum of PodPrice + stabilization)  [x 2 if !Exist()]
+ * in float64 exactly as Go evaluates it on amd64 (no fused multiply-add; the pod prices are ADDED ONE POD AT A TIME in
+ * scheduling order, price.go:128-135; math.Tanh restated from Go's pure-Go tanh.go / exp.go, price.go:146).
+ *   node_price [T]            pricingModel.NodePrice(template node, now, now + 1h)
+ *   pod_price [num_podspecs]  pricingModel.PodPrice of a pod of that spec (pods of a group are equivalent)
+ *   unfitness [T] or NULL     NodeUnfitness(preferredNode, node); NULL = SimpleNodeUnfitness (preferred.go:87-92) from
+ *                             preferred_cpu_milli and the template's cpu capacity
+ *   has_gpu [T]               gpu.NodeHasGpu(GPULabel, node): unfitness is overridden by 1000 (price.go:150-153)
+ *   exists [T]                NodeGroup.Exist(); a group yet to be created costs x 2 (price.go:157-159)
+ *   price_error [T] or NULL   NodePrice / PodPrice returned an error: the option is skipped (price.go:120,130) */
+typedef struct cae_price_inputs {
+  const double* node_price;
+  const double* pod_price;
+  const double* unfitness;
+  const uint8_t* has_gpu;
+  const uint8_t* exists;
+  const uint8_t* price_error;
+  double stabilization_price;
+  int64_t preferred_cpu_milli;
+} cae_price_inputs;
+/* score [T] of every option (0.0 where node_count == 0).  node_count / sched_count / order as returned by
+ * cae_estimate_all; all three NULL = score the device-resident result of the last cae_estimate_all (rows of other ranks
+ * come back 0.0, so a sum all-reduce assembles the vector like cae_waste_scores). */
+int32_t cae_price_scores(cae_engine* e, const cae_price_inputs* in, const int32_t* node_count, const int32_t* sched_count,
+                         const int32_t* order, double* score);
+/* The filter chain over assembled vectors, with the price and priority filters:
+ *   price_score / price_error  from cae_price_scores / cae_price_inputs (needed when the chain holds CAE_EXP_PRICE)
+ *   priority [T]               highest priority of the ConfigMap whose regexp list matches the node group id, < 0 = the id
+ *                              matches no entry (expander/priority/priority.go:119-165; the regexps are the shim's) */
+int32_t cae_expander_chain_ex(const int32_t* chain, int32_t chain_len, int32_t num_templates, const int32_t* node_count,
+                              const int32_t* pod_count, const double* waste_score, const double* price_score,
+                              const uint8_t* price_error, const int32_t* priority, uint8_t* best_mask /* [T] */);
 
 int32_t cae_get_stats(cae_engine* e, cae_stats* out);
 

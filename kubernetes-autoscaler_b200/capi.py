@@ -87,6 +87,10 @@ class cae_stats(C.Structure):
     _fields_ = _parse_struct(_SRC, "cae_stats")
 
 
+class cae_price_inputs(C.Structure):
+    _fields_ = _parse_struct(_SRC, "cae_price_inputs")
+
+
 def declared_functions() -> List[str]:
     """Names of every function the header declares (used by the symbol-export test)."""
     return sorted(set(re.findall(r"\b(cae_\w+)\s*\(", _SRC)))
@@ -154,6 +158,10 @@ def load_engine_lib() -> C.CDLL:
     lib.cae_filter_schedulable.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                            C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.cae_filter_schedulable.restype = C.c_int32
+    lib.cae_price_scores.argtypes = [C.c_void_p, P(cae_price_inputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.cae_price_scores.restype = C.c_int32
+    lib.cae_expander_chain_ex.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 7
+    lib.cae_expander_chain_ex.restype = C.c_int32
     lib.cae_waste_scores.argtypes = [C.c_void_p, C.c_void_p]
     lib.cae_waste_scores.restype = C.c_int32
     lib.cae_expander_chain.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -489,7 +489,9 @@ using cae::Engine;
 // (expander/factory/chain.go:36-45) — it keeps the reference's order-dependent quirks
 // (waste.go:58-65: equality tested before the nil/less-than branch).
 static int32_t run_expander_chain(const int32_t* chain, int32_t chain_len, int T, const int32_t* node_count,
-                                  const int32_t* pod_count, const double* waste, uint8_t* best_mask) {
+                                  const int32_t* pod_count, const double* waste, uint8_t* best_mask,
+                                  const double* price = nullptr, const uint8_t* price_error = nullptr,
+                                  const int32_t* priority = nullptr) {
   std::vector<int> opts;
   for (int t = 0; t < T; ++t) if (node_count[t] > 0) opts.push_back(t);
   for (int c = 0; c < chain_len; ++c) {
@@ -514,6 +516,23 @@ static int32_t run_expander_chain(const int32_t* chain, int32_t chain_len, int T
         if (node_count[t] == least) { best.push_back(t); continue; }
         if (node_count[t] < least) { least = node_count[t]; best.assign(1, t); }
       }
+    } else if (chain[c] == CAE_EXP_PRICE) {   // expander/price/price.go:166-173
+      if (!price) { cae::set_error("price filter without price scores"); return -2; }
+      double best_score = 0.0;
+      for (int t : opts) {
+        if (price_error && price_error[t]) continue;
+        if (best.empty() || best_score == price[t]) { best.push_back(t); best_score = price[t]; }
+        else if (best_score > price[t]) { best.assign(1, t); best_score = price[t]; }
+      }
+    } else if (chain[c] == CAE_EXP_PRIORITY) {   // expander/priority/priority.go:119-165
+      if (!priority) { cae::set_error("priority filter without priorities"); return -2; }
+      int max_prio = -1;
+      for (int t : opts) {
+        if (priority[t] < 0 || priority[t] < max_prio) continue;   // not in the configuration / lower priority
+        if (priority[t] > max_prio) { max_prio = priority[t]; best.clear(); }
+        best.push_back(t);
+      }
+      if (best.empty()) best = opts;   // "no priorities info found for any of the expansion options. No options filtered."
     } else { cae::set_error("unknown expander filter"); return 1; }
     opts.swap(best);
     if (opts.size() == 1) break;
@@ -753,6 +772,62 @@ int32_t cae_expander_chain(const int32_t* chain, int32_t chain_len, int32_t num_
                            const int32_t* pod_count, const double* waste_score, uint8_t* best_mask) {
   if (!chain || !node_count || !pod_count || !waste_score || num_templates < 0) return -2;
   return run_expander_chain(chain, chain_len, num_templates, node_count, pod_count, waste_score, best_mask);
+}
+
+int32_t cae_price_scores(cae_engine* h, const cae_price_inputs* in, const int32_t* node_count, const int32_t* sched_count,
+                         const int32_t* order, double* score) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (!e || !e->loaded || !in || !score || !in->node_price || !in->pod_price) { cae::set_error("cae_price_scores: bad arguments"); return -2; }
+  if ((node_count == nullptr) != (sched_count == nullptr) || (node_count == nullptr) != (order == nullptr)) {
+    cae::set_error("cae_price_scores: node_count, sched_count and order must be given together");
+    return -2;
+  }
+  cudaSetDevice(e->cfg.device);
+  const int T = e->T, E = std::max(e->E, 1), S = e->num_podspecs;
+  if (T == 0) return 0;
+  // one staging blob: node_price | pod_price | unfitness | score, then the byte vectors
+  const size_t nd = (size_t)T + S + (in->unfitness ? T : 0) + T;
+  double* d_f = nullptr;
+  uint8_t* d_b = nullptr;
+  CAE_CUDA(cudaMalloc(&d_f, nd * sizeof(double)));
+  CAE_CUDA(cudaMalloc(&d_b, (size_t)3 * T));
+  cae_price_inputs dev = *in;
+  size_t off = 0;
+  CAE_CUDA(cudaMemcpyAsync(d_f + off, in->node_price, sizeof(double) * T, cudaMemcpyHostToDevice, e->stream)); dev.node_price = d_f + off; off += T;
+  CAE_CUDA(cudaMemcpyAsync(d_f + off, in->pod_price, sizeof(double) * S, cudaMemcpyHostToDevice, e->stream)); dev.pod_price = d_f + off; off += S;
+  if (in->unfitness) { CAE_CUDA(cudaMemcpyAsync(d_f + off, in->unfitness, sizeof(double) * T, cudaMemcpyHostToDevice, e->stream)); dev.unfitness = d_f + off; off += T; }
+  double* d_score = d_f + off;
+  dev.has_gpu = dev.exists = dev.price_error = nullptr;
+  if (in->has_gpu) { CAE_CUDA(cudaMemcpyAsync(d_b, in->has_gpu, T, cudaMemcpyHostToDevice, e->stream)); dev.has_gpu = d_b; }
+  if (in->exists) { CAE_CUDA(cudaMemcpyAsync(d_b + T, in->exists, T, cudaMemcpyHostToDevice, e->stream)); dev.exists = d_b + T; }
+  int32_t *d_nc = e->d_counts2, *d_sched = e->d_sched, *d_order = e->d_order, *d_tmp = nullptr;
+  if (node_count) {
+    CAE_CUDA(cudaMalloc(&d_tmp, sizeof(int32_t) * ((size_t)T + (size_t)2 * T * E)));
+    d_nc = d_tmp; d_sched = d_tmp + T; d_order = d_sched + (size_t)T * E;
+    CAE_CUDA(cudaMemcpyAsync(d_nc, node_count, sizeof(int32_t) * T, cudaMemcpyHostToDevice, e->stream));
+    CAE_CUDA(cudaMemcpyAsync(d_sched, sched_count, sizeof(int32_t) * (size_t)T * E, cudaMemcpyHostToDevice, e->stream));
+    CAE_CUDA(cudaMemcpyAsync(d_order, order, sizeof(int32_t) * (size_t)T * E, cudaMemcpyHostToDevice, e->stream));
+  }
+  // with caller-supplied rows every template is scored; the device-resident result only holds this rank's shard
+  const int tb = e->t_begin, te = e->t_end;
+  if (node_count) { e->t_begin = 0; e->t_end = T; }
+  const int rc = cae::launch_price(e, dev, d_nc, d_sched, d_order, d_score);
+  e->t_begin = tb; e->t_end = te;
+  if (rc) return rc;
+  CAE_CUDA(cudaMemcpyAsync(score, d_score, sizeof(double) * T, cudaMemcpyDeviceToHost, e->stream));
+  CAE_CUDA(cudaStreamSynchronize(e->stream));
+  cudaFree(d_f); cudaFree(d_b);
+  if (d_tmp) cudaFree(d_tmp);
+  return 0;
+}
+
+int32_t cae_expander_chain_ex(const int32_t* chain, int32_t chain_len, int32_t num_templates, const int32_t* node_count,
+                              const int32_t* pod_count, const double* waste_score, const double* price_score,
+                              const uint8_t* price_error, const int32_t* priority, uint8_t* best_mask) {
+  if (!chain || !node_count || !pod_count || num_templates < 0) return -2;
+  for (int c = 0; c < chain_len; ++c)
+    if (chain[c] == CAE_EXP_LEAST_WASTE && !waste_score) { cae::set_error("least-waste filter without waste scores"); return -2; }
+  return run_expander_chain(chain, chain_len, num_templates, node_count, pod_count, waste_score, best_mask, price_score, price_error, priority);
 }
 
 int32_t cae_get_stats(cae_engine* h, cae_stats* out) {

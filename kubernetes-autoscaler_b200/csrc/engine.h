@@ -197,6 +197,8 @@ struct FilterLaunch {
   uint8_t *class_mark, *ctrl_over;
 };
 int launch_filter(Engine* e, const FilterLaunch& f);
+int launch_price(Engine* e, const cae_price_inputs& in_dev, const int32_t* d_node_count, const int32_t* d_sched, const int32_t* d_order,
+                 double* d_score);
 int launch_expander(Engine* e, const int32_t* chain, int chain_len, const int32_t* d_node_count,
                     const int32_t* d_pod_count, const int32_t* d_sched, uint8_t* d_mask, double* d_waste);
 

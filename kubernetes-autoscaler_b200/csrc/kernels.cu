@@ -12,6 +12,8 @@
 #include <cfloat>
 #include <climits>
 
+#include <math_constants.h>
+
 #include "engine.h"
 
 namespace cae {
@@ -293,6 +295,104 @@ __global__ void waste_kernel(DevObjects o, int E, int T, int N, const int32_t* _
     double wm = __ddiv_rn(__ll2double_rn(amem - mem), __ll2double_rn(amem));
     waste[t] = nc > 0 ? __dadd_rn(wc, wm) : 0.0;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Price expander score (expander/price/price.go:90-183) in float64, operation by operation as Go evaluates it on
+// amd64 (no FMA contraction: every product / sum is its own IEEE operation).
+// ------------------------------------------------------------------------------------------------
+// math.Exp, pure-Go path (src/math/exp.go: exp + expmulti; argument reduction by ln2 in two pieces, degree-5 minimax)
+__device__ double go_exp(double x) {
+  const double Ln2Hi = 6.93147180369123816490e-01, Ln2Lo = 1.90821492927058770002e-10, Log2e = 1.44269504088896338700e+00;
+  const double Overflow = 7.09782712893383973096e+02, Underflow = -7.45133219101941108420e+02, NearZero = 1.0 / (1 << 28);
+  if (x != x || x == CUDART_INF) return x;
+  if (x == -CUDART_INF) return 0.0;
+  if (x > Overflow) return CUDART_INF;
+  if (x < Underflow) return 0.0;
+  if (-NearZero < x && x < NearZero) return __dadd_rn(1.0, x);
+  int k = 0;
+  if (x < 0) k = (int)__dadd_rn(__dmul_rn(Log2e, x), -0.5);
+  else if (x > 0) k = (int)__dadd_rn(__dmul_rn(Log2e, x), 0.5);
+  const double hi = __dadd_rn(x, -__dmul_rn((double)k, Ln2Hi));
+  const double lo = __dmul_rn((double)k, Ln2Lo);
+  const double P1 = 1.66666666666666657415e-01, P2 = -2.77777777770155933842e-03, P3 = 6.61375632143793436117e-05,
+               P4 = -1.65339022054652515390e-06, P5 = 4.13813679705723846039e-08;
+  const double r = __dadd_rn(hi, -lo);
+  const double t = __dmul_rn(r, r);
+  // c := r - t*(P1+t*(P2+t*(P3+t*(P4+t*P5))))
+  double poly = __dadd_rn(P4, __dmul_rn(t, P5));
+  poly = __dadd_rn(P3, __dmul_rn(t, poly));
+  poly = __dadd_rn(P2, __dmul_rn(t, poly));
+  poly = __dadd_rn(P1, __dmul_rn(t, poly));
+  const double c = __dadd_rn(r, -__dmul_rn(t, poly));
+  // y := 1 - ((lo - (r*c)/(2-c)) - hi)
+  const double y = __dadd_rn(1.0, -__dadd_rn(__dadd_rn(lo, -__ddiv_rn(__dmul_rn(r, c), __dadd_rn(2.0, -c))), -hi));
+  return ldexp(y, k);   // exact scaling
+}
+// math.Tanh, pure-Go path (src/math/tanh.go, Cephes rational approximation below 0.625)
+__device__ double go_tanh(double x) {
+  const double MAXLOG = 8.8029691931113054295988e+01;
+  double z = fabs(x);
+  if (z > 0.5 * MAXLOG) return x < 0 ? -1.0 : 1.0;
+  if (z >= 0.625) {
+    const double s = go_exp(__dmul_rn(2.0, z));
+    z = __dadd_rn(1.0, -__ddiv_rn(2.0, __dadd_rn(s, 1.0)));
+    return x < 0 ? -z : z;
+  }
+  if (x == 0) return x;
+  const double P0 = -9.64399179425052238628e-1, P1 = -9.92877231001918586564e1, P2 = -1.61468768441708447952e3;
+  const double Q0 = 1.12811678491632931402e2, Q1 = 2.23548839060100448583e3, Q2 = 4.84406305325125486048e3;
+  const double s = __dmul_rn(x, x);
+  // z = x + x*s*((P0*s+P1)*s+P2)/(((s+Q0)*s+Q1)*s+Q2)
+  const double num = __dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(P0, s), P1), s), P2);
+  const double den = __dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(s, Q0), s), Q1), s), Q2);
+  return __dadd_rn(x, __ddiv_rn(__dmul_rn(__dmul_rn(x, s), num), den));
+}
+
+__global__ void price_kernel(DevObjects o, int E, int T, int N, int t_begin, int t_end, cae_price_inputs in,
+                             const int32_t* __restrict__ node_count, const int32_t* __restrict__ sched,
+                             const int32_t* __restrict__ order, double* __restrict__ score) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  double out = 0.0;
+  const int nc = (t >= t_begin && t < t_end) ? node_count[t] : 0;
+  if (nc > 0) {
+    const double total_node = __dmul_rn(in.node_price[t], (double)nc);
+    double total_pod = 0.0;    // totalPodPrice += podPrice, one pod at a time, in scheduling order (price.go:128-135)
+    for (int gi = 0; gi < E; ++gi) {
+      int g = order[(size_t)t * E + gi];
+      if (g < 0) break;
+      g &= ~ORDER_NOT_ON_FRESH;
+      const int c = sched[(size_t)t * E + g];
+      if (c <= 0) continue;
+      const double p = in.pod_price[o.pend_spec[o.group_off[g]]];
+      for (int i = 0; i < c; ++i) total_pod = __dadd_rn(total_pod, p);
+    }
+    const double sub = __ddiv_rn(__dadd_rn(total_node, in.stabilization_price), __dadd_rn(total_pod, in.stabilization_price));
+    double unfit;
+    if (in.unfitness) unfit = in.unfitness[t];
+    else {   // SimpleNodeUnfitness: math.Max(pref/eval, eval/pref)
+      const double pref = (double)in.preferred_cpu_milli, ev = (double)o.node_cap_cpu[N + t];
+      const double a = __ddiv_rn(pref, ev), b = __ddiv_rn(ev, pref);
+      unfit = (a != a || b != b) ? a + b : (a > b ? a : b);
+    }
+    // (nodeUnfitness-1.0)*(1.0-math.Tanh(float64(option.NodeCount-1)/15.0)) + 1.0
+    double supp = __dadd_rn(__dmul_rn(__dadd_rn(unfit, -1.0), __dadd_rn(1.0, -go_tanh(__ddiv_rn((double)(nc - 1), 15.0)))), 1.0);
+    if (in.has_gpu && in.has_gpu[t]) supp = 1000.0;
+    out = __dmul_rn(supp, sub);
+    if (in.exists && !in.exists[t]) out = __dmul_rn(out, 2.0);
+  }
+  score[t] = out;
+}
+
+int launch_price(Engine* e, const cae_price_inputs& in_dev, const int32_t* d_node_count, const int32_t* d_sched, const int32_t* d_order,
+                 double* d_score) {
+  if (e->T == 0) return 0;
+  price_kernel<<<(e->T + 63) / 64, 64, 0, e->stream>>>(e->dobj, e->E, e->T, e->N, e->t_begin, e->t_end, in_dev, d_node_count, d_sched,
+                                                        d_order, d_score);
+  e->stats.kernel_launches++;
+  CAE_KERNEL_OK();
+  return 0;
 }
 
 int launch_expander(Engine* e, const int32_t*, int, const int32_t* d_node_count, const int32_t*,

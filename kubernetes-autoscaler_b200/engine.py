@@ -191,6 +191,38 @@ class Engine:
         self._check(self.lib.cae_waste_scores(self.h, waste.ctypes.data_as(C.c_void_p)))
         return waste
 
+    def price_scores(self, node_price, pod_price, stabilization_price: float, preferred_cpu_milli: int = 0, unfitness=None,
+                     has_gpu=None, exists=None, node_count=None, sched=None, order=None) -> np.ndarray:
+        """Price expander score per option (expander/price/price.go).  node_count/sched/order None = the device-resident
+        result of the last estimate_all."""
+        T = self.enc.T
+        keep = []
+
+        def arr(a, dt):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dt)
+            keep.append(a)
+            return a
+        pin = capi.cae_price_inputs()
+        f64p, u8p = C.POINTER(C.c_double), C.POINTER(C.c_uint8)
+        pin.node_price = arr(node_price, np.float64).ctypes.data_as(f64p)
+        pin.pod_price = arr(pod_price, np.float64).ctypes.data_as(f64p)
+        u = arr(unfitness, np.float64)
+        pin.unfitness = u.ctypes.data_as(f64p) if u is not None else None
+        g = arr(has_gpu, np.uint8)
+        pin.has_gpu = g.ctypes.data_as(u8p) if g is not None else None
+        x = arr(exists, np.uint8)
+        pin.exists = x.ctypes.data_as(u8p) if x is not None else None
+        pin.price_error = None
+        pin.stabilization_price = float(stabilization_price)
+        pin.preferred_cpu_milli = int(preferred_cpu_milli)
+        score = np.zeros(T, np.float64)
+        vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        self._check(self.lib.cae_price_scores(self.h, C.byref(pin), vp(arr(node_count, np.int32)), vp(arr(sched, np.int32)),
+                                              vp(arr(order, np.int32)), vp(score)))
+        return score
+
     def filter_schedulable(self, pod_order: Sequence[int], hint_node=None, sim_class=None, class_ctrl=None, node_ok=None,
                            last_index: int = 0, break_on_failure: bool = False):
         """HintingSimulator.TrySchedulePods on the cluster snapshot of the last load.  Returns (assigned[P] cluster node
@@ -248,6 +280,35 @@ def expander_chain(chain: Sequence[int], node_count, pod_count, waste) -> np.nda
     if rc != 0:
         raise EngineError("cae_expander_chain status %d: %s" % (rc, (lib.cae_last_error() or b"").decode()))
     return mask
+
+
+def expander_chain_ex(chain: Sequence[int], node_count, pod_count, waste=None, price=None, price_error=None, priority=None) -> np.ndarray:
+    """cae_expander_chain_ex: the chain with the price (price.go:166-173) and priority (priority.go:119-165) filters."""
+    lib = capi.load_engine_lib()
+    ch = np.asarray(chain, np.int32)
+    nc = np.ascontiguousarray(node_count, np.int32)
+    pc = np.ascontiguousarray(pod_count, np.int32)
+    opt = lambda a, dt: None if a is None else np.ascontiguousarray(a, dt)
+    w, pr, pe, prio = opt(waste, np.float64), opt(price, np.float64), opt(price_error, np.uint8), opt(priority, np.int32)
+    mask = np.zeros(len(nc), np.uint8)
+    vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    rc = lib.cae_expander_chain_ex(vp(ch), len(ch), len(nc), vp(nc), vp(pc), vp(w), vp(pr), vp(pe), vp(prio), vp(mask))
+    if rc != 0:
+        raise EngineError("cae_expander_chain_ex status %d: %s" % (rc, (lib.cae_last_error() or b"").decode()))
+    return mask
+
+
+def resolve_priorities(config: dict, group_ids: Sequence[str]) -> np.ndarray:
+    """What the Go shim does for the priority expander: highest priority of the ConfigMap (priority -> regexp list) whose
+    list matches the node group id (regexp.FindStringIndex = unanchored search), -1 when no entry matches
+    (expander/priority/priority.go:137-150, groupIDMatchesList :171-178)."""
+    import re
+    out = np.full(len(group_ids), -1, np.int32)
+    for i, gid in enumerate(group_ids):
+        for prio, res in config.items():
+            if any(re.search(r, gid) for r in res):
+                out[i] = max(out[i], int(prio))
+    return out
 
 
 def unpack_bits(bits: np.ndarray, P: int) -> np.ndarray:

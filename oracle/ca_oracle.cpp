@@ -18,6 +18,7 @@
  * K8S/framework/plugins/podtopologyspread/filtering.go:237-311 and interpodaffinity/filtering.go:204-271.
  */
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -806,6 +807,128 @@ double cao_waste_score(const cae_objects* o, int t, int node_count, const int32_
   double wmem = (double)(amem - rmem) / (double)amem;
   return wcpu + wmem;
 }
+/* ---- price expander (expander/price/price.go:90-183) ------------------------------------------------------------
+ * math.Tanh / math.Exp restated from Go's pure-Go implementations (src/math/tanh.go, src/math/exp.go); this file is
+ * compiled without FMA contraction (x86-64 baseline), like Go's amd64 code generator at GOAMD64=v1. */
+static double goExp(double x) {
+  const double Ln2Hi = 6.93147180369123816490e-01, Ln2Lo = 1.90821492927058770002e-10, Log2e = 1.44269504088896338700e+00;
+  const double Overflow = 7.09782712893383973096e+02, Underflow = -7.45133219101941108420e+02, NearZero = 1.0 / (1 << 28);
+  if (std::isnan(x) || (std::isinf(x) && x > 0)) return x;
+  if (std::isinf(x)) return 0;
+  if (x > Overflow) return std::numeric_limits<double>::infinity();
+  if (x < Underflow) return 0;
+  if (-NearZero < x && x < NearZero) return 1 + x;
+  int k = 0;
+  if (x < 0) k = (int)(Log2e * x - 0.5);
+  else if (x > 0) k = (int)(Log2e * x + 0.5);
+  double hi = x - (double)k * Ln2Hi;
+  double lo = (double)k * Ln2Lo;
+  const double P1 = 1.66666666666666657415e-01, P2 = -2.77777777770155933842e-03, P3 = 6.61375632143793436117e-05,
+               P4 = -1.65339022054652515390e-06, P5 = 4.13813679705723846039e-08;
+  double r = hi - lo;
+  double t = r * r;
+  double c = r - t * (P1 + t * (P2 + t * (P3 + t * (P4 + t * P5))));
+  double y = 1 - ((lo - (r * c) / (2 - c)) - hi);
+  return std::ldexp(y, k);
+}
+static double goTanh(double x) {
+  const double MAXLOG = 8.8029691931113054295988e+01;
+  double z = std::fabs(x);
+  if (z > 0.5 * MAXLOG) return x < 0 ? -1 : 1;
+  if (z >= 0.625) {
+    double s = goExp(2 * z);
+    z = 1 - 2 / (s + 1);
+    return x < 0 ? -z : z;
+  }
+  if (x == 0) return x;
+  const double P[3] = {-9.64399179425052238628e-1, -9.92877231001918586564e1, -1.61468768441708447952e3};
+  const double Q[3] = {1.12811678491632931402e2, 2.23548839060100448583e3, 4.84406305325125486048e3};
+  double s = x * x;
+  return x + x * s * ((P[0] * s + P[1]) * s + P[2]) / (((s + Q[0]) * s + Q[1]) * s + Q[2]);
+}
+double cao_go_tanh(double x) { return goTanh(x); }
+/* score of every option; sched/order rows as Estimate returned them (scheduledPods = groups in processing order, a prefix each) */
+int cao_price_scores(const cae_objects* o, const double* node_price, const double* pod_price, const double* unfitness,
+                     const uint8_t* has_gpu, const uint8_t* exists, double stabilization, int64_t preferred_cpu_milli,
+                     const int32_t* node_count, const int32_t* sched, const int32_t* order, double* score) {
+  int T = o->num_templates, E = o->num_groups, N = o->num_cluster_nodes;
+  for (int t = 0; t < T; ++t) {
+    score[t] = 0;
+    if (node_count[t] <= 0) continue;
+    double totalNodePrice = node_price[t] * (double)node_count[t];
+    double totalPodPrice = 0;
+    for (int gi = 0; gi < E; ++gi) {
+      int g = order[(size_t)t * E + gi];
+      if (g < 0) break;
+      for (int p = o->group_off[g]; p < o->group_off[g] + sched[(size_t)t * E + g]; ++p) totalPodPrice += pod_price[o->pend_spec[p]];
+    }
+    double priceSubScore = (totalNodePrice + stabilization) / (totalPodPrice + stabilization);
+    double nodeUnfitness;
+    if (unfitness) nodeUnfitness = unfitness[t];
+    else { /* SimpleNodeUnfitness (preferred.go:87-92) */
+      double pref = (double)preferred_cpu_milli, ev = (double)o->node_cap_cpu[N + t];
+      double a = pref / ev, b = ev / pref;
+      nodeUnfitness = (std::isnan(a) || std::isnan(b)) ? a + b : std::max(a, b);
+    }
+    double supressedUnfitness = (nodeUnfitness - 1.0) * (1.0 - goTanh((double)(node_count[t] - 1) / 15.0)) + 1.0;
+    if (has_gpu && has_gpu[t]) supressedUnfitness = 1000.0; /* gpuUnfitnessOverride */
+    double optionScore = supressedUnfitness * priceSubScore;
+    if (exists && !exists[t]) optionScore *= 2.0; /* notExistCoeficient */
+    score[t] = optionScore;
+  }
+  return 0;
+}
+/* the chain with price (price.go:166-173) and priority (priority.go:119-165) filters over given vectors */
+int cao_expander_ex(int T, const int32_t* chain, int chain_len, const int32_t* node_count, const int32_t* pod_count,
+                    const double* waste, const double* price, const uint8_t* price_error, const int32_t* priority, uint8_t* mask) {
+  std::vector<int> opts;
+  for (int t = 0; t < T; ++t) if (node_count[t] > 0) opts.push_back(t);
+  for (int c = 0; c < chain_len; ++c) {
+    std::vector<int> best;
+    if (chain[c] == CAE_EXP_LEAST_WASTE) {
+      double least = 0;
+      for (int t : opts) {
+        if (waste[t] == least) best.push_back(t);
+        if (best.empty() || waste[t] < least) { least = waste[t]; best.assign(1, t); }
+      }
+    } else if (chain[c] == CAE_EXP_MOST_PODS) {
+      int mx = 0;
+      for (int t : opts) {
+        if (pod_count[t] == mx) { best.push_back(t); continue; }
+        if (pod_count[t] > mx) { mx = pod_count[t]; best.assign(1, t); }
+      }
+    } else if (chain[c] == CAE_EXP_LEAST_NODES) {
+      int least = std::numeric_limits<int>::max();
+      for (int t : opts) {
+        if (node_count[t] == 0) continue;
+        if (node_count[t] == least) { best.push_back(t); continue; }
+        if (node_count[t] < least) { least = node_count[t]; best.assign(1, t); }
+      }
+    } else if (chain[c] == CAE_EXP_PRICE) {
+      double bestOptionScore = 0.0;
+      for (int t : opts) {
+        if (price_error && price_error[t]) continue; /* continue nextoption */
+        if (best.empty() || bestOptionScore == price[t]) { best.push_back(t); bestOptionScore = price[t]; }
+        else if (bestOptionScore > price[t]) { best.assign(1, t); bestOptionScore = price[t]; }
+      }
+    } else if (chain[c] == CAE_EXP_PRIORITY) {
+      int maxPrio = -1;
+      for (int t : opts) {
+        if (priority[t] < 0) continue;          /* !found: "The group won't be used" */
+        if (priority[t] < maxPrio) continue;
+        if (priority[t] > maxPrio) { maxPrio = priority[t]; best.clear(); }
+        best.push_back(t);
+      }
+      if (best.empty()) best = opts;            /* "No options filtered." */
+    } else return 1;
+    opts = best;
+    if (opts.size() == 1) break;
+  }
+  for (int t = 0; t < T; ++t) mask[t] = 0;
+  for (int t : opts) mask[t] = 1;
+  return 0;
+}
+
 int cao_expander(const cae_objects* o, const int32_t* chain, int chain_len, const int32_t* node_count,
                  const int32_t* pod_count, const int32_t* sched_count, uint8_t* mask, double* waste_out) {
   int T = o->num_templates, E = o->num_groups;

@@ -52,6 +52,12 @@ def lib() -> C.CDLL:
         l.cao_waste_score.restype = C.c_double
         l.cao_expander.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
         l.cao_expander.restype = i32
+        l.cao_go_tanh.argtypes = [C.c_double]
+        l.cao_go_tanh.restype = C.c_double
+        l.cao_price_scores.argtypes = [vp, vp, vp, vp, vp, vp, C.c_double, C.c_int64, vp, vp, vp, vp]
+        l.cao_price_scores.restype = i32
+        l.cao_expander_ex.argtypes = [i32, vp, i32, vp, vp, vp, vp, vp, vp, vp]
+        l.cao_expander_ex.restype = i32
         l.cao_filter_schedulable.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32, i32, vp, vp, vp]
         l.cao_filter_schedulable.restype = i32
         _lib = l
@@ -126,6 +132,32 @@ def expander(enc, chain: Sequence[int], node_count, pod_count, sched):
                             _p(np.ascontiguousarray(sched, np.int32)), _p(mask), _p(waste))
     assert rc == 0
     return mask, waste
+
+
+def go_tanh(x: float) -> float:
+    return lib().cao_go_tanh(float(x))
+
+
+def price_scores(enc, node_price, pod_price, stabilization_price, preferred_cpu_milli=0, unfitness=None, has_gpu=None,
+                 exists=None, node_count=None, sched=None, order=None) -> np.ndarray:
+    a = lambda x, dt: None if x is None else np.ascontiguousarray(x, dt)
+    np_, pp, uf, hg, ex = a(node_price, np.float64), a(pod_price, np.float64), a(unfitness, np.float64), a(has_gpu, np.uint8), a(exists, np.uint8)
+    nc, sc, od = a(node_count, np.int32), a(sched, np.int32), a(order, np.int32)
+    score = np.zeros(enc.T, np.float64)
+    rc = lib().cao_price_scores(enc.ptr(), _p(np_), _p(pp), _p(uf), _p(hg), _p(ex), float(stabilization_price), int(preferred_cpu_milli),
+                                _p(nc), _p(sc), _p(od), _p(score))
+    assert rc == 0
+    return score
+
+
+def expander_ex(chain: Sequence[int], node_count, pod_count, waste=None, price=None, price_error=None, priority=None) -> np.ndarray:
+    a = lambda x, dt: None if x is None else np.ascontiguousarray(x, dt)
+    ch, nc, pc = a(chain, np.int32), a(node_count, np.int32), a(pod_count, np.int32)
+    w, pr, pe, prio = a(waste, np.float64), a(price, np.float64), a(price_error, np.uint8), a(priority, np.int32)
+    mask = np.zeros(len(nc), np.uint8)
+    rc = lib().cao_expander_ex(len(nc), _p(ch), len(ch), _p(nc), _p(pc), _p(w), _p(pr), _p(pe), _p(prio), _p(mask))
+    assert rc == 0
+    return mask
 
 
 def get_min_limit(base: int, target: int) -> int:

@@ -371,3 +371,27 @@ def test_pack_longest_first_order(oracle, monkeypatch):
             _check_estimate(e, oracle, enc, np.full(enc.T, 1000))
     finally:
         e.close()
+
+
+def test_price_scores_bit_exact(eng, oracle):
+    """Price expander score (expander/price/price.go:113-159) on the device vs the oracle: float64, bit-identical, both from the
+    device-resident Estimate() result and from caller-supplied rows; node counts up to the tanh's exp branch (>= 11 nodes)."""
+    from kubernetes_autoscaler_b200.engine import expander_chain_ex
+    enc = synth.generate(2, pods=8_000, templates=64)
+    eng.load(enc)
+    caps = np.full(enc.T, 1000, np.int32)
+    nc, pc, sched, order = eng.estimate_all(caps)
+    rng = np.random.default_rng(7)
+    node_price = rng.uniform(0.01, 5.0, enc.T)
+    pod_price = rng.uniform(0.0, 0.2, enc.struct.num_podspecs)
+    has_gpu = (rng.random(enc.T) < 0.2).astype(np.uint8)
+    exists = (rng.random(enc.T) < 0.7).astype(np.uint8)
+    want = oracle.price_scores(enc, node_price, pod_price, 0.013, 4000, has_gpu=has_gpu, exists=exists, node_count=nc, sched=sched, order=order)
+    got_dev = eng.price_scores(node_price, pod_price, 0.013, 4000, has_gpu=has_gpu, exists=exists)
+    got_rows = eng.price_scores(node_price, pod_price, 0.013, 4000, has_gpu=has_gpu, exists=exists, node_count=nc, sched=sched, order=order)
+    assert int(nc.max()) >= 11 and np.count_nonzero(want) > 8
+    assert np.array_equal(got_dev, want) and np.array_equal(got_rows, want)
+    unfit = rng.uniform(1.0, 3.0, enc.T)
+    want2 = oracle.price_scores(enc, node_price, pod_price, 0.0, unfitness=unfit, node_count=nc, sched=sched, order=order)
+    assert np.array_equal(eng.price_scores(node_price, pod_price, 0.0, unfitness=unfit), want2)
+    assert np.array_equal(expander_chain_ex([3, 2], nc, pc, price=want), oracle.expander_ex([3, 2], nc, pc, price=want))
