@@ -502,29 +502,47 @@ def main():
     except Exception as ex:
         parity = {"checked": False, "error": repr(ex)}
 
-    # ---- e2e through the C ABI with host buffers: load (H2D) + pass + D2H of bits/counts ----------
-    e2e_ms = []
-    h2d = d2h = 0
-    for i in range(max(3, min(args.steps, 10)) + 1):
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        t0 = time.perf_counter()
-        eng.load(enc)
-        bits, _, cnt = eng.feasibility()
-        if count_t is not None:
-            dist.all_reduce(count_t)
+    # ---- e2e through the C ABI with host buffers --------------------------------------------------------
+    # a tick = the pending-pod rows of this step travel H2D (cae_load_pending: the per-tick delta against the resident
+    # snapshot), the dense pass runs, the bit matrix + counts travel D2H.  Also reported: the same with a FULL cae_load per
+    # step (interning + every table + class matrices: round 1's definition) and the counts-only answer (no bit matrix).
+    def e2e_loop(mode):
+        nonlocal h2d, d2h
+        ms = []
+        for i in range(max(3, min(args.steps, 10)) + 1):
             torch.cuda.synchronize()
-        dt = 1e3 * (time.perf_counter() - t0)
-        if i > 0:
-            e2e_ms.append(dt)
-        st = eng.stats()
-        h2d, d2h = st.h2d_bytes, st.d2h_bytes
-    e2e_step = float(np.mean(e2e_ms))
-    if dist is not None:
-        tt = torch.tensor([e2e_step], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_step = float(tt[0])
+            if dist is not None:
+                dist.barrier()
+            t0 = time.perf_counter()
+            if mode == "full":
+                eng.load(enc)
+            else:
+                assert eng.load_pending(enc)
+            up = eng.stats().h2d_bytes
+            if mode == "counts":
+                eng.feasibility(want_bits=False)
+            else:
+                eng.feasibility()
+            if count_t is not None:
+                dist.all_reduce(count_t)
+                torch.cuda.synchronize()
+            dt = 1e3 * (time.perf_counter() - t0)
+            if i > 0:
+                ms.append(dt)
+            if mode == "delta":
+                h2d, d2h = up, eng.stats().d2h_bytes
+        v = float(np.mean(ms))
+        if dist is not None:
+            tt = torch.tensor([v], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            v = float(tt[0])
+        return v
+
+    h2d = d2h = 0
+    eng.load(enc)
+    e2e_full = e2e_loop("full")
+    e2e_step = e2e_loop("delta")
+    e2e_counts = e2e_loop("counts")
     samples = _clock_sampler_stop(sampler)
 
     # ---- the dense pass where it is not a launch-latency test: C3 (5 x 10^8 cells) on one GPU ------------
@@ -631,7 +649,11 @@ def main():
         "collective": ("none" if world == 1 else ("fused exchange over NVLink peer memory inside the kernel" if fused else "NCCL all_reduce int32[T]")),
         "wall_ms_per_step": float(np.mean(wall_ms)), "clocks": cs,
         "e2e": {"value": (P1 * world) * T / (e2e_step * 1e-3), "unit": "evals/s", "ms_per_step": e2e_step,
-                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "what": "per step: cae_load_pending (this step's pending-pod rows, host -> device, per-pod rows re-derived) + dense pass + "
+                        "device -> host of the bit matrix and the counts; nodes / templates / pod-spec tables stay resident between ticks",
+                "ms_per_step_full_load": e2e_full, "value_full_load": (P1 * world) * T / (e2e_full * 1e-3),
+                "ms_per_step_counts_only": e2e_counts, "value_counts_only": (P1 * world) * T / (e2e_counts * 1e-3)},
         "gpu_launches": int(launches), "parity_checked": bool(parity.get("checked")), "parity": parity,
         "roofline": roofline, "roofline_secondary": roofline2, "cpu_baseline": cpu,
         "dense_pass_large": dense_large, "decision_latency": headline_decision, "decisions": decisions}))

@@ -286,6 +286,17 @@ int32_t cae_load(cae_engine* e, const cae_objects* objs);
  *   reasons   [T][Plocal] uint8 enum cae_reason, only if cfg.want_reasons.  May be NULL.
  *   fit_count [T] int32 number of local pods that fit template t (caller all-reduces over shards).
  * Plocal = pods of this shard (block partition of [0,P) over world_size). */
+/* The per-tick delta: new pending-pod rows against the snapshot that is already resident.
+ * Replaces: the part of DeltaSnapshotStore.SetClusterState / Fork-Commit (simulator/clustersnapshot/store/delta.go:499-588)
+ * that changes between two scale-up loops when nodes, templates and the set of pod specs are unchanged — the list of
+ * pending pods and their grouping.  Everything derived from the object world (interned tables, class matrices, rank
+ * dictionaries, topology counters) stays in HBM; only pend_spec[num_pending] and group_off[num_groups + 1] travel
+ * (4 B per pod), the per-pod rows and group records are re-derived on the device.
+ * Status 2 = the delta does not apply (a pod spec that was not pending at the last cae_load, more pods / groups than the
+ * resident buffers hold, or — with topology-spread / inter-pod-affinity counters in the snapshot — a different
+ * group -> spec sequence): call cae_load with the full snapshot instead.  Nothing is changed in that case. */
+int32_t cae_load_pending(cae_engine* e, int32_t num_pending, const int32_t* pend_spec, int32_t num_groups, const int32_t* group_off);
+
 int32_t cae_feasibility(cae_engine* e, uint32_t* fit_bits, uint8_t* reasons, int32_t* fit_count);
 
 /* Exemplar feasibility, what the orchestrator itself asks: group exemplar x template.

@@ -138,6 +138,8 @@ def load_engine_lib() -> C.CDLL:
     lib.cae_version.restype = C.c_char_p
     lib.cae_load.argtypes = [C.c_void_p, P(cae_objects)]
     lib.cae_load.restype = C.c_int32
+    lib.cae_load_pending.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.cae_load_pending.restype = C.c_int32
     lib.cae_feasibility.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.cae_feasibility.restype = C.c_int32
     lib.cae_feasibility_groups.argtypes = [C.c_void_p, C.c_void_p]

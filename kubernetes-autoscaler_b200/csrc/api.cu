@@ -217,6 +217,47 @@ struct LoadTimer {   // CAE_LOAD_TIMING=1: host wall clock of the phases of cae_
   ~LoadTimer() { if (on) fprintf(stderr, "cae_load:%s\n", out.c_str()); }
 };
 
+// Host copy of the pending-pod rows in pinned memory (source of the H2D copy of cae_load_pending, read by the filter pass),
+// the spec of every group and whether the groups are homogeneous.  `check_pending`: refuse specs that were not pending at
+// the last full load (returns 2).
+static int stage_pending(Engine* e, int P, const int32_t* pend_spec, int E, const int32_t* group_off, bool check_pending) {
+  const size_t words = (size_t)P + E + 1;
+  if (words > e->pending_stage_words) {
+    if (e->h_pending_stage) cudaFreeHost(e->h_pending_stage);
+    e->h_pending_stage = nullptr;
+    e->pending_stage_words = 0;
+    const size_t cap_words = std::max(words, (size_t)e->cap_P + e->cap_E + 1);
+    CAE_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&e->h_pending_stage), cap_words * 4, cudaHostAllocDefault));
+    e->pending_stage_words = cap_words;
+  }
+  const int S = e->num_podspecs;
+  // one pass per group: the exemplar's spec must have been pending at the last full load, the other pods must equal it
+  std::vector<int32_t> gspec(E, -1);
+  bool homog = true;
+  for (int g = 0; g < E; ++g) {
+    const int b = group_off[g], en = group_off[g + 1];
+    if (en <= b) continue;
+    const int s0 = pend_spec[b];
+    if (check_pending && (s0 < 0 || s0 >= S || !e->h_spec_pending[s0])) { set_error("cae_load_pending: a pod spec that was not pending at the last cae_load"); return 2; }
+    gspec[g] = s0;
+    int diff = 0;
+    for (int p = b + 1; p < en; ++p) diff |= pend_spec[p] ^ s0;
+    homog &= diff == 0;
+  }
+  if (!homog && check_pending)   // heterogeneous groups (only the filter pass accepts them): every pod's spec is checked
+    for (int p = 0; p < P; ++p) {
+      const int s = pend_spec[p];
+      if (s < 0 || s >= S || !e->h_spec_pending[s]) { set_error("cae_load_pending: a pod spec that was not pending at the last cae_load"); return 2; }
+    }
+  if (P) memcpy(e->h_pending_stage, pend_spec, sizeof(int32_t) * P);
+  memcpy(e->h_pending_stage + P, group_off, sizeof(int32_t) * (E + 1));
+  e->h_pend_spec = e->h_pending_stage;
+  e->h_group_off = e->h_pending_stage + P;
+  e->h_group_spec.swap(gspec);
+  e->groups_homogeneous = homog;
+  return 0;
+}
+
 static int do_load(Engine* e, const cae_objects* o) {
   LoadTimer lt;
   if (o->abi_version != CAE_ABI_VERSION) { set_error("cae_objects.abi_version mismatch"); return -2; }
@@ -447,9 +488,10 @@ static int do_load(Engine* e, const cae_objects* o) {
   e->d_reasons = nullptr;
   if (e->cfg.want_reasons && dev_alloc(e, &e->d_reasons, (size_t)std::max(T, 1) * std::max(e->Pl, 1))) return -1;
 
-  // host copies for host-side steps (homogeneity check)
-  e->h_group_off.assign(o->group_off, o->group_off + o->num_groups + 1);
-  e->h_pend_spec.assign(o->pend_spec, o->pend_spec + o->num_pending);
+  // host copies for host-side steps (homogeneity check) and for the per-tick delta (cae_load_pending)
+  e->h_spec_pending = spec_pending;
+  e->cap_P = e->P; e->cap_E = e->E; e->cap_Pl = e->Pl;
+  { int rc = stage_pending(e, e->P, o->pend_spec, e->E, o->group_off, false); if (rc) return rc; }
 
   lt.mark("dev_alloc+memsets");
   if (e->up.flush(e->stream, &e->stats.h2d_bytes)) return -1;   // ONE pinned H2D copy per arena chunk
@@ -592,6 +634,8 @@ void cae_destroy(cae_engine* h) {
   if (e->d_pack_scratch) cudaFree(e->d_pack_scratch);
   if (e->d_fm_scratch) cudaFree(e->d_fm_scratch);
   if (e->d_fm_blob) cudaFree(e->d_fm_blob);
+  if (e->h_pending_stage) cudaFreeHost(e->h_pending_stage);
+  if (e->ev2) { cudaEventDestroy(e->ev2); cudaEventDestroy(e->ev3); }
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -605,6 +649,44 @@ int32_t cae_load(cae_engine* h, const cae_objects* objs) {
   return cae::do_load(e, objs);
 }
 
+int32_t cae_load_pending(cae_engine* h, int32_t num_pending, const int32_t* pend_spec, int32_t num_groups, const int32_t* group_off) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (!e || !e->loaded) { cae::set_error("cae_load_pending before cae_load"); return -2; }
+  if (num_pending < 0 || num_groups < 0 || (num_pending && !pend_spec) || !group_off) { cae::set_error("cae_load_pending: bad arguments"); return -2; }
+  cudaSetDevice(e->cfg.device);
+  const int P = num_pending, E = num_groups;
+  // shard of this rank under the same rule as cae_load
+  const int W = std::max(1, e->cfg.world_size), rk = e->cfg.rank;
+  int pb = (int)((int64_t)P * rk / W), pe = (int)((int64_t)P * (rk + 1) / W);
+  pb = (pb / 32) * 32;
+  if (rk + 1 < W) pe = (pe / 32) * 32;
+  if (e->cfg.flags & CAE_CFG_PODS_PRESHARDED) { pb = 0; pe = P; }
+  const int Pl = pe - pb;
+  if (P > e->cap_P || E > e->cap_E || Pl > e->cap_Pl) { cae::set_error("cae_load_pending: more pods / groups than the resident buffers hold"); return 2; }
+  if (group_off[0] != 0 || group_off[E] != P) { cae::set_error("cae_load_pending: group_off does not cover the pending pods"); return -2; }
+  if (e->has_dynamic) {   // the topology counters know which GROUPS feed them: the group -> spec sequence must be the resident one
+    bool same = E == e->E;
+    for (int g = 0; g < E && same; ++g) {
+      const int s_new = group_off[g + 1] > group_off[g] ? pend_spec[group_off[g]] : -1;
+      same = s_new == e->h_group_spec[g];
+    }
+    if (!same) { cae::set_error("cae_load_pending: the group -> spec sequence changed under topology counters"); return 2; }
+  }
+  // wait for the previous delta's copies before the pinned rows are overwritten (normally long finished)
+  CAE_CUDA(cudaStreamSynchronize(e->stream));
+  { int rc = cae::stage_pending(e, P, pend_spec, E, group_off, true); if (rc) return rc; }
+  const size_t words = (size_t)P + E + 1;
+  if (P) CAE_CUDA(cudaMemcpyAsync(const_cast<int32_t*>(e->dobj.pend_spec), e->h_pend_spec, sizeof(int32_t) * P, cudaMemcpyHostToDevice, e->stream));
+  CAE_CUDA(cudaMemcpyAsync(const_cast<int32_t*>(e->dobj.group_off), e->h_group_off, sizeof(int32_t) * (E + 1), cudaMemcpyHostToDevice, e->stream));
+  e->stats.h2d_bytes = (int64_t)words * 4;
+  e->P = P; e->E = E; e->p_begin = pb; e->p_end = pe; e->Pl = Pl; e->Plw = (Pl + 31) / 32;
+  e->group_reason_valid = false;
+  if (cae::launch_expand_pods(e)) return -1;
+  if (cae::launch_group_records(e)) return -1;
+  // no synchronize: the stream orders the copies and the two kernels before whatever the caller launches next
+  return 0;
+}
+
 int32_t cae_feasibility(cae_engine* h, uint32_t* fit_bits, uint8_t* reasons, int32_t* fit_count) {
   Engine* e = reinterpret_cast<Engine*>(h);
   if (!e || !e->loaded) { cae::set_error("cae_feasibility before cae_load"); return -2; }
@@ -614,8 +696,8 @@ int32_t cae_feasibility(cae_engine* h, uint32_t* fit_bits, uint8_t* reasons, int
   if (cae::launch_feasibility(e, want_r)) return -1;
   cudaEventRecord(e->ev1, e->stream);
   e->stats.d2h_bytes = 0;
-  cudaEvent_t c0, c1;
-  cudaEventCreate(&c0); cudaEventCreate(&c1);
+  if (!e->ev2) { cudaEventCreate(&e->ev2); cudaEventCreate(&e->ev3); }
+  cudaEvent_t c0 = e->ev2, c1 = e->ev3;
   cudaEventRecord(c0, e->stream);
   if (fit_bits && e->T && e->Plw) {
     CAE_CUDA(cudaMemcpyAsync(fit_bits, e->d_fit_bits, sizeof(uint32_t) * (size_t)e->T * e->Plw, cudaMemcpyDeviceToHost, e->stream));
@@ -639,7 +721,6 @@ int32_t cae_feasibility(cae_engine* h, uint32_t* fit_bits, uint8_t* reasons, int
   e->stats.feasibility_ms = ms;
   cudaEventElapsedTime(&ms, c0, c1);
   e->stats.d2h_ms = ms;
-  cudaEventDestroy(c0); cudaEventDestroy(c1);
   e->stats.evals = (int64_t)e->Pl * e->T;
   if (peer_status) { cae::set_error("peer exchange timed out: a rank did not contribute its histogram"); return -1; }
   return 0;
@@ -661,13 +742,8 @@ int32_t cae_estimate_all(cae_engine* h, const int32_t* max_nodes, int32_t* node_
   Engine* e = reinterpret_cast<Engine*>(h);
   if (!e || !e->loaded) { cae::set_error("cae_estimate_all before cae_load"); return -2; }
   cudaSetDevice(e->cfg.device);
-  // groups must be homogeneous (equivalence.BuildPodGroups guarantees it: core/scaleup/equivalence/groups.go:40-104)
-  for (int g = 0; g < e->E; ++g)
-    for (int p = e->h_group_off[g] + 1; p < e->h_group_off[g + 1]; ++p)
-      if (e->h_pend_spec[p] != e->h_pend_spec[e->h_group_off[g]]) {
-        cae::set_error("pod group with non-equivalent pods");
-        return 1;
-      }
+  // groups must be homogeneous (equivalence.BuildPodGroups guarantees it: core/scaleup/equivalence/groups.go:40-104); checked at load
+  if (!e->groups_homogeneous) { cae::set_error("pod group with non-equivalent pods"); return 1; }
   const int T = e->T, E = e->E;
   if (T == 0) return 0;
   e->pack_cap = 1;

@@ -67,7 +67,7 @@ struct Arena {
 struct Engine {
   cae_config cfg{};
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   Arena up;         // uploaded tables (pinned mirror), reset per load
   Arena scratch;    // device-only tables of the current load
   Engine() { up.mirrored = true; }
@@ -167,7 +167,13 @@ struct Engine {
   int64_t peer_step = 0;
   int32_t* d_work_counter = nullptr;
   // host copies needed by host-side steps
-  std::vector<int32_t> h_group_off, h_pend_spec;
+  const int32_t *h_group_off = nullptr, *h_pend_spec = nullptr;   // host copy of the pending-pod rows: views into h_pending_stage
+  std::vector<int32_t> h_group_spec;      // [E] spec of each group's pods (-1 = empty group)
+  bool groups_homogeneous = true;         // every group holds pods of ONE spec (equivalence.BuildPodGroups guarantees it)
+  std::vector<uint8_t> h_spec_pending;    // [num_podspecs] spec carried by a pending pod at the last full load
+  int cap_P = 0, cap_E = 0, cap_Pl = 0;   // capacities of the resident per-pod / per-group buffers (cae_load_pending)
+  int32_t* h_pending_stage = nullptr;     // pinned staging of pend_spec | group_off for the delta upload
+  size_t pending_stage_words = 0;
   std::vector<int64_t> h_spec_req;        // [num_podspecs][R]
   std::vector<int64_t> h_cap_cpu, h_cap_mem;  // per template
   int num_podspecs = 0;

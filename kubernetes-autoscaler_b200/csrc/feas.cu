@@ -503,7 +503,11 @@ static int launch_feas_lut_a(Engine* e, bool want_reasons, const K1Args& a, cons
 constexpr int K1_LUT_MAX_ROWS = FEAS_LUT_MAX_ROWS;
 
 int launch_feasibility(Engine* e, bool want_reasons) {
-  if (e->Pl == 0 || e->Tw == 0) return 0;
+  if (e->Tw == 0) return 0;
+  if (e->Pl == 0) {   // no pending pods on this rank: an all-zero histogram (the exchange, if any, is the caller's NCCL path)
+    CAE_CUDA(cudaMemsetAsync(e->d_fit_count, 0, sizeof(int32_t) * e->T, e->stream));
+    return 0;
+  }
   if (e->peer_world > 1 && e->T > Engine::PEER_CAP) {   // never hand back a local histogram as if it were the global one
     set_error("fused histogram exchange: more templates than the exchange buffer holds (use the NCCL all-reduce of cae_device_buffer(0))");
     return 1;

@@ -132,6 +132,18 @@ class Engine:
         self.enc = enc
         self._check(self.lib.cae_load(self.h, enc.ptr()))
 
+    def load_pending(self, enc: EncodedObjects) -> bool:
+        """The per-tick delta (cae_load_pending): only the pending-pod rows of `enc` travel; nodes, templates and pod specs
+        must be the ones of the last load().  Returns False when the engine answers "use a full load" (status 2)."""
+        a = enc.arrays
+        rc = self.lib.cae_load_pending(self.h, enc.P, a["pend_spec"].ctypes.data_as(C.c_void_p), enc.E,
+                                       a["group_off"].ctypes.data_as(C.c_void_p))
+        if rc == 2:
+            return False
+        self._check(rc)
+        self.enc = enc
+        return True
+
     def feasibility(self, want_bits: bool = True):
         """Dense pods x templates pass. Returns (fit_bits [T][ceil(Pl/32)] uint32 | None,
         reasons [T][Pl] uint8 | None, fit_count [T] int32) for this rank's pod shard."""

@@ -395,3 +395,35 @@ def test_price_scores_bit_exact(eng, oracle):
     want2 = oracle.price_scores(enc, node_price, pod_price, 0.0, unfitness=unfit, node_count=nc, sched=sched, order=order)
     assert np.array_equal(eng.price_scores(node_price, pod_price, 0.0, unfitness=unfit), want2)
     assert np.array_equal(expander_chain_ex([3, 2], nc, pc, price=want), oracle.expander_ex([3, 2], nc, pc, price=want))
+
+
+def test_load_pending_delta(eng, oracle):
+    """cae_load_pending: new pending-pod rows against the resident snapshot (the per-tick delta) give the same dense pass
+    and the same Estimate() as a full load of the same objects, and as the oracle; deltas that do not apply answer status 2."""
+    from kubernetes_autoscaler_b200.engine import unpack_bits
+    enc = synth.generate(2, pods=12_000, templates=160)
+    eng.load(enc)
+    for pb, pe in ((0, 12_000), (1_000, 9_000), (5_000, 5_512), (0, 0)):
+        sub = enc.slice_pods(pb, pe)
+        assert eng.load_pending(sub)
+        bits, reasons, count = eng.feasibility()
+        want, _ = oracle.feasibility_dense(sub)
+        assert np.array_equal(reasons, want) and np.array_equal(count, (want == 0).sum(axis=1))
+        if sub.P:
+            assert np.array_equal(unpack_bits(bits, sub.P), want == 0)
+        caps = np.full(sub.T, 40, np.int32)
+        nc, pc, sched, order = eng.estimate_all(caps)
+        onc, opc, osched, oorder, _ = oracle.estimate_all(sub, caps)
+        assert np.array_equal(nc, onc) and np.array_equal(pc, opc) and np.array_equal(sched, osched) and np.array_equal(order, oorder)
+    # more pods than the resident buffers hold -> full load needed
+    eng.load(enc.slice_pods(0, 4_000))
+    assert not eng.load_pending(enc)
+    # topology counters in the snapshot: the same group -> spec sequence applies, clipped groups do not
+    enc3 = synth.generate(3, pods=3_000, templates=24, cluster_nodes=60)
+    eng.load(enc3)
+    assert eng.load_pending(enc3)
+    caps = np.full(enc3.T, 50, np.int32)
+    nc, pc, sched, order = eng.estimate_all(caps)
+    onc, opc, osched, oorder, _ = oracle.estimate_all(enc3, caps)
+    assert np.array_equal(nc, onc) and np.array_equal(pc, opc) and np.array_equal(sched, osched) and np.array_equal(order, oorder)
+    assert not eng.load_pending(enc3.slice_pods(100, 2_000))
