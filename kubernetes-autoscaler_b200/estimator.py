@@ -199,8 +199,23 @@ class ScaleUpSimulation:
                 out.append(Option(ng, count, pods))
         return out
 
-    def best_options(self, chain: Sequence[str]) -> List[str]:
-        """expander chain (factory/chain.go:36-45) up to the random fallback: surviving node groups."""
-        mask, self.waste = self.engine.expander_best([EXPANDER_BY_NAME[c] for c in chain], self.node_count,
-                                                     self.pod_count, self.sched)
+    def best_options(self, chain: Sequence[str], options: Optional[Sequence[Option]] = None) -> List[str]:
+        """expander chain (factory/chain.go:36-45) up to the random fallback: surviving node groups.
+        `options`: the options that reached ExpanderStrategy.BestOption (orchestrator.go:178) — node groups filtered out
+        before (all-or-nothing, empty options) do not take part, and adjusted node counts (ZeroOrMaxNodeScaling) are the
+        ones scored."""
+        nc, pc, sched = self.node_count, self.pod_count, self.sched
+        if options is not None:
+            import numpy as np
+            by_ng = {o.node_group: o for o in options}
+            nc, pc, sched = np.array(nc), np.array(pc), np.array(sched)
+            for t, ng in enumerate(self.ids):
+                o = by_ng.get(ng)
+                if o is None:
+                    nc[t] = 0
+                    pc[t] = 0
+                    sched[t] = 0
+                else:
+                    nc[t] = o.node_count
+        mask, self.waste = self.engine.expander_best([EXPANDER_BY_NAME[c] for c in chain], nc, pc, sched)
         return [ng for t, ng in enumerate(self.ids) if mask[t]]

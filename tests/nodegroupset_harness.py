@@ -1,4 +1,4 @@
-"""Host-side mirror of the step AFTER the path (first half): which similar node groups may share a
+"""TEST HARNESS (not product code): host-side mirror of the step AFTER the path (first half): which similar node groups may share a
 scale-up, and how the new nodes are split between them.  Small integer work on the host; its only input from the
 engine is the exemplar feasibility matrix (``ScaleUpSimulation.schedulable_pod_groups``).
 
@@ -15,7 +15,7 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Dict, List, Sequence
 
-from .estimator import NodeGroupInfo
+from kubernetes_autoscaler_b200.estimator import NodeGroupInfo
 
 
 @dataclass
@@ -70,7 +70,9 @@ def BalanceScaleUpBetweenGroups(groups: Sequence[NodeGroupInfo], newNodes: int) 
         else:                                          # full (or over its max): swap it out of the active range
             infos[start], infos[cur] = infos[cur], infos[start]
             start += 1
-        if cur < len(infos) - 1 and info.new_size > infos[cur + 1].new_size:
+        # Go holds a POINTER to the slot (currentInfo := &scaleUpInfos[currentIndex]): after the swap above it reads the
+        # element that was swapped INTO the slot, not the full group that left it (balancing_processor.go:150-170)
+        if cur < len(infos) - 1 and infos[cur].new_size > infos[cur + 1].new_size:
             cur += 1
         else:
             cur = start

@@ -1,4 +1,7 @@
-"""The scale-up tick end to end on the host, composed from the pieces the engine accelerates — the reading order of
+"""TEST HARNESS (not product code): the Go side keeps ScaleUpOrchestrator.ScaleUp; this mirror exists
+so that the engine's answers can be pinned on the reference's decision-level tests (orchestrator_test.go).
+
+The scale-up tick end to end on the host, composed from the pieces the engine accelerates — the reading order of
 ``ScaleUpOrchestrator.ScaleUp`` (``cluster-autoscaler/core/scaleup/orchestrator/orchestrator.go:87-285``):
 
     BuildPodGroups -> valid node groups -> SchedulablePodGroups (engine, E x T) -> limiter caps -> Estimate for every
@@ -14,13 +17,13 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence
 
-from .engine import Engine
-from .estimator import (EstimationContext, NodeGroupInfo, Option, ScaleUpSimulation, ThresholdBasedEstimationLimiter,
+from kubernetes_autoscaler_b200.engine import Engine
+from kubernetes_autoscaler_b200.estimator import (EstimationContext, NodeGroupInfo, Option, ScaleUpSimulation, ThresholdBasedEstimationLimiter,
                         ClusterCapacityThreshold, SngCapacityThreshold, StaticThreshold)
-from .nodegroupset import (BalanceScaleUpBetweenGroups, ComputeSimilarNodeGroups, CreateGenericNodeInfoComparator,
+from nodegroupset_harness import (BalanceScaleUpBetweenGroups, ComputeSimilarNodeGroups, CreateGenericNodeInfoComparator,
                            FindSimilarNodeGroups, ScaleUpInfo)
-from .objects import Namespace, NodeInfo, Pod
-from .podutil import build_pod_groups
+from kubernetes_autoscaler_b200.objects import Namespace, NodeInfo, Pod
+from kubernetes_autoscaler_b200.podutil import build_pod_groups
 
 ScaleUpSuccessful, ScaleUpNoOptionsAvailable, ScaleUpError = "ScaleUpSuccessful", "ScaleUpNoOptionsAvailable", "ScaleUpError"
 
@@ -63,7 +66,12 @@ class ScaleUpOrchestrator:
 
     def ScaleUp(self, unschedulablePods: Sequence[Pod], cluster: Sequence[NodeInfo], nodeInfos: Dict[str, NodeInfo],
                 nodeGroups: Sequence[NodeGroupInfo], allOrNothing: bool = False,
-                namespaces: Sequence[Namespace] = (), simulation_factory=ScaleUpSimulation) -> ScaleUpStatus:
+                namespaces: Sequence[Namespace] = (), simulation_factory=ScaleUpSimulation,
+                expander_strategy=None, binpacking_limiter=None) -> ScaleUpStatus:
+        """expander_strategy(options) -> Option: stands for expander.Strategy.BestOption when given (the reference tests use a
+        reporting mock); binpacking_limiter: object with StopBinpacking(options) -> bool, asked after every node group in
+        order (processors/binpacking/binpacking_limiter.go) — the engine computes every group in one pass, the limiter cuts
+        the option list where the sequential loop would have stopped."""
         groups = build_pod_groups(list(unschedulablePods))                                   # :107
         considered = [ng.id for ng in nodeGroups]
         by_id = {ng.id: ng for ng in nodeGroups}
@@ -92,15 +100,23 @@ class ScaleUpOrchestrator:
                 continue
             if opt.node_count > 0 and opt.pods:
                 options.append(opt)
+            if binpacking_limiter is not None and binpacking_limiter.StopBinpacking(options):   # :164-166
+                break
+        self.last_options = list(options)
         schedulable_somewhere = {g for gs in schedulable.values() for g in gs}
+        # GetRemainingPods (:843-857): pods of the groups that are schedulable on NO node group
         remain = [p for gi, g in enumerate(groups) if gi not in schedulable_somewhere for p in g.pods]
         if not options:
-            return ScaleUpStatus(ScaleUpNoOptionsAvailable, pods_remain_unschedulable=remain or all_pods, considered_node_groups=considered)
-        surviving = sim.best_options(list(self.options.expander))                            # :178
-        surviving = [ng for ng in surviving if any(o.node_group == ng for o in options)]
-        if not surviving:
             return ScaleUpStatus(ScaleUpNoOptionsAvailable, pods_remain_unschedulable=remain, considered_node_groups=considered)
-        best = next(o for o in options if o.node_group == surviving[0])
+        if expander_strategy is not None:
+            best = expander_strategy(options)                                                # :178
+            if best is None:
+                return ScaleUpStatus(ScaleUpNoOptionsAvailable, pods_remain_unschedulable=remain, considered_node_groups=considered)
+        else:
+            surviving = sim.best_options(list(self.options.expander), options)               # only what reached the expander
+            if not surviving:
+                return ScaleUpStatus(ScaleUpNoOptionsAvailable, pods_remain_unschedulable=remain, considered_node_groups=considered)
+            best = next(o for o in options if o.node_group == surviving[0])
         try:
             newNodes = self.GetCappedNewNodeCount(best.node_count, len(cluster))             # :194
         except RuntimeError as ex:

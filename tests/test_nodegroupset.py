@@ -2,7 +2,7 @@
 import pytest
 
 from kubernetes_autoscaler_b200.estimator import NodeGroupInfo
-from kubernetes_autoscaler_b200.nodegroupset import (BalanceScaleUpBetweenGroups, ComputeSimilarNodeGroups,
+from nodegroupset_harness import (BalanceScaleUpBetweenGroups, ComputeSimilarNodeGroups,
                                                      matchingSchedulablePodGroups)
 
 
@@ -59,7 +59,7 @@ def test_compute_similar_node_groups():
 
 
 # ---- processors/nodegroupset/compare_nodegroups_test.go:41-197 ----------------------------------------------------------------
-from kubernetes_autoscaler_b200.nodegroupset import CreateGenericNodeInfoComparator, FindSimilarNodeGroups  # noqa: E402
+from nodegroupset_harness import CreateGenericNodeInfoComparator, FindSimilarNodeGroups  # noqa: E402
 from kubernetes_autoscaler_b200.objects import BuildTestNode, BuildTestPod, NodeInfo  # noqa: E402
 from kubernetes_autoscaler_b200.snapshotz import quantity_value  # noqa: E402
 

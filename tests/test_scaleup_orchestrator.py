@@ -6,7 +6,7 @@ import pytest
 
 from kubernetes_autoscaler_b200.estimator import NodeGroupInfo
 from kubernetes_autoscaler_b200.objects import BuildTestNode, BuildTestPod, NodeInfo, Taint, Toleration, WithTolerations
-from kubernetes_autoscaler_b200.scaleup import (AutoscalingOptions, ScaleUpNoOptionsAvailable, ScaleUpOrchestrator, ScaleUpSuccessful)
+from scaleup_harness import (AutoscalingOptions, ScaleUpNoOptionsAvailable, ScaleUpOrchestrator, ScaleUpSuccessful)
 
 
 class OracleEngine:
