@@ -275,6 +275,34 @@ def decision_run(torch, dist, Engine, synth, config, rank, world, local_rank, re
             row = [float(x) for x in tt]
         if rep:
             rows.append(row)
+    # the same decision when only the pending-pod rows changed since the last tick (cae_load_pending instead of cae_load)
+    delta_ms = []
+    for rep in range(3):
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        assert eng.load_pending(enc)
+        nc2, pc2, _, _ = eng.estimate_all(caps, want_sched=False, copy=False)
+        if dist is not None:
+            ptr, _ = eng.device_buffer(1)
+
+            class _Wrap2:
+                __cuda_array_interface__ = {"shape": (2 * enc.T,), "typestr": "<i4", "data": (ptr, False), "version": 3}
+            c2 = torch.as_tensor(_Wrap2(), device="cuda")
+            w2 = torch.from_numpy(eng.waste_scores()).cuda()
+            dist.all_reduce(c2)
+            dist.all_reduce(w2)
+            both2 = c2.cpu().numpy()
+            expander_chain([0, 1, 2], both2[:enc.T], both2[enc.T:], w2.cpu().numpy())
+        else:
+            eng.expander_best([0, 1, 2], nc2, pc2)
+        dt = 1e3 * (time.perf_counter() - t0)
+        if dist is not None:
+            tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt[0])
+        delta_ms.append(dt)
     steps = int(eng.stats().estimate_group_steps)
     if dist is not None:
         tt = torch.tensor([steps], device="cuda", dtype=torch.int64)
@@ -286,6 +314,7 @@ def decision_run(torch, dist, Engine, synth, config, rank, world, local_rank, re
     out = {"workload": synth.CONFIGS[config].name + ", node cap %d per template" % cap, "config": config, "n_gpus": world,
            "ms": float(med[0]), "load_ms": float(med[1]), "estimate_wall_ms": float(med[2]), "estimate_device_ms": float(med[3]),
            "reduce_and_expander_ms": float(med[4]), "templates_sharded": world > 1,
+           "ms_with_pending_delta": float(np.median(delta_ms)),
            "nodes_total": int(nc.sum()), "pods_scheduled_total": int(pc.sum()), "options_surviving_chain": int(mask.sum()),
            "group_steps": steps}
     if rank != 0:
@@ -426,14 +455,22 @@ def main():
             dist.all_reduce(count_t)                           # int32[T] histogram over NVLink
             ar1.record()
 
-    for _ in range(args.warmup):
+    sampler = _clock_sampler_start([local_rank]) if rank == 0 else None   # rank 0's GPU only: NVML queries delay launches
+    first_sample = None
+    if sampler is not None:
+        # nvidia-smi initialises NVML on EVERY GPU of the box (seconds on an 8-GPU host) and that stalls kernel launches:
+        # wait for its first sample line, so that the initialisation is over before the timed steps start
+        import select
+        r, _, _ = select.select([sampler.stdout], [], [], 20.0)
+        if r:
+            first_sample = sampler.stdout.readline()
+        time.sleep(0.1)
+    if dist is not None:
+        dist.barrier()
+    for _ in range(args.warmup):   # warm-up AFTER the wait above: the GPUs idled while nvidia-smi initialised
         flush_l2()
         step_resident()
     torch.cuda.synchronize()
-
-    sampler = _clock_sampler_start([local_rank]) if rank == 0 else None   # rank 0's GPU only: NVML queries delay launches
-    if sampler is not None:
-        time.sleep(0.5)            # nvidia-smi initialises NVML on every GPU of the box: keep that out of the timed steps
     launches0 = eng.stats().kernel_launches
     dev_ms, wall_ms, ar_ms = [], [], []
     for _ in range(args.steps):
@@ -544,6 +581,8 @@ def main():
     e2e_step = e2e_loop("delta")
     e2e_counts = e2e_loop("counts")
     samples = _clock_sampler_stop(sampler)
+    if first_sample and first_sample.count(",") >= 5:
+        samples.insert(0, [x.strip() for x in first_sample.split(",")])
 
     # ---- the dense pass where it is not a launch-latency test: C3 (5 x 10^8 cells) on one GPU ------------
     dense_large = None
@@ -646,6 +685,7 @@ def main():
         "config": _config_dict(cfg, P1, T, world),
         "kernel_ms": kern_ms, "allreduce_ms": allreduce_ms,
         "step_ms_max_over_ranks": {"min": step_stats[0], "median": step_stats[1], "p99": step_stats[2], "max": step_stats[3]},
+        "step_ms_rank0": [round(float(x), 5) for x in dev_ms],
         "collective": ("none" if world == 1 else ("fused exchange over NVLink peer memory inside the kernel" if fused else "NCCL all_reduce int32[T]")),
         "wall_ms_per_step": float(np.mean(wall_ms)), "clocks": cs,
         "e2e": {"value": (P1 * world) * T / (e2e_step * 1e-3), "unit": "evals/s", "ms_per_step": e2e_step,

@@ -61,7 +61,7 @@ struct GroupDyn {
   int nq;
   int qid[DYN_MAX_Q], kind[DYN_MAX_Q], k[DYN_MAX_Q], host[DYN_MAX_Q], Dc[DYN_MAX_Q], tslot[DYN_MAX_Q];
   int wown[DYN_MAX_Q], self[DYN_MAX_Q], maxskew[DYN_MAX_Q], mindom[DYN_MAX_Q], elig_new[DYN_MAX_Q], dsw[DYN_MAX_Q];
-  int minv[DYN_MAX_Q], nmin[DYN_MAX_Q], ndom[DYN_MAX_Q], tot[DYN_MAX_Q], boff[DYN_MAX_Q];
+  int minv[DYN_MAX_Q], nmin[DYN_MAX_Q], ndom[DYN_MAX_Q], tot[DYN_MAX_Q], boff[DYN_MAX_Q], nfeed[DYN_MAX_Q];
   int aff_self;
 };
 
@@ -611,28 +611,36 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
         // ---- describe the group's counters ----
         BP_PROF_BEGIN();
         __syncthreads();
-        if (tid == 0) {
-          int nq = 0;
-          for (int q = d.dc_q_off[dc]; q < d.dc_q_off[dc + 1]; ++q) {
-            if (!d.q_active[q]) continue;
-            const int k = d.q_k[q], kind = d.q_kind[q];
-            wd.qid[nq] = q; wd.kind[nq] = kind; wd.k[nq] = k; wd.host[nq] = d.is_host[k]; wd.Dc[nq] = d.Dc[k];
-            const int td = d.dom[(size_t)k * NT + N + t];
-            wd.tslot[nq] = td < 0 ? -1 : (td < d.Dc[k] ? td : d.Dc[k]);
-            wd.wown[nq] = d.q_wown[q]; wd.self[nq] = d.q_self[q];
-            wd.maxskew[nq] = kind == Q_PTS ? o.pts_max_skew[d.q_p0[q]] : 0;
-            wd.mindom[nq] = kind == Q_PTS ? o.pts_min_domains[d.q_p0[q]] : 0;
-            wd.elig_new[nq] = d.elig[(size_t)q * p.U + col_new];
-            wd.dsw[nq] = d.ds_w[(size_t)q * p.T + t];
-            wd.tot[nq] = d.base_tot[q];
-            wd.boff[nq] = d.q_base_off[q];
-            wd.minv[nq] = d.st_min1[q]; wd.nmin[nq] = d.st_nmin[q]; wd.ndom[nq] = d.st_ndom[q];
-            S.flag[nq] = 0;
-            ++nq;
+        {
+          // warp 0, one lane per counter of the class: one 64-byte record + three template-dependent values each,
+          // inactive counters are squeezed out with a ballot
+          const int q0 = d.dc_q_off[dc], qn = d.dc_q_off[dc + 1] - q0;
+          if (warp == 0) {
+            QRec r{};
+            int td = -1, en = 0, dsw = 0;
+            const int q = q0 + lane;
+            if (lane < qn) {
+              const int4* src = reinterpret_cast<const int4*>(d.qrec + q);
+              int4* dst = reinterpret_cast<int4*>(&r);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) dst[i] = __ldg(src + i);
+              td = d.dom[(size_t)r.k * NT + N + t];
+              en = d.elig[(size_t)q * p.U + col_new];
+              dsw = d.ds_w[(size_t)q * p.T + t];
+            }
+            const unsigned act = __ballot_sync(0xffffffffu, lane < qn && r.active);
+            if (lane < qn && r.active) {
+              const int i = __popc(act & ((1u << lane) - 1));
+              wd.qid[i] = q; wd.kind[i] = r.kind; wd.k[i] = r.k; wd.host[i] = r.host; wd.Dc[i] = r.Dc;
+              wd.tslot[i] = td < 0 ? -1 : (td < r.Dc ? td : r.Dc);
+              wd.wown[i] = r.wown; wd.self[i] = r.self; wd.maxskew[i] = r.maxskew; wd.mindom[i] = r.mindom;
+              wd.elig_new[i] = en; wd.dsw[i] = dsw; wd.tot[i] = r.base_tot; wd.boff[i] = r.boff;
+              wd.minv[i] = r.st_min1; wd.nmin[i] = r.st_nmin; wd.ndom[i] = r.st_ndom;
+              wd.nfeed[i] = r.nfeed;
+              S.flag[i] = 0;
+            }
+            if (lane == 0) { wd.nq = __popc(act); wd.aff_self = d.dc_aff_self[dc]; S.need_log = 0; }
           }
-          wd.nq = nq;
-          wd.aff_self = d.dc_aff_self[dc];
-          S.need_log = 0;
         }
         __syncthreads();
         const int nq = wd.nq;
@@ -710,7 +718,7 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
                 if (wd.kind[q] == Q_PTS && p0 > 0 && dsw > 0) S.flag[q] = 1;
               }
             }
-            if (d.q_nfeed[wd.qid[q]] - (wd.wown[q] > 0 ? 1 : 0) > 0) need_log = 1;
+            if (wd.nfeed[q] - (wd.wown[q] > 0 ? 1 : 0) > 0) need_log = 1;
           }
           S.need_log = need_log;
         }

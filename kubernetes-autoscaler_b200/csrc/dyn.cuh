@@ -23,6 +23,15 @@ constexpr int DYN_MAX_KEYS = 8;
 constexpr int DYN_MAX_Q = 12;  // counters per dynamic class
 enum { Q_PTS = 0, Q_AFF = 1, Q_ANTI = 2, Q_EXIST = 3 };
 
+// Everything about one counter that does not depend on the template, gathered once per load so that a thread block
+// describes a dynamic group with one 64-byte load per counter instead of fifteen dependent table reads.
+struct alignas(16) QRec {
+  int32_t kind, k, host, Dc;
+  int32_t wown, self, maxskew, mindom;
+  int32_t boff, base_tot, st_min1, st_nmin;
+  int32_t st_ndom, active, nfeed, pad;
+};
+
 struct DynTables {
   int K = 0;                        // topology keys in use
   int key_id[DYN_MAX_KEYS];         // label key id
@@ -60,6 +69,7 @@ struct DynTables {
   int32_t* st_nmin = nullptr;       // [Q] present cluster domains attaining st_min1
   int32_t* q_nfeed = nullptr;       // [Q] pending groups whose pods have non-zero weight
   uint8_t* group_feeds = nullptr;   // [E] pods of the group count for a counter of ANOTHER group
+  QRec* qrec = nullptr;             // [Q] static description of every counter (dyn_qrec_kernel)
 };
 
 // domain of universe column u for compact key k; `fresh_ordinal` numbers the nodes Estimate added

@@ -200,6 +200,21 @@ __global__ void dyn_post_code_kernel(DevObjects o, DynTables d, int U, uint8_t* 
   post_code[(size_t)dc * o.T + t] = r;
 }
 
+__global__ void dyn_qrec_kernel(DevObjects o, DynTables d) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= d.Q) return;
+  QRec r{};
+  const int k = d.q_k[q], kind = d.q_kind[q];
+  r.kind = kind; r.k = k; r.host = d.is_host[k]; r.Dc = d.Dc[k];
+  r.wown = d.q_wown[q]; r.self = d.q_self[q];
+  r.maxskew = kind == Q_PTS ? o.pts_max_skew[d.q_p0[q]] : 0;
+  r.mindom = kind == Q_PTS ? o.pts_min_domains[d.q_p0[q]] : 0;
+  r.boff = d.q_base_off[q]; r.base_tot = d.base_tot[q];
+  r.st_min1 = d.st_min1[q]; r.st_nmin = d.st_nmin[q]; r.st_ndom = d.st_ndom[q];
+  r.active = d.q_active[q]; r.nfeed = d.q_nfeed[q];
+  d.qrec[q] = r;
+}
+
 int launch_dynamic_tables(Engine* e, const uint8_t* d_spec_used, const int32_t* d_dc_ngroups) {
   DynTables& d = e->dyn;
   if (d.Q == 0) return 0;
@@ -213,7 +228,8 @@ int launch_dynamic_tables(Engine* e, const uint8_t* d_spec_used, const int32_t* 
   dyn_stats_kernel<<<(Q + 127) / 128, 128, 0, e->stream>>>(e->dobj, d);
   if (e->E > 0) dyn_feed_kernel<<<dim3((e->E + 127) / 128, Q), 128, 0, e->stream>>>(e->dobj, d, e->E, e->d_spec_dc, d_dc_ngroups);
   if (e->T > 0) dyn_post_code_kernel<<<dim3((e->T + 127) / 128, d.DC), 128, 0, e->stream>>>(e->dobj, d, U, e->d_post_code);
-  e->stats.kernel_launches += 9;
+  dyn_qrec_kernel<<<(Q + 127) / 128, 128, 0, e->stream>>>(e->dobj, d);
+  e->stats.kernel_launches += 10;
   CAE_KERNEL_OK();
   return 0;
 }
