@@ -618,9 +618,6 @@ int32_t cae_create(const cae_config* cfg, cae_engine** out) {
   cudaEventCreate(&e->ev1);
   { const char* v = getenv("CAE_K1_BITSLICE"); e->force_bitslice = v && v[0] == '1'; }
   { const char* v = getenv("CAE_K1_WARPS"); if (v && atoi(v) == 8) e->k1_warps = 8; }
-  { const char* v = getenv("CAE_PACK_LPT"); e->pack_lpt = v && v[0] == '1'; }
-  { const char* v = getenv("CAE_PACK_V1"); e->pack_v1 = v && v[0] == '1'; }
-  { const char* v = getenv("CAE_PACK_WARPS_PER_SM"); if (v && atoi(v) >= 1 && atoi(v) <= 64) e->pack_warps_per_sm = atoi(v); }
   *out = reinterpret_cast<cae_engine*>(e);
   return 0;
 }
@@ -760,7 +757,7 @@ int32_t cae_estimate_all(cae_engine* h, const int32_t* max_nodes, int32_t* node_
   if (!e->group_reason_valid && cae::launch_group_feasibility(e)) return -1;
   int rc = cae::launch_order(e);
   if (rc) return rc;
-  rc = e->pack_v1 ? cae::launch_pack(e) : cae::launch_binpack(e);
+  rc = cae::launch_binpack(e);
   if (rc) return rc;
   cudaEventRecord(e->ev1, e->stream);
   int32_t pack_status = 0;

@@ -50,6 +50,14 @@ struct BpParams {
   int act_dim[CAE_MAX_RES];
   int32_t *node_count, *pod_count, *sched, *work_counter, *status;
   long long* prof;         // optional [16] counters (CAE_PACK_PROF)
+  // filter-out-schedulable pass (FM): HintingSimulator.TrySchedulePods on the cluster nodes; `grec` then holds one record
+  // per RUN of consecutive identical pods (pad[0] = offset of the run in fm_pods)
+  int fm_runs, fm_last_index, fm_break, fm_nctrl;
+  const int32_t *fm_pods, *fm_hint, *fm_class, *fm_class_ctrl;
+  const uint8_t* fm_node_ok;
+  int32_t *fm_assigned, *fm_out;          // [P] node or -1; {lastIndex, overflowing controllers, pods scheduled, moved}
+  int32_t* fm_ctrl_cnt;                   // [controllers] classes stored per controller (zeroed)
+  uint8_t *fm_class_mark, *fm_ctrl_over;  // [classes] known unschedulable, [controllers] overflowing (zeroed)
   unsigned char* scratch;
   size_t scratch_per_cta;
 };
@@ -73,7 +81,7 @@ struct BpShared {
   long long rb[2][32][CAE_MAX_RES];   // refresh of the per-template capacity bounds
   int ri[2][32][3];
   int hist[BP_HIST + 1];      // #nodes per capacity value (closed-form lap count)
-  int t, L, rem, pre_s, log_n, overflow, newly, need_log, mlast;
+  int t, L, rem, pre_s, log_n, overflow, newly, need_log, mlast, lastnode;
 };
 
 __device__ __forceinline__ int bp_wsum(int v) { return __reduce_add_sync(0xffffffffu, v); }   // REDUX: one instruction
@@ -187,15 +195,21 @@ __device__ __forceinline__ int bp_div_f(int64_t f, int64_t r, float rinv, int kb
   return q;
 }
 
-template <int A, int TPB, bool WIN>
-__global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(DevObjects o, DynTables d, BpParams p) {
+// FM = true: the same machinery as HintingSimulator.TrySchedulePods on the CLUSTER snapshot
+// (simulator/scheduling/hinting_simulator.go:53-135; filterOutSchedulableByPacking, core/podlistprocessor/
+// filter_out_schedulable.go:96-126): ONE simulation on one thread block, no template, the node list is the N cluster nodes,
+// pods arrive as runs of consecutive identical pods in the caller's order.  Plain runs are dealt in closed form (lap by lap,
+// because every pod's node is reported), hinted pods and pods under topology counters one by one, with the
+// SimilarPodsScheduling shortcut (similar_pods.go:59-104).
+template <int A, int TPB, bool WIN, bool FM>
+__global__ void __launch_bounds__(TPB, FM ? 1 : BP_MIN_CTAS * 256 / TPB) binpack_kernel(DevObjects o, DynTables d, BpParams p) {
   constexpr int NW = TPB / 32;
   constexpr int A1 = A > 0 ? A : 1;
   extern __shared__ __align__(16) unsigned char bp_dsm[];
   __shared__ BpShared S;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = p.N, NT = p.N + p.T;
-  const int Neff = p.has_dyn ? N : 0;   // cluster nodes carry run state only when a placement can reach them
+  const int Neff = (p.has_dyn || FM) ? N : 0;   // cluster nodes carry run state only when a placement can reach them
   const int win = p.win;
   const int Xg = Neff + (win ? 0 : p.cap);
   // ---- shared window: the nodes this estimate adds ----
@@ -217,7 +231,8 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
   int32_t* wpres = wcnt + (size_t)DYN_MAX_Q * p.dstride;
   int32_t* wver = wpres + (size_t)DYN_MAX_Q * p.dstride;                                       // slot version
   int32_t* logbuf = wver + (size_t)DYN_MAX_Q * p.dstride;                                      // [log_cap][3]
-  uint8_t* g_sched = reinterpret_cast<uint8_t*>(logbuf + (size_t)p.log_cap * 3);               // [Xg]
+  int32_t* g_aux = logbuf + (size_t)p.log_cap * 3;                                            // [Xg] pods dealt to a node (FM)
+  uint8_t* g_sched = reinterpret_cast<uint8_t*>(g_aux + Xg);                                   // [Xg]
 
   // added node j (shared window, or the slab behind the cluster nodes when the window does not fit)
   auto afr = [&](int a, int j) -> int64_t& { if constexpr (WIN) return s_free[a * win + j]; else return g_free[(size_t)a * Xg + Neff + j]; };
@@ -250,7 +265,8 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
     __syncthreads();
     if (tid == 0) {
       const int i = atomicAdd(p.work_counter, 1);
-      S.t = i >= p.t_end - p.t_begin ? p.t_end : (p.perm ? p.perm[i] : p.t_begin + i);
+      if (FM) S.t = i == 0 ? 0 : p.t_end;
+      else S.t = i >= p.t_end - p.t_begin ? p.t_end : (p.perm ? p.perm[i] : p.t_begin + i);
       S.log_n = 0; S.overflow = 0;
     }
     __syncthreads();
@@ -260,12 +276,25 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
 
     int64_t tfree[A1];
 #pragma unroll
-    for (int a = 0; a < A; ++a) tfree[a] = p.tmpl_free[(size_t)a * p.T + t];
-    const int tslots = p.tmpl_slots[t];
-    const int max_nodes = p.max_nodes ? p.max_nodes[t] : 0;
+    for (int a = 0; a < A; ++a) tfree[a] = FM ? 0 : p.tmpl_free[(size_t)a * p.T + t];
+    const int tslots = FM ? 0 : p.tmpl_slots[t];
+    const int max_nodes = (!FM && p.max_nodes) ? p.max_nodes[t] : 0;
     const int col_new = N + p.T + t;  // universe column of the sanitized template
-    int n_new = 0, nodes_with_pods = 0, pods_total = 0, last_index = 0;
-    bool new_nodes_available = true, cl_init = false;
+    int n_new = 0, nodes_with_pods = 0, pods_total = 0, last_index = FM ? p.fm_last_index : 0;
+    bool new_nodes_available = !FM, cl_init = false, fm_stop = false, fm_moved = false;
+    auto ensure_cluster = [&]() {  // run state of the cluster nodes, needed once a placement can reach them
+      if (cl_init) return;
+      for (int x = tid; x < N; x += TPB) {
+#pragma unroll
+        for (int a = 0; a < A; ++a) g_free[(size_t)a * Xg + x] = p.c_free[(size_t)a * N + x];
+        g_slots[x] = p.c_slots[x];
+        g_ports[x] = 0ull;
+        g_sched[x] = 0;
+      }
+      cl_init = true;
+      __syncthreads();
+    };
+    if (FM) ensure_cluster();
     // Upper bounds of what ANY added node still has (free only shrinks, so a stale bound stays valid): a group whose
     // request exceeds them skips its pass over the open nodes; tightened whenever such a pass finds no room at all.
     int64_t maxfree[A1];
@@ -296,7 +325,7 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
       for (int a = 0; a < A; ++a) maxfree[a] = bp_wmax_ll(lane < NW ? S.rb[par][lane][a] : LLONG_MIN);
       par ^= 1;
     };
-    const int n_groups = p.order_n[t];
+    const int n_groups = FM ? p.fm_runs : p.order_n[t];
 
     auto log_append = [&](int x, int spec, int cnt) {  // any thread
       const int idx = atomicAdd(&S.log_n, 1);
@@ -446,7 +475,7 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
 
     // Group records travel one group ahead: warp 0 copies the next group's record into shared memory with cp.async
     // while the block works on the current one; the order row is read two entries ahead.
-    const int32_t* order_row = p.order + (size_t)t * p.E;
+    const int32_t* order_row = FM ? nullptr : p.order + (size_t)t * p.E;   // FM: the runs in order
     auto fetch_rec = [&](int graw, int buf) {
       if (warp == 0) {
         if (lane < 9) bp_cp_async16(reinterpret_cast<char*>(&S.rec[buf]) + lane * 16,
@@ -454,7 +483,7 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
         bp_cp_async_commit();
       }
     };
-    int ord_cur = n_groups > 0 ? order_row[0] : 0, ord_next = n_groups > 1 ? order_row[1] : 0;
+    int ord_cur = n_groups > 0 ? (FM ? 0 : order_row[0]) : 0, ord_next = n_groups > 1 ? (FM ? 1 : order_row[1]) : 0;
     if (n_groups > 0) fetch_rec(ord_cur, 0);
     if (warp == 0) bp_cp_async_wait();
     __syncthreads();
@@ -462,7 +491,7 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
     for (int gi = 0; gi < n_groups; ++gi) {
       const GroupRec& rc = S.rec[gi & 1];
       if (gi + 1 < n_groups) fetch_rec(ord_next, (gi + 1) & 1);
-      const int ord_next2 = gi + 2 < n_groups ? order_row[gi + 2] : 0;
+      const int ord_next2 = gi + 2 < n_groups ? (FM ? gi + 2 : order_row[gi + 2]) : 0;
       const int g = ord_cur & ~ORDER_NOT_ON_FRESH;
       int n = rc.n;
       const int spec = rc.spec;
@@ -477,6 +506,7 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
       const unsigned long long pconf = rc.pconf;  // port sets this pod collides with
       const unsigned long long pbit = rc.pbit;
       const bool feeds = (rc.flags & GREC_FEEDS) != 0;
+      const int pb = rc.pad[0];   // FM: offset of the run in fm_pods
       bool can_existing = n_new > 0 && static_new && maxslots >= 1;   // some added node may still take this pod
 #pragma unroll
       for (int a = 0; a < A; ++a) can_existing = can_existing && !(req[a] > 0 && req[a] > maxfree[a]);
@@ -572,7 +602,133 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
         __syncthreads();
       };
 
-      if (dc == 0) {
+      // SimilarPodsScheduling (similar_pods.go:59-104): a pod that fitted nowhere marks its (controller, spec) class, at most
+      // 10 classes per controller; later pods of a marked class are not tried
+      const int fm_cls = (FM && p.fm_class) ? p.fm_class[p.fm_pods[pb]] : -1;
+      bool fm_blocked = FM && fm_cls >= 0 && p.fm_class_mark[fm_cls] != 0;
+      auto fm_mark_failed = [&]() {
+        if (fm_cls < 0) return;
+        const int ctrl = p.fm_class_ctrl[fm_cls];
+        const int cnt = p.fm_ctrl_cnt[ctrl];
+        __syncthreads();
+        if (tid == 0) {
+          if (cnt >= 10) p.fm_ctrl_over[ctrl] = 1;
+          else { p.fm_ctrl_cnt[ctrl] = cnt + 1; p.fm_class_mark[fm_cls] = 1; }
+        }
+        if (cnt < 10) fm_blocked = true;
+        __syncthreads();
+      };
+      const int fm_hint = (FM && p.fm_hint) ? p.fm_hint[p.fm_pods[pb]] : -1;   // hinted pods are singleton runs
+      // FM: deal m identical pods over the cluster nodes with capacities g_kc[x], lap by lap (lap l serves the nodes with
+      // capacity >= l in cyclic order from lastIndex), reporting every pod's node; books the pods and moves lastIndex
+      auto fm_deal = [&](int m) {
+        const int s = last_index < N ? last_index : 0;
+        for (int x = tid; x < N; x += TPB) g_aux[x] = 0;
+        int done = 0, lap = 1;
+        while (done < m) {
+          int basecnt = 0;
+          for (int base = 0; base < N; base += TPB) {
+            const int x = base + tid;
+            const bool ex = x < N && g_kc[x] >= lap;
+            const unsigned mm = __ballot_sync(0xffffffffu, ex);
+            if (lane == 0) S.ri[par][warp][0] = __popc(mm);
+            __syncthreads();
+            const int v = lane < NW ? S.ri[par][lane][0] : 0;
+            int inc = v;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+              const int u = __shfl_up_sync(0xffffffffu, inc, off);
+              if (lane >= off) inc += u;
+            }
+            const int wpre = __shfl_sync(0xffffffffu, inc - v, warp);
+            const int all = __shfl_sync(0xffffffffu, inc, 31);
+            if (x < N) {
+              const int pj = basecnt + wpre + __popc(mm & ((1u << lane) - 1));
+              g_pre[x] = pj;
+              if (x == s) S.pre_s = pj;
+            }
+            basecnt += all;
+            par ^= 1;
+          }
+          __syncthreads();
+          const int pre_s = S.pre_s, tot = basecnt, take = min(tot, m - done);
+          for (int x = tid; x < N; x += TPB) {
+            if (g_kc[x] < lap) continue;
+            int rank = g_pre[x] - pre_s;
+            if (x < s) rank += tot;
+            if (rank < take) {
+              p.fm_assigned[p.fm_pods[pb + done + rank]] = x;
+              g_aux[x] += 1;
+              if (rank == take - 1) S.lastnode = x;
+            }
+          }
+          done += take;
+          ++lap;
+          __syncthreads();
+        }
+        if (m > 0) {
+          for (int x = tid; x < N; x += TPB) if (g_aux[x] > 0) book_c(x, g_aux[x]);
+          last_index = (S.lastnode + 1) % N;
+          fm_moved = true;
+          placed += m;
+        }
+        __syncthreads();
+      };
+      if (FM && dc == 0 && fm_hint < 0) {
+        // ======================= plain run on the cluster nodes: dealt lap by lap ==================
+        if (fm_stop || fm_blocked || N == 0) {
+          if (p.fm_break && n > 0) fm_stop = true;     // every pod of the run stays unschedulable (breakOnFailure, :71-73)
+        } else {
+          int total = 0, zero = 0, zero2 = 0;
+          const int clampv = n < (1 << 26) ? n + 1 : (1 << 26);
+          for (int x = tid; x < N; x += TPB) {
+            const bool ok = (p.pre_code[(size_t)sc * p.U + x] & 0x0F) == 0 && !o.node_unschedulable[x] && (!p.fm_node_ok || p.fm_node_ok[x]);
+            const int k = ok ? res_cap_c(x, n) : 0;
+            g_kc[x] = k;
+            total = min(total + min(k, clampv), clampv);
+          }
+          blk_csum_max_sum<NW>(S, par, clampv, total, zero, zero2);
+          const int m = min(n, total);     // pods that find a node
+          fm_deal(m);
+          if (m < n) {                      // the next pod fits nowhere: the identical pods behind it see the same state
+            fm_mark_failed();
+            if (p.fm_break) fm_stop = true;
+          }
+        }
+      } else if (FM && dc == 0) {
+        // ======================= hinted plain pod (singleton run) ==================================
+        int where = -1;
+        if (!fm_stop) {
+          const int h = fm_hint;   // tryScheduleUsingHints (:80-106); lastIndex untouched
+          if (h >= 0 && h < N && (!p.fm_node_ok || p.fm_node_ok[h]) && (p.pre_code[(size_t)sc * p.U + h] & 0x0F) == 0 && res_cap_c(h, 1) > 0) {
+            __syncthreads();
+            if (tid == 0) book_c(h, 1);
+            __syncthreads();
+            where = h;
+            placed += 1;
+          }
+          if (where < 0 && !fm_blocked && N > 0) {   // SchedulePodOnAnyNodeMatching (:117): whole list, cyclic from lastIndex
+            int best = INT_MAX, zero = 0;
+            for (int x = tid; x < N; x += TPB) {
+              if (o.node_unschedulable[x] || (p.fm_node_ok && !p.fm_node_ok[x]) || (p.pre_code[(size_t)sc * p.U + x] & 0x0F) != 0) continue;
+              if (res_cap_c(x, 1) > 0) { int dd = x - last_index; if (dd < 0) dd += N; best = min(best, dd); }
+            }
+            blk_min_sum<NW>(S, par, best, zero);
+            if (best != INT_MAX) {
+              int hit = last_index + best;
+              if (hit >= N) hit -= N;
+              if (tid == 0) book_c(hit, 1);
+              __syncthreads();
+              last_index = (hit + 1) % N;
+              fm_moved = true;
+              where = hit;
+              placed += 1;
+            } else fm_mark_failed();
+          }
+          if (where < 0 && p.fm_break) fm_stop = true;
+        }
+        if (tid == 0) p.fm_assigned[p.fm_pods[pb]] = where;
+      } else if (dc == 0) {
         // ======================= plain group: closed form =======================================
         BP_PROF_COUNT(8, 1);
         BP_PROF_BEGIN();
@@ -602,7 +758,7 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
           if (!stop) add_new_nodes(fresh_cap(n), false);
         }
         BP_PROF_END(1);
-      } else if (!new_nodes_available && !can_existing) {
+      } else if (!FM && !new_nodes_available && !can_existing) {
         // no node may be added any more and no added node has room: every pod of the group fails at once
       } else {
         // ======================= dynamic group ===================================================
@@ -624,9 +780,11 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
               int4* dst = reinterpret_cast<int4*>(&r);
 #pragma unroll
               for (int i = 0; i < 4; ++i) dst[i] = __ldg(src + i);
-              td = d.dom[(size_t)r.k * NT + N + t];
-              en = d.elig[(size_t)q * p.U + col_new];
-              dsw = d.ds_w[(size_t)q * p.T + t];
+              if (!FM) {   // FM: no template, nothing is ever added
+                td = d.dom[(size_t)r.k * NT + N + t];
+                en = d.elig[(size_t)q * p.U + col_new];
+                dsw = d.ds_w[(size_t)q * p.T + t];
+              }
             }
             const unsigned act = __ballot_sync(0xffffffffu, lane < qn && r.active);
             if (lane < qn && r.active) {
@@ -718,7 +876,7 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
                 if (wd.kind[q] == Q_PTS && p0 > 0 && dsw > 0) S.flag[q] = 1;
               }
             }
-            if (wd.nfeed[q] - (wd.wown[q] > 0 ? 1 : 0) > 0) need_log = 1;
+            if (FM || wd.nfeed[q] - (wd.wown[q] > 0 ? 1 : 0) > 0) need_log = 1;   // FM: earlier runs of this very spec count too
           }
           S.need_log = need_log;
         }
@@ -763,19 +921,6 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
           }
         }
 
-        auto ensure_cluster = [&]() {  // run state of the cluster nodes, needed once a fallback can place onto them
-          if (cl_init) return;
-          for (int x = tid; x < N; x += TPB) {
-#pragma unroll
-            for (int a = 0; a < A; ++a) g_free[(size_t)a * Xg + x] = p.c_free[(size_t)a * N + x];
-            g_slots[x] = p.c_slots[x];
-            g_ports[x] = 0ull;
-            g_sched[x] = 0;
-          }
-          cl_init = true;
-          __syncthreads();
-        };
-
         BP_PROF_END(2);
         // ---- capacity form: every counter of the group is either a per-node capacity or a budget ----
         // Hostname counters (each node is its own domain): a spread constraint whose global minimum is pinned at 0
@@ -796,6 +941,7 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
           }
           // the fallback of :186-205 places onto cluster nodes, whose other-key domains differ: per-pod loop
           if (hp >= 0 && (any_z || wd.minv[hp] != 0)) ok = false;
+          if (FM && (any_z || fm_hint >= 0)) ok = false;   // other-key domains differ between cluster nodes / hinted pod: one by one
           // capacity a hostname counter puts on a node whose domain (slot sl, -1 = label missing) holds c matches
           auto hq_cap = [&](int q, int sl, int c, bool counted) -> int {
             if (wd.kind[q] == Q_PTS) {
@@ -876,7 +1022,8 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
             ensure_cluster();
             int blocked = 0;
             for (int x = tid; x < N; x += TPB) {
-              const bool stat_ok = (p.pre_code[(size_t)sc * p.U + x] & 0x0F) == 0 && !o.node_unschedulable[x];
+              const bool stat_ok = (p.pre_code[(size_t)sc * p.U + x] & 0x0F) == 0 && !o.node_unschedulable[x] &&
+                                   !(FM && p.fm_node_ok && !p.fm_node_ok[x]);
               const int rc = stat_ok ? res_cap_c(x, n) : 0;
               int cp, ci;
               h_caps(x, cp, ci);
@@ -894,7 +1041,25 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
             return blocked > 0;
           };
           if (ok && hp >= 0 && !(wd.wown[hp] == 0 || wd.nmin[hp] > n)) ok = N > 0 ? cluster_caps() : false;   // is the minimum pinned?
-          if (ok) {
+          if (FM && ok) {
+            // hostname counters only: per-node capacities over the cluster nodes, dealt like a plain run
+            fast = true;
+            if (fm_stop || fm_blocked || N == 0) {
+              if (p.fm_break && n > 0) fm_stop = true;
+            } else {
+              if (!caps_done) cluster_caps();
+              const int clampv = n < (1 << 26) ? n + 1 : (1 << 26);
+              int total = 0, zero = 0, zero2 = 0;
+              for (int x = tid; x < N; x += TPB) total = min(total + min(g_kc[x], clampv), clampv);
+              blk_csum_max_sum<NW>(S, par, clampv, total, zero, zero2);
+              const int m = min(n, total);
+              fm_deal(m);
+              if (m < n) {
+                fm_mark_failed();
+                if (p.fm_break) fm_stop = true;
+              }
+            }
+          } else if (ok) {
             fast = true;
             const bool uni = !need_log;   // no other group feeds these counters: every added node reads the defaults
             int b = B;                    // pods the budget still admits
@@ -1108,6 +1273,41 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
           run_flagged();
         };
 
+        if constexpr (FM) {
+          // ---- HintingSimulator.TrySchedulePods over the cluster nodes, pod by pod ----
+          const int run_n = n;
+          bool run_failed = false;  // a pod of this run fitted nowhere: the identical pods behind it see the same state
+          for (int i = 0; i < run_n; ++i) {
+            const int pod = p.fm_pods[pb + i];
+            int where = -1;
+            if (!fm_stop) {
+              const int h = p.fm_hint ? p.fm_hint[pod] : -1;   // tryScheduleUsingHints (:80-106); lastIndex untouched
+              if (h >= 0 && h < N && (!p.fm_node_ok || p.fm_node_ok[h]) && eval(h) == CAE_R_OK) { place(h); where = h; }
+              if (where < 0 && !fm_blocked && !run_failed && N > 0) {
+                // SchedulePodOnAnyNodeMatching (:117): whole list, cyclic from lastIndex
+                int best = INT_MAX, zero = 0;
+                for (int x = tid; x < N; x += TPB) {
+                  if (o.node_unschedulable[x] || (p.fm_node_ok && !p.fm_node_ok[x])) continue;
+                  if (eval(x) == CAE_R_OK) { int dd = x - last_index; if (dd < 0) dd += N; best = min(best, dd); }
+                }
+                blk_min_sum<NW>(S, par, best, zero);
+                if (best != INT_MAX) {
+                  int hit = last_index + best;
+                  if (hit >= N) hit -= N;
+                  place(hit);
+                  last_index = (hit + 1) % N;
+                  fm_moved = true;
+                  where = hit;
+                } else {
+                  run_failed = true;
+                  fm_mark_failed();
+                }
+              }
+              if (where < 0 && p.fm_break) fm_stop = true;   // breakOnFailure (:71-73)
+            }
+            if (tid == 0) p.fm_assigned[pod] = where;
+          }
+        } else {
         // ---- tryToScheduleOnExistingNodes: per pod, first passing added node in cyclic order ----
         BP_PROF_BEGIN();
         while (n > 0 && can_existing) {
@@ -1165,17 +1365,26 @@ __global__ void __launch_bounds__(TPB, BP_MIN_CTAS * 256 / TPB) binpack_kernel(D
         }
         BP_PROF_END(6);
         BP_PROF_COUNT(11, placed);
+        }  // !FM
         }  // !fast
       }
       pods_total += placed;
-      if (tid == 0) p.sched[(size_t)t * p.E + g] = placed;
+      if (!FM && tid == 0) p.sched[(size_t)t * p.E + g] = placed;
       if (warp == 0) bp_cp_async_wait();   // the next group's record has landed
       __syncthreads();
       ord_cur = ord_next;
       ord_next = ord_next2;
     }
     if (p.prof && tid == 0) atomicAdd((unsigned long long*)&p.prof[7], (unsigned long long)(clock64() - prof_tmpl0));
-    if (tid == 0) {
+    if constexpr (FM) {
+      int over = 0, zero = 0;
+      for (int c = tid; c < p.fm_nctrl; c += TPB) over += p.fm_ctrl_over[c] != 0;
+      blk_sum_max<NW>(S, par, over, zero);
+      if (tid == 0) {
+        p.fm_out[0] = last_index; p.fm_out[1] = over; p.fm_out[2] = pods_total; p.fm_out[3] = fm_moved ? 1 : 0;
+        if (S.overflow && p.status) atomicExch(p.status, 1);
+      }
+    } else if (tid == 0) {
       p.node_count[t] = nodes_with_pods;
       p.pod_count[t] = pods_total;
       if (S.overflow && p.status) atomicExch(p.status, 1);
@@ -1206,7 +1415,7 @@ __global__ void lpt_rank_kernel(const long long* __restrict__ cost, int t_begin,
 
 template <int A, int TPB>
 static int launch_binpack_at(Engine* e, int blocks_wanted, size_t smem, const BpParams& p, int* blocks_out, bool query_only) {
-  auto kern = p.win ? binpack_kernel<A, TPB, true> : binpack_kernel<A, TPB, false>;
+  auto kern = p.win ? binpack_kernel<A, TPB, true, false> : binpack_kernel<A, TPB, false, false>;
   CAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   CAE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, smem));
@@ -1269,7 +1478,7 @@ int launch_binpack(Engine* e) {
   for (int k = 0; k < e->dyn.K; ++k) dmax = std::max(dmax, e->dyn.Dc[k] + 1 + (e->dyn.is_host[k] ? cap : 0));
   p.dstride = p.has_dyn ? dmax : 1;
   p.log_cap = p.has_dyn ? (int)std::min<size_t>(4 * ((size_t)Neff + cap) + 1024, (size_t)1 << 24) : 1;
-  size_t per_cta = 16 + Xg * ((size_t)A1 * 8 + 8 + 4 + 4 + 4) + (size_t)3 * DYN_MAX_Q * p.dstride * 4 + (size_t)p.log_cap * 12 + Xg;
+  size_t per_cta = 16 + Xg * ((size_t)A1 * 8 + 8 + 4 + 4 + 4 + 4) + (size_t)3 * DYN_MAX_Q * p.dstride * 4 + (size_t)p.log_cap * 12 + Xg;
   per_cta = (per_cta + 255) & ~(size_t)255;
   p.scratch_per_cta = per_cta;
   int blocks = 0;
@@ -1316,6 +1525,101 @@ int launch_binpack(Engine* e) {
             "counts{plain=%lld fast=%lld generic=%lld generic_pods=%lld genA_iters=%lld genB_iters=%lld cluster_caps=%lld cluster_phase=%lld}\n",
             launched, smem, p.win, h[0], h[1], h[2], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11], h[12], h[13], h[14], h[15]);
   }
+  return 0;
+}
+
+// ---- filter-out-schedulable pass -----------------------------------------------------------------------------------------
+__global__ void run_rec_kernel(DevObjects o, DynTables d, int runs, const int32_t* __restrict__ run_off, const int32_t* __restrict__ pods,
+                               int n_act, const int* __restrict__ act_dim, int has_dyn, const int32_t* __restrict__ spec_sc,
+                               const int32_t* __restrict__ spec_dc, const int32_t* __restrict__ pc_of,
+                               const unsigned long long* __restrict__ port_conf, GroupRec* __restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= runs) return;
+  GroupRec g{};
+  const int pb = run_off[r];
+  g.n = run_off[r + 1] - pb;
+  g.pad[0] = pb;
+  const int spec = o.pend_spec[pods[pb]];
+  g.spec = spec;
+  g.sc = spec_sc[spec];
+  g.dc = has_dyn ? spec_dc[spec] : 0;
+  const int plist = o.ps_port_list[spec];
+  const bool has_ports = o.port_off[plist + 1] > o.port_off[plist];
+  g.pconf = has_ports ? port_conf[plist] : 0ull;
+  g.pbit = has_ports ? (1ull << pc_of[plist]) : 0ull;
+  bool feeds = false;   // runs are not groups: log every placement that some counter counts
+  if (has_dyn) for (int q = 0; q < d.Q && !feeds; ++q) feeds = d.wmat[(size_t)q * d.S + spec] != 0;
+  g.flags = (has_ports ? GREC_HAS_PORTS : 0u) | (feeds ? GREC_FEEDS : 0u) | (o.ps_hostname_spread[spec] ? GREC_HOST_SPREAD : 0u);
+  for (int a = 0; a < n_act; ++a) {
+    g.req[a] = o.ps_req[(size_t)spec * R + act_dim[a]];
+    g.rinv[a] = g.req[a] > 0 ? __frcp_rn(__ll2float_rn(g.req[a])) : 0.f;
+  }
+  out[r] = g;
+}
+
+template <int A>
+static void launch_filter_a(cudaStream_t st, const DevObjects& o, const DynTables& d, const BpParams& p) {
+  binpack_kernel<A, 512, false, true><<<1, 512, 0, st>>>(o, d, p);
+}
+
+// HintingSimulator.TrySchedulePods on the cluster snapshot (one thread block).  `f` = device blob laid out by
+// cae_filter_schedulable (api.cu); class marks and controller counters are zeroed there.
+int launch_filter(Engine* e, const FilterLaunch& f) {
+  BpParams p{};
+  p.E = e->E; p.T = e->T; p.N = e->N; p.U = e->U;
+  p.has_dyn = e->has_dynamic ? 1 : 0;
+  for (int a = 0; a < CAE_MAX_RES; ++a) p.act_dim[a] = e->act_dim[a];
+  p.pre_code = e->d_pre_code; p.spec_sc = e->d_spec_sc; p.spec_dc = e->d_spec_dc;
+  p.pc_of = e->d_pc_of; p.port_conf = e->d_port_conf; p.c_free = e->d_c_free; p.c_slots = e->d_c_slots;
+  p.work_counter = e->d_work_counter; p.status = e->d_work_counter + 1;
+  p.t_begin = 0; p.t_end = 1; p.cap = 0; p.win = 0;
+  p.fm_runs = f.runs; p.fm_last_index = f.last_index; p.fm_break = f.break_on_failure; p.fm_nctrl = f.nctrl;
+  p.fm_pods = f.pods; p.fm_hint = f.hint; p.fm_class = f.cls; p.fm_class_ctrl = f.class_ctrl;
+  p.fm_node_ok = f.node_ok; p.fm_assigned = f.assigned; p.fm_out = f.out;
+  p.fm_ctrl_cnt = f.ctrl_cnt; p.fm_class_mark = f.class_mark; p.fm_ctrl_over = f.ctrl_over;
+  const int A1 = std::max(e->A, 1);
+  const size_t Xg = (size_t)e->N;
+  int dmax = 1;
+  for (int k = 0; k < e->dyn.K; ++k) dmax = std::max(dmax, e->dyn.Dc[k] + 2);
+  p.dstride = p.has_dyn ? dmax : 1;
+  p.log_cap = p.has_dyn ? f.n_pods + 1024 : 1;   // one entry per placement at most
+  size_t per_cta = 16 + Xg * ((size_t)A1 * 8 + 8 + 4 + 4 + 4 + 4) + (size_t)3 * DYN_MAX_Q * p.dstride * 4 + (size_t)p.log_cap * 12 + Xg;
+  per_cta = (per_cta + 255) & ~(size_t)255;
+  p.scratch_per_cta = per_cta;
+  const size_t rec_bytes = ((size_t)std::max(f.runs, 1) * sizeof(GroupRec) + 255) & ~(size_t)255;
+  const size_t need = per_cta + rec_bytes;
+  const size_t sig = per_cta * 1000003u + Xg * 10007u + (size_t)p.dstride * 101u + (size_t)p.log_cap * 7u + (size_t)A1 + 0x7000000000ull;
+  if (need > e->fm_scratch_bytes) {
+    if (e->d_fm_scratch) cudaFree(e->d_fm_scratch);
+    e->d_fm_scratch = nullptr;
+    e->fm_scratch_bytes = 0;
+    CAE_CUDA(cudaMalloc(&e->d_fm_scratch, need));
+    e->fm_scratch_bytes = need;
+    e->fm_layout_sig = 0;
+  }
+  if (sig != e->fm_layout_sig) {
+    CAE_CUDA(cudaMemsetAsync(e->d_fm_scratch, 0, need, e->stream));
+    e->fm_layout_sig = sig;
+  }
+  p.scratch = static_cast<unsigned char*>(e->d_fm_scratch);
+  GroupRec* d_rec = reinterpret_cast<GroupRec*>(p.scratch + per_cta);
+  p.grec = d_rec;
+  CAE_CUDA(cudaMemsetAsync(e->d_work_counter, 0, sizeof(int32_t) * 2, e->stream));
+  run_rec_kernel<<<(f.runs + 127) / 128, 128, 0, e->stream>>>(e->dobj, e->dyn, f.runs, f.run_off, f.pods, e->A, e->d_act_dim, p.has_dyn,
+                                                             e->d_spec_sc, e->d_spec_dc, e->d_pc_of, e->d_port_conf, d_rec);
+  switch (e->A) {
+    case 0: launch_filter_a<0>(e->stream, e->dobj, e->dyn, p); break;
+    case 1: launch_filter_a<1>(e->stream, e->dobj, e->dyn, p); break;
+    case 2: launch_filter_a<2>(e->stream, e->dobj, e->dyn, p); break;
+    case 3: launch_filter_a<3>(e->stream, e->dobj, e->dyn, p); break;
+    case 4: launch_filter_a<4>(e->stream, e->dobj, e->dyn, p); break;
+    case 5: launch_filter_a<5>(e->stream, e->dobj, e->dyn, p); break;
+    case 6: launch_filter_a<6>(e->stream, e->dobj, e->dyn, p); break;
+    case 7: launch_filter_a<7>(e->stream, e->dobj, e->dyn, p); break;
+    default: launch_filter_a<8>(e->stream, e->dobj, e->dyn, p); break;
+  }
+  e->stats.kernel_launches += 2;
+  CAE_KERNEL_OK();
   return 0;
 }
 

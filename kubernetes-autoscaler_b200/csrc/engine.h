@@ -119,10 +119,8 @@ struct Engine {
   uint8_t lut_word[CAE_MAX_RES] = {0}, lut_shift[CAE_MAX_RES] = {0};
   uint32_t lut_mask[CAE_MAX_RES] = {0};
   uint32_t* d_rlut = nullptr;             // [lut_rows][Twp]
-  bool pack_lpt = false;                  // CAE_PACK_LPT=1: hand templates to the estimator warps longest first (experimental, off)
   long long* d_tmpl_cost = nullptr;       // [T] pods in the schedulable groups of a template (order kernel)
   int32_t* d_perm = nullptr;              // [T] work order of the pack
-  int pack_warps_per_sm = 20;             // resident estimator warps per SM (CAE_PACK_WARPS_PER_SM)
   int k1_warps = 16;                      // warps per thread block of the LUT variant (CAE_K1_WARPS=8|16)
   bool force_bitslice = false;            // CAE_K1_BITSLICE=1: always take the bit-sliced comparator (tests)
   int32_t* d_pod_sc = nullptr;            // [P]
@@ -179,7 +177,6 @@ struct Engine {
   int num_podspecs = 0;
   int sm_count = 148;
   int smem_optin = 227 * 1024;             // opt-in shared memory per thread block
-  bool pack_v1 = false;                   // CAE_PACK_V1=1: the round-1 warp-per-template estimator (A/B measurements only)
 };
 
 // kernels.cu
@@ -193,7 +190,6 @@ int launch_feasibility(Engine* e, bool want_reasons);
 int launch_group_feasibility(Engine* e);
 int launch_order(Engine* e);
 int launch_group_records(Engine* e);     // GroupRec[E] (after the class / counter tables of a load)
-int launch_pack(Engine* e);      // round-1 estimator kernel (pack.cu): kept for A/B runs and the filter pass
 int launch_binpack(Engine* e);   // K3: block-per-template estimator (binpack.cu)
 struct FilterLaunch {
   int runs, n_pods, last_index, break_on_failure, nctrl;

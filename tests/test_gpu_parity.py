@@ -359,18 +359,27 @@ def test_dense_many_distinct_requests(eng, oracle):
     _check_dense(eng, oracle, enc)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("CAE_TEST_EXPERIMENTAL") != "1",
-                    reason="CAE_PACK_LPT is an unmeasured, default-off work order (written after the round's GPU budget ran out)")
-def test_pack_longest_first_order(oracle, monkeypatch):
-    """CAE_PACK_LPT=1 only permutes the order in which templates are handed to warps: results must not change."""
+def test_estimate_is_independent_of_the_work_order(oracle):
+    """The estimator hands templates to thread blocks longest-first (device-side LPT over the pods of their schedulable
+    groups); a template's result must not depend on which block simulates it or when: two engines, two shards."""
     from kubernetes_autoscaler_b200.engine import Engine
-    monkeypatch.setenv("CAE_PACK_LPT", "1")
-    e = Engine(device=0)
-    try:
-        for enc in (synth.generate(2, pods=6_000, templates=96), synth.generate(3, pods=3_000, templates=70, cluster_nodes=40)):
-            _check_estimate(e, oracle, enc, np.full(enc.T, 1000))
-    finally:
-        e.close()
+    for enc in (synth.generate(2, pods=6_000, templates=96), synth.generate(3, pods=3_000, templates=70, cluster_nodes=40)):
+        caps = np.full(enc.T, 1000, np.int32)
+        onc, opc, osched, oorder, _ = oracle.estimate_all(enc, caps)
+        rows = np.zeros((2, enc.T), np.int64)
+        for rank in (0, 1):
+            e = Engine(device=0, rank=rank, world_size=2)
+            try:
+                e.load(enc)
+                nc, pc, sched, order = e.estimate_all(caps)
+                tb, te = e.template_shard(enc.T)
+                assert np.array_equal(nc[tb:te], onc[tb:te]) and np.array_equal(pc[tb:te], opc[tb:te])
+                assert np.array_equal(sched[tb:te], osched[tb:te]) and np.array_equal(order[tb:te], oorder[tb:te])
+                assert not nc[:tb].any() and not nc[te:].any()     # rows of the other shard stay zero (sum all-reduce assembles)
+                rows[rank] = nc
+            finally:
+                e.close()
+        assert np.array_equal(rows.sum(axis=0), onc)
 
 
 def test_price_scores_bit_exact(eng, oracle):
