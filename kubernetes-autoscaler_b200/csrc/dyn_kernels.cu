@@ -122,21 +122,35 @@ __global__ void dyn_dsw_kernel(DevObjects o, DynTables d) {
 }
 
 // min / second min / number of present domains per PTS counter (criticalPaths, filtering.go:97-136)
+// one WARP per counter: lanes stride over its cluster domains; (min, smallest index attaining it, min over the OTHER present
+// domains, #present domains, #domains at the min) merged with shuffles
 __global__ void dyn_stats_kernel(DevObjects o, DynTables d) {
-  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (q >= d.Q) return;
-  int m1 = INT_MAX, a1 = -1, m2 = INT_MAX, nd = 0;
+  int m1 = INT_MAX, a1 = INT_MAX, m2 = INT_MAX, nd = 0;
   const int off = d.q_base_off[q], n = d.q_base_off[q + 1] - off;
-  for (int i = 0; i < n; ++i) {
+  for (int i = lane; i < n; i += 32) {
     if (d.base_pres[off + i] <= 0) continue;
     ++nd;
-    int c = d.base_cnt[off + i];
+    const int c = d.base_cnt[off + i];
     if (c < m1) { m2 = m1; m1 = c; a1 = i; }
     else if (c < m2) m2 = c;
   }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    const int om1 = __shfl_xor_sync(0xffffffffu, m1, s), oa1 = __shfl_xor_sync(0xffffffffu, a1, s);
+    const int om2 = __shfl_xor_sync(0xffffffffu, m2, s), ond = __shfl_xor_sync(0xffffffffu, nd, s);
+    nd += ond;
+    if (om1 < m1 || (om1 == m1 && oa1 < a1)) { m2 = min(om2, m1); m1 = om1; a1 = oa1; }   // the other side holds the minimum
+    else m2 = min(m2, om1);
+  }
   int nm = 0;
-  for (int i = 0; i < n; ++i) if (d.base_pres[off + i] > 0 && d.base_cnt[off + i] == m1) ++nm;
-  d.st_min1[q] = m1; d.st_arg1[q] = a1; d.st_min2[q] = m2; d.st_ndom[q] = nd; d.st_nmin[q] = nm;
+  for (int i = lane; i < n; i += 32) if (d.base_pres[off + i] > 0 && d.base_cnt[off + i] == m1) ++nm;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) nm += __shfl_xor_sync(0xffffffffu, nm, s);
+  if (lane == 0) {
+    d.st_min1[q] = m1; d.st_arg1[q] = a1 == INT_MAX ? -1 : a1; d.st_min2[q] = m2; d.st_ndom[q] = nd; d.st_nmin[q] = nm;
+  }
 }
 
 __global__ void dyn_feed_kernel(DevObjects o, DynTables d, int E, const int32_t* __restrict__ spec_dc,
@@ -225,7 +239,7 @@ int launch_dynamic_tables(Engine* e, const uint8_t* d_spec_used, const int32_t* 
   dyn_elig_kernel<<<dim3((U + 127) / 128, Q), 128, 0, e->stream>>>(e->dobj, d, U, e->d_pre_code);
   if (e->N > 0) dyn_base_kernel<<<dim3((e->N + 127) / 128, Q), 128, 0, e->stream>>>(e->dobj, d, U);
   if (e->T > 0) dyn_dsw_kernel<<<dim3((e->T + 127) / 128, Q), 128, 0, e->stream>>>(e->dobj, d);
-  dyn_stats_kernel<<<(Q + 127) / 128, 128, 0, e->stream>>>(e->dobj, d);
+  dyn_stats_kernel<<<(Q * 32 + 127) / 128, 128, 0, e->stream>>>(e->dobj, d);
   if (e->E > 0) dyn_feed_kernel<<<dim3((e->E + 127) / 128, Q), 128, 0, e->stream>>>(e->dobj, d, e->E, e->d_spec_dc, d_dc_ngroups);
   if (e->T > 0) dyn_post_code_kernel<<<dim3((e->T + 127) / 128, d.DC), 128, 0, e->stream>>>(e->dobj, d, U, e->d_post_code);
   dyn_qrec_kernel<<<(Q + 127) / 128, 128, 0, e->stream>>>(e->dobj, d);
