@@ -319,6 +319,14 @@ int32_t cae_feasibility_groups(cae_engine* e, uint8_t* reasons);
  * sum all-reduce over shards assembles the result. */
 int32_t cae_estimate_all(cae_engine* e, const int32_t* max_nodes, int32_t* node_count,
                          int32_t* pod_count, int32_t* sched_count, int32_t* order);
+/* The same with SchedulerPluginRunner.lastIndex (simulator/clustersnapshot/predicate/plugin_runner.go:34,81,123) carried per
+ * template: last_index_in[t] (>= 0, NULL = 0) is the runner's value when the Estimate of template t starts — it may be RAW,
+ * i.e. left by a longer node list: the reference uses it modulo the current list length until a scan places a pod —
+ * last_index_out[t] its value when that Estimate returns (it survives the snapshot's Revert).  cae_estimate_all starts every
+ * Estimate at 0, which makes the node groups independent; a caller that wants ONE long-lived runner across node groups
+ *  chains the calls: out[t] of one call is in[t+1] of the next. */
+int32_t cae_estimate_all_ex(cae_engine* e, const int32_t* max_nodes, const int32_t* last_index_in, int32_t* node_count,
+                            int32_t* pod_count, int32_t* sched_count, int32_t* order, int32_t* last_index_out);
 
 /* Expander filters over the options produced by cae_estimate_all (one option per template with
  * node_count > 0).  Replaces: expander.Filter.BestOptions for least-waste / most-pods / least-nodes

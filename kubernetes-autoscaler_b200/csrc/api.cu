@@ -480,7 +480,7 @@ static int do_load(Engine* e, const cae_objects* o) {
       dev_alloc(e, &e->d_chunk_done, (size_t)std::max(e->Twp / FEAS_TW, 1), true) || dev_alloc(e, &e->d_group_reason, (size_t)std::max(T, 1) * std::max(e->E, 1)) ||
       dev_alloc(e, &e->d_counts2, (size_t)2 * std::max(T, 1), true) || dev_alloc(e, &e->d_sched, (size_t)std::max(T, 1) * std::max(e->E, 1), true) ||
       dev_alloc(e, &e->d_order, (size_t)std::max(T, 1) * std::max(e->E, 1)) || dev_alloc(e, &e->d_grec, (size_t)std::max(e->E, 1)) || dev_alloc(e, &e->d_order_n, (size_t)std::max(T, 1), true) ||
-      dev_alloc(e, &e->d_max_nodes, (size_t)std::max(T, 1), true) || dev_alloc(e, &e->d_tmpl_cost, (size_t)std::max(T, 1), true) ||
+      dev_alloc(e, &e->d_max_nodes, (size_t)std::max(T, 1), true) || dev_alloc(e, &e->d_last_index_buf, (size_t)2 * std::max(T, 1), true) || dev_alloc(e, &e->d_tmpl_cost, (size_t)std::max(T, 1), true) ||
       dev_alloc(e, &e->d_perm, (size_t)std::max(T, 1)) || dev_alloc(e, &e->d_work_counter, 4, true) ||
       dev_alloc(e, &e->d_act_dim, CAE_MAX_RES))
     return -1;
@@ -736,6 +736,11 @@ int32_t cae_feasibility_groups(cae_engine* h, uint8_t* reasons) {
 
 int32_t cae_estimate_all(cae_engine* h, const int32_t* max_nodes, int32_t* node_count, int32_t* pod_count,
                          int32_t* sched_count, int32_t* order) {
+  return cae_estimate_all_ex(h, max_nodes, nullptr, node_count, pod_count, sched_count, order, nullptr);
+}
+
+int32_t cae_estimate_all_ex(cae_engine* h, const int32_t* max_nodes, const int32_t* last_index_in, int32_t* node_count,
+                            int32_t* pod_count, int32_t* sched_count, int32_t* order, int32_t* last_index_out) {
   Engine* e = reinterpret_cast<Engine*>(h);
   if (!e || !e->loaded) { cae::set_error("cae_estimate_all before cae_load"); return -2; }
   cudaSetDevice(e->cfg.device);
@@ -748,6 +753,14 @@ int32_t cae_estimate_all(cae_engine* h, const int32_t* max_nodes, int32_t* node_
     int m = max_nodes ? max_nodes[t] : 0;
     e->pack_cap = std::max(e->pack_cap, m > 0 ? m : (m == 0 ? e->P + 1 : 1));
   }
+  e->d_last_index_in = nullptr;
+  e->d_last_index_out = last_index_out ? e->d_last_index_buf + T : nullptr;
+  if (last_index_in) {
+    for (int t = 0; t < T; ++t) if (last_index_in[t] < 0) { cae::set_error("cae_estimate_all_ex: negative lastIndex"); return -2; }
+    CAE_CUDA(cudaMemcpyAsync(e->d_last_index_buf, last_index_in, sizeof(int32_t) * T, cudaMemcpyHostToDevice, e->stream));
+    e->d_last_index_in = e->d_last_index_buf;
+  }
+  if (last_index_out) CAE_CUDA(cudaMemsetAsync(e->d_last_index_buf + T, 0, sizeof(int32_t) * T, e->stream));
   if (max_nodes) CAE_CUDA(cudaMemcpyAsync(e->d_max_nodes, max_nodes, sizeof(int32_t) * T, cudaMemcpyHostToDevice, e->stream));
   else CAE_CUDA(cudaMemsetAsync(e->d_max_nodes, 0, sizeof(int32_t) * T, e->stream));
   CAE_CUDA(cudaMemsetAsync(e->d_counts2, 0, sizeof(int32_t) * 2 * T, e->stream));
@@ -768,6 +781,7 @@ int32_t cae_estimate_all(cae_engine* h, const int32_t* max_nodes, int32_t* node_
   if (pod_count) CAE_CUDA(cudaMemcpyAsync(pod_count, e->d_counts2 + T, sizeof(int32_t) * T, cudaMemcpyDeviceToHost, e->stream));
   if (sched_count && E) CAE_CUDA(cudaMemcpyAsync(sched_count, e->d_sched, sizeof(int32_t) * (size_t)T * E, cudaMemcpyDeviceToHost, e->stream));
   if (order && E) CAE_CUDA(cudaMemcpyAsync(order, e->d_order, sizeof(int32_t) * (size_t)T * E, cudaMemcpyDeviceToHost, e->stream));
+  if (last_index_out) CAE_CUDA(cudaMemcpyAsync(last_index_out, e->d_last_index_buf + T, sizeof(int32_t) * T, cudaMemcpyDeviceToHost, e->stream));
   CAE_CUDA(cudaStreamSynchronize(e->stream));
   {
     int64_t steps = 0;

@@ -49,6 +49,8 @@ struct BpParams {
   const int32_t* c_slots;
   int act_dim[CAE_MAX_RES];
   int32_t *node_count, *pod_count, *sched, *work_counter, *status;
+  const int32_t* last_index_in;   // [T] or NULL: the plugin runner's lastIndex when the Estimate of template t starts
+  int32_t* last_index_out;        // [T] or NULL: ... and when it returns
   long long* prof;         // optional [16] counters (CAE_PACK_PROF)
   // filter-out-schedulable pass (FM): HintingSimulator.TrySchedulePods on the cluster nodes; `grec` then holds one record
   // per RUN of consecutive identical pods (pad[0] = offset of the run in fm_pods)
@@ -280,7 +282,10 @@ __global__ void __launch_bounds__(TPB, FM ? 1 : BP_MIN_CTAS * 256 / TPB) binpack
     const int tslots = FM ? 0 : p.tmpl_slots[t];
     const int max_nodes = (!FM && p.max_nodes) ? p.max_nodes[t] : 0;
     const int col_new = N + p.T + t;  // universe column of the sanitized template
-    int n_new = 0, nodes_with_pods = 0, pods_total = 0, last_index = FM ? p.fm_last_index : 0;
+    // lastIndex may come in RAW (left by a longer node list): plugin_runner.go:81 uses it modulo the CURRENT list length
+    // until a scan places a pod (:123), so every scan start below is taken through li_eff()
+    int n_new = 0, nodes_with_pods = 0, pods_total = 0, last_index = FM ? p.fm_last_index : (p.last_index_in ? p.last_index_in[t] : 0);
+    auto li_eff = [&]() -> int { const int len = N + n_new; return len > 0 ? last_index % len : 0; };
     bool new_nodes_available = !FM, cl_init = false, fm_stop = false, fm_moved = false;
     auto ensure_cluster = [&]() {  // run state of the cluster nodes, needed once a placement can reach them
       if (cl_init) return;
@@ -733,7 +738,8 @@ __global__ void __launch_bounds__(TPB, FM ? 1 : BP_MIN_CTAS * 256 / TPB) binpack
         BP_PROF_COUNT(8, 1);
         BP_PROF_BEGIN();
         if (can_existing) {
-          const int s = last_index >= N ? last_index - N : 0;  // first added node in cyclic scan order
+          const int li0 = li_eff();
+          const int s = li0 >= N ? li0 - N : 0;  // first added node in cyclic scan order
           int got, newly, last_dist;
           round_robin(n_new, s, n,
                       [&](int i) { return res_cap_a(i, n); },
@@ -1068,7 +1074,8 @@ __global__ void __launch_bounds__(TPB, FM ? 1 : BP_MIN_CTAS * 256 / TPB) binpack
             // ---- tryToScheduleOnExistingNodes ----
             if (can_existing && min(n, b) > 0 && (!uni || S_new > 0)) {
               if (tid == 0) S.mlast = 0;
-              const int s = last_index >= N ? last_index - N : 0;
+              const int li0 = li_eff();
+              const int s = li0 >= N ? li0 - N : 0;
               const int lastj = n_new - 1, want = min(n, b);
               int got, newly, last_dist;
               round_robin(n_new, s, want,
@@ -1100,7 +1107,8 @@ __global__ void __launch_bounds__(TPB, FM ? 1 : BP_MIN_CTAS * 256 / TPB) binpack
               if (N == 0) return;
               BP_PROF_COUNT(15, 1);
               if (!caps_done) cluster_caps();
-              const int s = last_index < N ? last_index : 0;
+              const int li0 = li_eff();
+              const int s = li0 < N ? li0 : 0;
               int got, newly, last_dist;
               round_robin(N, s, n,
                           [&](int i) { return g_kc[i]; },
@@ -1312,7 +1320,8 @@ __global__ void __launch_bounds__(TPB, FM ? 1 : BP_MIN_CTAS * 256 / TPB) binpack
         BP_PROF_BEGIN();
         while (n > 0 && can_existing) {
           BP_PROF_COUNT(12, 1);
-          const int s = last_index >= N ? last_index - N : 0;
+          const int li0 = li_eff();
+          const int s = li0 >= N ? li0 - N : 0;
           int best = INT_MAX, zero = 0;
           for (int j = tid; j < n_new; j += TPB)
             if (eval(Neff + j) == CAE_R_OK) { int dd = j - s; if (dd < 0) dd += n_new; best = min(best, dd); }
@@ -1336,17 +1345,17 @@ __global__ void __launch_bounds__(TPB, FM ? 1 : BP_MIN_CTAS * 256 / TPB) binpack
             else if (host_spread && r == CAE_R_PTS_SKEW) {
               // SchedulePodOnAnyNodeMatching(name != lastNodeName) (:190-205): whole list, cyclic from lastIndex
               ensure_cluster();
-              const int len = N + n_new, lastpos = N + n_new - 1;
+              const int len = N + n_new, lastpos = N + n_new - 1, li0 = li_eff();
               int best = INT_MAX, zero = 0;
               for (int idx = tid; idx < len; idx += TPB) {
                 if (idx == lastpos) continue;
                 if (idx < N && o.node_unschedulable[idx]) continue;   // plugin_runner.go:92-94
                 const int x = idx < N ? idx : Neff + (idx - N);
-                if (eval(x) == CAE_R_OK) { int dd = idx - last_index; if (dd < 0) dd += len; best = min(best, dd); }
+                if (eval(x) == CAE_R_OK) { int dd = idx - li0; if (dd < 0) dd += len; best = min(best, dd); }
               }
               blk_min_sum<NW>(S, par, best, zero);
               if (best != INT_MAX) {
-                int hit = last_index + best;
+                int hit = li0 + best;
                 if (hit >= len) hit -= len;
                 place(hit < N ? hit : Neff + (hit - N));
                 last_index = (hit + 1) % len;
@@ -1387,6 +1396,7 @@ __global__ void __launch_bounds__(TPB, FM ? 1 : BP_MIN_CTAS * 256 / TPB) binpack
     } else if (tid == 0) {
       p.node_count[t] = nodes_with_pods;
       p.pod_count[t] = pods_total;
+      if (p.last_index_out) p.last_index_out[t] = last_index;
       if (S.overflow && p.status) atomicExch(p.status, 1);
     }
   }
@@ -1462,6 +1472,7 @@ int launch_binpack(Engine* e) {
   p.node_count = e->d_counts2; p.pod_count = e->d_counts2 + e->T; p.sched = e->d_sched;
   p.work_counter = e->d_work_counter; p.status = e->d_work_counter + 1;
   p.t_begin = e->t_begin; p.t_end = e->t_end;
+  p.last_index_in = e->d_last_index_in; p.last_index_out = e->d_last_index_out;
   // node capacity of a simulation: the largest limiter cap, or (unlimited) one node per pod + 1
   // (every added node but possibly one holds >= 1 pod)
   const int cap = std::max(1, std::min(e->P + 1, e->pack_cap));

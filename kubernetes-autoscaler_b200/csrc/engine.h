@@ -144,6 +144,9 @@ struct Engine {
   GroupRec* d_grec = nullptr;             // [E]
   double* d_score = nullptr;              // [T][E]
   int32_t* d_max_nodes = nullptr;         // [T]
+  int32_t* d_last_index_buf = nullptr;    // [2T] lastIndex in | out (cae_estimate_all_ex)
+  const int32_t* d_last_index_in = nullptr;   // set per call: NULL = every Estimate starts at 0
+  int32_t* d_last_index_out = nullptr;
   int32_t* d_pc_of = nullptr;             // [num_port_lists] compact id of a pending pod's port list, -1 otherwise
   unsigned long long* d_port_conf = nullptr;  // [num_port_lists] conflict mask over compact ids
   int pack_cap = 1 << 30;                 // node capacity of a pack slab (from the limiter caps)

@@ -165,6 +165,20 @@ class Engine:
         self._check(self.lib.cae_feasibility_groups(self.h, out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def estimate_all_li(self, max_nodes, last_index_in):
+        """cae_estimate_all_ex: Estimate of every template with the plugin runner's lastIndex carried in per template.
+        Returns node_count, pod_count, sched, order, last_index_out."""
+        enc = self.enc
+        T, E = enc.T, enc.E
+        mn = None if max_nodes is None else np.ascontiguousarray(max_nodes, np.int32)
+        li = np.ascontiguousarray(last_index_in, np.int32)
+        nc, pc = np.zeros(T, np.int32), np.zeros(T, np.int32)
+        sched, order = np.zeros((T, E), np.int32), np.zeros((T, E), np.int32)
+        lo = np.zeros(T, np.int32)
+        vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        self._check(self.lib.cae_estimate_all_ex(self.h, vp(mn), vp(li), vp(nc), vp(pc), vp(sched), vp(order), vp(lo)))
+        return nc, pc, sched, order, lo
+
     def estimate_all(self, max_nodes: Optional[Sequence[int]] = None, want_sched: bool = True, copy: bool = True):
         """Returns node_count[T], pod_count[T], sched_count[T][E], order[T][E] (rows outside this
         rank's template shard are zero / -1).  Outputs land in pinned buffers; copy=False returns

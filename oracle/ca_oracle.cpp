@@ -533,10 +533,12 @@ struct EstimateResult {
   std::vector<int> order;       /* group ids in processing order */
   std::vector<int> sched;       /* per group id: pods scheduled */
   std::vector<int> placements;  /* node list index per scheduled pod, in scheduling order */
+  int last_index = 0;           /* SchedulerPluginRunner.lastIndex when Estimate returns (raw: it survives the Revert) */
 };
 
 /* BinpackingNodeEstimator.Estimate (estimator/binpacking_estimator.go:97-139) */
-void estimate(Snapshot& s, int tmpl, const std::vector<int>& groups_in, int max_nodes, int num_groups, EstimateResult& res) {
+void estimate(Snapshot& s, int tmpl, const std::vector<int>& groups_in, int max_nodes, int num_groups, EstimateResult& res,
+              int last_index_in = 0) {
   const cae_objects* o = s.c.o;
   int tnode = o->num_cluster_nodes + tmpl;
   res.sched.assign(num_groups, 0);
@@ -550,7 +552,8 @@ void estimate(Snapshot& s, int tmpl, const std::vector<int>& groups_in, int max_
   std::stable_sort(scored.begin(), scored.end(), [](auto& a, auto& b) { return a.first > b.first; });
   Limiter lim{max_nodes};
   s.fork();
-  s.last_index = 0; /* fresh runner per Estimate (header note) */
+  s.last_index = last_index_in; /* 0 = fresh runner per Estimate (header note); a caller may carry the runner's value over
+                                   (plugin_runner.go:81,123: used modulo the CURRENT list length until a scan places a pod) */
   int new_node_index = 0, last_node = -1; /* estimationState (:46-53) */
   int nodes_with_pods = 0;
   bool new_nodes_available = true;
@@ -608,6 +611,7 @@ void estimate(Snapshot& s, int tmpl, const std::vector<int>& groups_in, int max_
     }
   }
   res.node_count = nodes_with_pods;
+  res.last_index = s.last_index;
   s.revert(false);
 }
 
@@ -693,6 +697,37 @@ int cao_estimate_all(const cae_objects* o, const int32_t* max_nodes, int t_begin
   }
   ev = s.filter_evals;
   if (evals) *evals = ev;
+  return 0;
+}
+
+/* cao_estimate_all with the plugin runner's lastIndex carried in (and out) per template; chain != 0: template t starts from the
+ * value template t-1 ended with (one long-lived runner), last_index_in[t_begin] seeds the first. */
+int cao_estimate_all_li(const cae_objects* o, const int32_t* max_nodes, const int32_t* last_index_in, int chain, int t_begin, int t_end,
+                        int32_t* node_count, int32_t* pod_count, int32_t* sched_count, int32_t* order, int32_t* last_index_out) {
+  Snapshot s(o);
+  s.loadCluster();
+  int E = o->num_groups;
+  int carry = last_index_in ? last_index_in[t_begin] : 0;
+  for (int t = t_begin; t < t_end; ++t) {
+    std::vector<int> feasible;
+    s.fork();
+    s.nodes.push_back(s.makeNode(o->num_cluster_nodes + t));
+    for (int g = 0; g < E; ++g) {
+      if (o->group_off[g + 1] == o->group_off[g]) continue;
+      if (checkOnTemplate(s, o->pend_spec[o->group_off[g]], t) == CAE_R_OK) feasible.push_back(g);
+    }
+    s.revert(true);
+    EstimateResult res;
+    const int li = chain ? carry : (last_index_in ? last_index_in[t] : 0);
+    estimate(s, t, feasible, max_nodes ? max_nodes[t] : 0, E, res, li);
+    carry = res.last_index;
+    size_t row = (size_t)(t - t_begin);
+    node_count[row] = res.node_count;
+    pod_count[row] = res.pod_count;
+    if (sched_count) std::copy(res.sched.begin(), res.sched.end(), sched_count + row * E);
+    if (order) { std::fill(order + row * E, order + (row + 1) * E, -1); std::copy(res.order.begin(), res.order.end(), order + row * E); }
+    if (last_index_out) last_index_out[row] = res.last_index;
+  }
   return 0;
 }
 

@@ -38,6 +38,8 @@ def lib() -> C.CDLL:
         l.cao_estimate.restype = i32
         l.cao_estimate_all.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, i64p]
         l.cao_estimate_all.restype = i32
+        l.cao_estimate_all_li.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]
+        l.cao_estimate_all_li.restype = i32
         l.cao_pod_score.argtypes = [vp, i32, i32]
         l.cao_pod_score.restype = C.c_double
         l.cao_get_min_limit.argtypes = [C.c_int64, C.c_int64]
@@ -116,6 +118,20 @@ def estimate_all(enc, max_nodes: Optional[np.ndarray] = None, t_range: Optional[
                                 _p(order), C.byref(ev))
     assert rc == 0
     return node_count, pod_count, sched, order, ev.value
+
+
+def estimate_all_li(enc, max_nodes, last_index_in, chain: bool = False):
+    """estimate_all with the runner's lastIndex carried in per template (chain: from template to template).
+    Returns node_count, pod_count, sched, order, last_index_out."""
+    n = enc.T
+    mn = None if max_nodes is None else np.ascontiguousarray(max_nodes, np.int32)
+    li = np.ascontiguousarray(last_index_in, np.int32)
+    node_count, pod_count = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    sched, order = np.zeros((n, enc.E), np.int32), np.full((n, enc.E), -1, np.int32)
+    lo = np.zeros(n, np.int32)
+    rc = lib().cao_estimate_all_li(enc.ptr(), _p(mn), _p(li), int(chain), 0, n, _p(node_count), _p(pod_count), _p(sched), _p(order), _p(lo))
+    assert rc == 0
+    return node_count, pod_count, sched, order, lo
 
 
 def pod_score(enc, spec: int, tmpl: int) -> float:

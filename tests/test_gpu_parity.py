@@ -436,3 +436,29 @@ def test_load_pending_delta(eng, oracle):
     onc, opc, osched, oorder, _ = oracle.estimate_all(enc3, caps)
     assert np.array_equal(nc, onc) and np.array_equal(pc, opc) and np.array_equal(sched, osched) and np.array_equal(order, oorder)
     assert not eng.load_pending(enc3.slice_pods(100, 2_000))
+
+
+def test_last_index_carried_in_and_out(eng, oracle):
+    """cae_estimate_all_ex: the plugin runner's lastIndex per template, RAW values included (plugin_runner.go:81 takes it
+    modulo the current list length until a scan places a pod); and one long-lived runner chained over the node groups."""
+    rng = np.random.default_rng(11)
+    for enc in (synth.generate(2, pods=3_000, templates=40), synth.generate(3, pods=2_500, templates=24, cluster_nodes=48),
+                synth.generate(4, pods=3_000, templates=16, cluster_nodes=40)):
+        for cap in (25, 0):
+            caps = np.full(enc.T, cap, np.int32)
+            li = rng.integers(0, 400, enc.T).astype(np.int32)
+            li[::5] = 0
+            eng.load(enc)
+            got = eng.estimate_all_li(caps, li)
+            want = oracle.estimate_all_li(enc, caps, li)
+            for g, w, what in zip(got, want, ("node_count", "pod_count", "sched", "order", "last_index_out")):
+                assert np.array_equal(g, w), what
+        # one runner across the node groups: template t starts where template t-1 ended
+        caps = np.full(enc.T, 12, np.int32)
+        want = oracle.estimate_all_li(enc, caps, np.full(enc.T, 7, np.int32), chain=True)
+        carry, li = 7, np.zeros(enc.T, np.int32)
+        for t in range(min(enc.T, 6)):
+            li[t] = carry
+            nc, pc, sched, order, lo = eng.estimate_all_li(caps, li)
+            assert (nc[t], pc[t], lo[t]) == (want[0][t], want[1][t], want[4][t]) and np.array_equal(sched[t], want[2][t])
+            carry = int(lo[t])
