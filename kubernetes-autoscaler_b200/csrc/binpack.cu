@@ -166,6 +166,10 @@ __device__ __forceinline__ long long blk_sum_ll(BpShared& S, int& par, long long
   return a;
 }
 
+#ifndef BP_UNROLL
+#define BP_UNROLL 1
+#endif
+constexpr int kBpUnroll = BP_UNROLL;   // unroll factor of the per-node sweeps
 #ifndef BP_MIN_CTAS
 #define BP_MIN_CTAS 4
 #endif
@@ -348,6 +352,7 @@ __global__ void __launch_bounds__(TPB, FM ? 1 : BP_MIN_CTAS * 256 / TPB) binpack
       // pass 1: capacities; their sum only matters up to npods + 1, so it travels as a clamped 32-bit value
       const int clampv = npods < (1 << 26) ? npods + 1 : (1 << 26);
       int total = 0, kmax = 0, npos = 0;
+#pragma unroll kBpUnroll
       for (int i = tid; i < cnt; i += TPB) {
         const int k = capfn(i);
         kcref(i) = k;
@@ -459,6 +464,7 @@ __global__ void __launch_bounds__(TPB, FM ? 1 : BP_MIN_CTAS * 256 / TPB) binpack
         pre_s = S.pre_s;
         tot_extra = basecnt;
       }
+#pragma unroll kBpUnroll
       for (int i = tid; i < cnt; i += TPB) {
         const int k = kcref(i);
         if (k <= 0) continue;

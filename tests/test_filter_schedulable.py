@@ -336,3 +336,31 @@ def test_removal_persists_successful_simulations():
     assert sorted(p.name for ni in cluster for p in ni.pods) == ["p1", "p2", "p3"]
     # hints of the persisted simulation steer the next one (the pods would go back to where they were placed)
     assert r.schedulingSimulator.hints.Get(("default", "p1")) in ("n1", "n3")
+
+
+# ---- the reference's filter-pass benchmark vector: BenchmarkRunFiltersUntilPassingNode -------------------------------------
+# (simulator/clustersnapshot/predicate/plugin_runner_test.go:372-421): 5000 nodes of 10 m CPU with ten 1 m pods each, the
+# 5001st node (1000 m) is the only one that takes the 100 m pod; a fresh runner (lastIndex = 0) scans the whole list.
+def _benchmark_snapshot():
+    cluster = [NodeInfo(_ready_node("n-%d" % i, 10, 1000), [_scheduled("p-%d-%d" % (i, j), 1, 1) for j in range(10)]) for i in range(5000)]
+    cluster.append(NodeInfo(_ready_node("n-5000", 1000, 1000)))
+    return cluster, [BuildTestPod("p", 100, 1000)]
+
+
+def _run_benchmark_vector(sim):
+    cluster, pods = _benchmark_snapshot()
+    for _ in range(2):                      # "lastIndex = 0 // Reset state for each run"
+        sim.last_index = 0
+        sim.hints = plp.Hints()
+        statuses, _ = sim.TrySchedulePods(cluster, pods)
+        assert [(s.pod.name, s.node_name) for s in statuses] == [("p", "n-5000")]
+        assert sim.last_index == 0          # (5000 + 1) % 5001
+
+
+def test_oracle_run_filters_until_passing_node_benchmark_vector():
+    _run_benchmark_vector(OracleSimulator())
+
+
+@pytest.mark.gpu
+def test_gpu_run_filters_until_passing_node_benchmark_vector(gpu_engine):
+    _run_benchmark_vector(plp.HintingSimulator(gpu_engine))
