@@ -711,7 +711,7 @@ int32_t cae_feasibility(cae_engine* h, uint32_t* fit_bits, uint8_t* reasons, int
   cudaEventRecord(c1, e->stream);
   int32_t peer_status = 0;
   if (e->peer_world > 1)
-    CAE_CUDA(cudaMemcpyAsync(&peer_status, e->d_xbuf + (size_t)2 * Engine::PEER_MAX * Engine::PEER_CAP + 9, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CAE_CUDA(cudaMemcpyAsync(&peer_status, e->d_xbuf + (size_t)4 * Engine::PEER_MAX * Engine::PEER_CAP + 9, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
   CAE_CUDA(cudaStreamSynchronize(e->stream));
   float ms = 0;
   cudaEventElapsedTime(&ms, e->ev0, e->ev1);
@@ -1041,7 +1041,7 @@ void* cae_stream(cae_engine* h) {
 
 static int ensure_xbuf(Engine* e) {
   if (e->d_xbuf) return 0;
-  const size_t n = (size_t)2 * Engine::PEER_MAX * Engine::PEER_CAP + 16;   // [2][PEER_MAX][PEER_CAP] + counters (feas.cu)
+  const size_t n = (size_t)4 * Engine::PEER_MAX * Engine::PEER_CAP + 16;   // [2 parities][PEER_MAX][PEER_CAP] (count, tag) slots + counters (feas.cu)
   CAE_CUDA(cudaMalloc(&e->d_xbuf, n * sizeof(int32_t)));
   CAE_CUDA(cudaMemset(e->d_xbuf, 0, n * sizeof(int32_t)));
   return 0;

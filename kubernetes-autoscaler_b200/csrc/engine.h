@@ -161,7 +161,7 @@ struct Engine {
   size_t fm_blob_words = 0;
   // fused histogram exchange over peer memory (feas.cu)
   static constexpr int PEER_MAX = 8, PEER_CAP = 1 << 16;
-  int32_t* d_xbuf = nullptr;              // [2][PEER_MAX][PEER_CAP] all-gather slots + [2] arrival counters, done counter, status
+  int32_t* d_xbuf = nullptr;              // [2 parities][PEER_MAX][PEER_CAP] (count, step tag) slots + done counter, status
   int peer_world = 0;
   int32_t* peer_base[PEER_MAX] = {nullptr};
   int64_t peer_uses[2] = {0, 0};

@@ -80,15 +80,13 @@ constexpr int K1_TCHUNK = K1_TW * 32;
 constexpr int K1_LPITCH = K1_TW + 1;      // odd row pitch of the staged threshold rows
 
 // Fused exchange of the fit histogram over peer memory (see cae_peer_attach in include/caengine.h): an
-// all-gather.  Every rank owns an exchange buffer [2 parities][PEER_MAX ranks][PEER_CAP]; a step writes the local
-// histogram into slot `rank` of EVERY rank's buffer (plain coalesced stores over NVLink), signals arrival with a
-// system-scope atomic, waits for all ranks and sums the slots.  Parities alternate between steps: a rank can only
-// reach step s+2 after every peer signalled s+1, i.e. after every peer finished reading step s.
+// all-gather.  Every rank owns an exchange buffer [2 parities][PEER_MAX ranks][PEER_CAP] of (count, step tag) slots; a
+// step writes the local histogram into row `rank` of EVERY rank's buffer — one 8-byte store per template over NVLink —
+// and reads the rows of its own buffer until every slot carries this step's tag (k1_finish below).
 struct PeerPush {
   int world, rank;           // world 0 = disabled
-  int target;                // arrival count that completes this step
-  int32_t* data[8];          // every rank's [PEER_MAX][PEER_CAP] block of this step's parity (P2P-mapped)
-  int32_t* arrive[8];        // every rank's arrival counter of that parity
+  int tag;                   // step number carried by every slot of this step (never 0)
+  int2* data[8];             // every rank's [PEER_MAX][PEER_CAP] block of (count, tag) slots of this step's parity (P2P-mapped)
   int32_t* done_ctr;         // local: template chunks published
   int32_t* status;           // local: set to 1 when a peer never arrived
 };
@@ -115,6 +113,14 @@ __device__ __forceinline__ int k1_ld_acquire_sys(const int32_t* p) {
 }
 __device__ __forceinline__ void k1_red_release_sys(int32_t* p, int v) {
   asm volatile("red.release.sys.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void k1_st_volatile_v2(int2* p, int x, int y) {
+  asm volatile("st.volatile.global.v2.s32 [%0], {%1, %2};" ::"l"(p), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ int2 k1_ld_volatile_v2(const int2* p) {
+  int2 v;
+  asm volatile("ld.volatile.global.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
 }
 __device__ __forceinline__ unsigned long long k1_globaltimer() {
   unsigned long long t;
@@ -157,35 +163,33 @@ __device__ __forceinline__ void k1_finish(const K1Args& a, const PeerPush& pp, c
   }
   __syncthreads();
   if (!s_flag) return;
-  // the block that published the LAST chunk owns the complete local histogram: all-gather it.
-  // Chain per step: peer stores -> block barrier -> ONE release-add per peer (cumulative over the barrier, no separate
-  // system fence, no returned value) -> acquire-poll of the own arrival counter (own memory) -> sum.
+  // The block that published the LAST chunk owns the complete local histogram: all-gather it with a low-latency protocol
+  // (the one NCCL calls LL): every slot is ONE 8-byte store of (count, step tag) into the peer's buffer over NVLink, so a
+  // reader that sees this step's tag in a slot has this step's count — no fence, no separate flag, no round trip waiting
+  // for acknowledgements.  Two parities alternate: a rank can only write step s+2 after it has READ every peer's step s+1,
+  // which that peer wrote after it finished reading step s.
   __threadfence();
+  const int tag = pp.tag;
   for (int r = 0; r < pp.world; ++r) {
-    int32_t* dst = pp.data[r] + (size_t)pp.rank * Engine::PEER_CAP;
-    for (int t = tid; t < a.T; t += nthreads) dst[t] = __ldcg(&a.fit_count[t]);
+    int2* dst = pp.data[r] + (size_t)pp.rank * Engine::PEER_CAP;
+    for (int t = tid; t < a.T; t += nthreads) k1_st_volatile_v2(dst + t, __ldcg(&a.fit_count[t]), tag);
   }
-  __syncthreads();
-  if (tid < pp.world) k1_red_release_sys(pp.arrive[tid], 1);
-  if (tid == 0) {
-    const int32_t* arr = pp.arrive[pp.rank];
-    const unsigned long long t0ns = k1_globaltimer();
-    int ok = 1, spins = 0;
-    while (k1_ld_acquire_sys(arr) < pp.target) {
-      if ((++spins & 1023) == 0 && k1_globaltimer() - t0ns > 2000000000ull) { ok = 0; break; }  // 2 s of wall clock: a peer died; fail instead of hanging the GPU
-    }
-    s_flag = ok;
-    if (!ok) atomicExch(pp.status, 1);
-    *pp.done_ctr = 0;
-  }
-  __syncthreads();
-  if (!s_flag) return;
-  const int32_t* mine = pp.data[pp.rank];
-  for (int t = tid; t < a.T; t += nthreads) {
+  const int2* mine = pp.data[pp.rank];
+  const unsigned long long t0ns = k1_globaltimer();
+  int ok = 1;
+  for (int t = tid; t < a.T && ok; t += nthreads) {
     int v = 0;
-    for (int r = 0; r < pp.world; ++r) v += __ldcg(&mine[(size_t)r * Engine::PEER_CAP + t]);
-    a.fit_count[t] = v;
+    for (int r = 0; r < pp.world && ok; ++r) {
+      const int2* slot = mine + (size_t)r * Engine::PEER_CAP + t;
+      int2 x = k1_ld_volatile_v2(slot);
+      for (int spins = 0; x.y != tag; x = k1_ld_volatile_v2(slot))
+        if ((++spins & 1023) == 0 && k1_globaltimer() - t0ns > 2000000000ull) { ok = 0; break; }   // 2 s: a peer died; fail, never hang
+      v += x.x;
+    }
+    if (ok) a.fit_count[t] = v;
   }
+  if (!ok) atomicExch(pp.status, 1);
+  if (tid == 0) *pp.done_ctr = 0;
 }
 
 // ---- 32x32 bit transposes across a warp ---------------------------------------------------------------------
@@ -437,18 +441,15 @@ static PeerPush peer_push_args(Engine* e) {
   PeerPush pp{};
   if (e->peer_world > 1 && e->T <= Engine::PEER_CAP) {
     const int par = (int)(e->peer_step & 1);
-    const size_t blk = (size_t)Engine::PEER_MAX * Engine::PEER_CAP;
+    const size_t blk = (size_t)Engine::PEER_MAX * Engine::PEER_CAP;   // slots per parity
     pp.world = e->peer_world;
     pp.rank = e->cfg.rank;
-    e->peer_uses[par] += 1;
     e->peer_step += 1;
-    pp.target = (int)(e->peer_uses[par] * e->peer_world);
-    for (int r = 0; r < e->peer_world; ++r) {
-      pp.data[r] = e->peer_base[r] + par * blk;
-      pp.arrive[r] = e->peer_base[r] + 2 * blk + par;
-    }
-    pp.done_ctr = e->d_xbuf + 2 * blk + 8;
-    pp.status = e->d_xbuf + 2 * blk + 9;
+    pp.tag = (int)(e->peer_step & 0x7fffffff);
+    if (pp.tag == 0) pp.tag = 1;
+    for (int r = 0; r < e->peer_world; ++r) pp.data[r] = reinterpret_cast<int2*>(e->peer_base[r]) + par * blk;
+    pp.done_ctr = e->d_xbuf + 4 * blk + 8;
+    pp.status = e->d_xbuf + 4 * blk + 9;
   }
   return pp;
 }
