@@ -597,8 +597,13 @@ def main():
                 torch.cuda.synchronize()
                 if i:
                     ms3.append(eng.stats().feasibility_ms)
-            dense_large = {"workload": synth.CONFIGS[3].name, "cells": enc3.P * enc3.T, "ms": float(np.median(ms3)),
-                           "evals_per_s": enc3.P * enc3.T / (float(np.median(ms3)) * 1e-3)}
+            m3 = float(np.median(ms3))
+            alg3 = enc3.P * 12 + enc3.T * 4 + enc3.P * enc3.T // 8 + 4 * enc3.T     # W = 1 packed-rank word: same formula as `roofline`
+            pk3, _ = _peak_hbm()
+            dense_large = {"workload": synth.CONFIGS[3].name, "cells": enc3.P * enc3.T, "ms": m3,
+                           "evals_per_s": enc3.P * enc3.T / (m3 * 1e-3),
+                           "roofline": {"bound": "hbm", "algorithmic_bytes": alg3, "achieved": alg3 / (m3 * 1e-3) / 1e9, "peak": pk3,
+                                        "unit": "GB/s", "frac": alg3 / (m3 * 1e-3) / 1e9 / pk3}}
             eng.load(enc)
         except Exception as ex:
             dense_large = {"error": repr(ex)}

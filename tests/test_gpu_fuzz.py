@@ -104,7 +104,7 @@ def _rand_pod(rng, name):
     return p
 
 
-def _scenario(seed):
+def _scenario(seed, big=False):
     rng = random.Random(seed)
     residents = [_rand_pod(rng, "r%d" % i) for i in range(6)]
     for r in residents:
@@ -113,14 +113,15 @@ def _scenario(seed):
         if rng.random() < 0.1:
             r.terminating = True
     cluster = [NodeInfo(_rand_node(rng, "c%d" % i, False), [rng.choice(residents) for _ in range(rng.randint(0, 3))])
-               for i in range(rng.randint(0, 6))]
+               for i in range(rng.randint(8, 40) if big else rng.randint(0, 6))]
     ds = BuildTestPod("ds", 50, 1 << 24)
     ds.labels = {"app": rng.choice(APPS)}
     ds.tolerations = [Toleration("", "Exists", "", "")]
     templates = [NodeInfo(_rand_node(rng, "t%d" % i, True), [ds] if rng.random() < 0.5 else []) for i in range(rng.randint(1, 5))]
-    groups = [makePodEquivalenceGroup(_rand_pod(rng, "p%d" % i), rng.randint(1, 9)) for i in range(rng.randint(1, 8))]
+    groups = [makePodEquivalenceGroup(_rand_pod(rng, "p%d" % i), rng.randint(1, 60) if big else rng.randint(1, 9))
+              for i in range(rng.randint(3, 14) if big else rng.randint(1, 8))]
     namespaces = [Namespace("other", {"team": "a"})] if rng.random() < 0.5 else []
-    caps = [rng.choice([0, 0, 1, 2, 5, -1]) for _ in templates]
+    caps = [rng.choice([0, 0, 3, 8, 20, -1] if big else [0, 0, 1, 2, 5, -1]) for _ in templates]
     return cluster, templates, groups, namespaces, caps
 
 
@@ -152,6 +153,30 @@ def test_random_scenarios(eng, oracle, block):
         mask, waste = eng.expander_best([0, 1, 2], nc, pc)
         omask, owaste = oracle.expander(enc, [0, 1, 2], nc, pc, sched)
         assert np.array_equal(mask, omask) and np.array_equal(waste, owaste), "seed %d expander" % seed
+    assert not fails, "Estimate() differs from the oracle: " + "; ".join(fails)
+
+
+@pytest.mark.parametrize("block", range(int(os.environ.get("CAE_FUZZ_BIG_BLOCKS", "4"))))
+def test_random_scenarios_larger(eng, oracle, block):
+    """The same generator with 8-40 cluster nodes, up to 14 groups of up to 60 pods and larger caps: long round-robin laps,
+    the any-node fallback over many cluster nodes, budgets that run out mid-group, the limiter closing mid-group."""
+    from kubernetes_autoscaler_b200.engine import EngineUnsupported
+    refused = 0
+    fails = []
+    for seed in range(block * 15, block * 15 + 15):
+        cluster, templates, groups, namespaces, caps = _scenario(70_000 + seed, big=True)
+        enc = encode(cluster, templates, groups, namespaces=namespaces)
+        try:
+            eng.load(enc)
+        except EngineUnsupported:
+            refused += 1
+            assert refused <= 3
+            continue
+        caps_a = np.asarray(caps, np.int32)
+        nc, pc, sched, order = eng.estimate_all(caps_a)
+        onc, opc, osched, oorder, _ = oracle.estimate_all(enc, caps_a)
+        if not (np.array_equal(nc, onc) and np.array_equal(pc, opc) and np.array_equal(sched, osched) and np.array_equal(order, oorder)):
+            fails.append("seed %d: nodes %s vs %s, pods %s vs %s" % (seed, nc.tolist(), onc.tolist(), pc.tolist(), opc.tolist()))
     assert not fails, "Estimate() differs from the oracle: " + "; ".join(fails)
 
 
