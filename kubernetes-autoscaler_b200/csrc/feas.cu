@@ -178,14 +178,28 @@ __device__ __forceinline__ void k1_finish(const K1Args& a, const PeerPush& pp, c
   const unsigned long long t0ns = k1_globaltimer();
   int ok = 1;
   for (int t = tid; t < a.T && ok; t += nthreads) {
-    int v = 0;
-    for (int r = 0; r < pp.world && ok; ++r) {
-      const int2* slot = mine + (size_t)r * Engine::PEER_CAP + t;
-      int2 x = k1_ld_volatile_v2(slot);
-      for (int spins = 0; x.y != tag; x = k1_ld_volatile_v2(slot))
-        if ((++spins & 1023) == 0 && k1_globaltimer() - t0ns > 2000000000ull) { ok = 0; break; }   // 2 s: a peer died; fail, never hang
-      v += x.x;
+    // all ranks' slots of this template in flight at once (independent loads), then only the late ones are polled again
+    int2 x[Engine::PEER_MAX];
+    unsigned pending = 0;
+#pragma unroll
+    for (int r = 0; r < Engine::PEER_MAX; ++r)
+      if (r < pp.world) x[r] = k1_ld_volatile_v2(mine + (size_t)r * Engine::PEER_CAP + t);
+#pragma unroll
+    for (int r = 0; r < Engine::PEER_MAX; ++r)
+      if (r < pp.world && x[r].y != tag) pending |= 1u << r;
+    for (int spins = 0; pending; ) {
+#pragma unroll
+      for (int r = 0; r < Engine::PEER_MAX; ++r)
+        if ((pending >> r) & 1u) {
+          x[r] = k1_ld_volatile_v2(mine + (size_t)r * Engine::PEER_CAP + t);
+          if (x[r].y == tag) pending &= ~(1u << r);
+        }
+      if (pending && (++spins & 1023) == 0 && k1_globaltimer() - t0ns > 2000000000ull) { ok = 0; break; }   // 2 s: a peer died; fail, never hang
     }
+    int v = 0;
+#pragma unroll
+    for (int r = 0; r < Engine::PEER_MAX; ++r)
+      if (r < pp.world) v += x[r].x;
     if (ok) a.fit_count[t] = v;
   }
   if (!ok) atomicExch(pp.status, 1);
