@@ -1409,6 +1409,48 @@ __global__ void __launch_bounds__(TPB, FM ? 1 : BP_MIN_CTAS * 256 / TPB) binpack
   if (tid == 0) hdr[1] = gver_ctr;
 }
 
+// The kernel is instantiated for 9 resource-dimension counts x {shared window, slab} + the filter pass: the file is compiled
+// three times (-DBP_PART=0|1|2, A in {0,1,2} / {3,4,5} / {6,7,8}) so that build() can run the parts in parallel; the host
+// side below lives in part 0.
+#ifndef BP_PART
+#define BP_PART 0
+#endif
+int bp_launch_part0(Engine* e, int A, int blocks_wanted, size_t smem, const BpParams& p, int* blocks_out, bool query_only, bool filter);
+int bp_launch_part1(Engine* e, int A, int blocks_wanted, size_t smem, const BpParams& p, int* blocks_out, bool query_only, bool filter);
+int bp_launch_part2(Engine* e, int A, int blocks_wanted, size_t smem, const BpParams& p, int* blocks_out, bool query_only, bool filter);
+
+template <int A>
+static int bp_launch_a(Engine* e, int blocks_wanted, size_t smem, const BpParams& p, int* blocks_out, bool query_only, bool filter) {
+  if (filter) {
+    binpack_kernel<A, 512, false, true><<<1, 512, 0, e->stream>>>(e->dobj, e->dyn, p);
+    return 0;
+  }
+  auto kern = p.win ? binpack_kernel<A, 256, true, false> : binpack_kernel<A, 256, false, false>;
+  CAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CAE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+  if (per_sm < 1) { set_error("binpack_kernel does not fit an SM"); return -1; }
+  const int blocks = std::max(1, std::min(blocks_wanted, per_sm * e->sm_count));
+  *blocks_out = blocks;
+  if (query_only) return 0;
+  kern<<<blocks, 256, smem, e->stream>>>(e->dobj, e->dyn, p);
+  return 0;
+}
+#if BP_PART == 0
+int bp_launch_part0(Engine* e, int A, int bw, size_t smem, const BpParams& p, int* bo, bool q, bool f) {
+  return A == 0 ? bp_launch_a<0>(e, bw, smem, p, bo, q, f) : A == 1 ? bp_launch_a<1>(e, bw, smem, p, bo, q, f) : bp_launch_a<2>(e, bw, smem, p, bo, q, f);
+}
+#elif BP_PART == 1
+int bp_launch_part1(Engine* e, int A, int bw, size_t smem, const BpParams& p, int* bo, bool q, bool f) {
+  return A == 3 ? bp_launch_a<3>(e, bw, smem, p, bo, q, f) : A == 4 ? bp_launch_a<4>(e, bw, smem, p, bo, q, f) : bp_launch_a<5>(e, bw, smem, p, bo, q, f);
+}
+#else
+int bp_launch_part2(Engine* e, int A, int bw, size_t smem, const BpParams& p, int* bo, bool q, bool f) {
+  return A == 6 ? bp_launch_a<6>(e, bw, smem, p, bo, q, f) : A == 7 ? bp_launch_a<7>(e, bw, smem, p, bo, q, f) : bp_launch_a<8>(e, bw, smem, p, bo, q, f);
+}
+#endif
+
+#if BP_PART == 0
 // work order of the estimator blocks: templates by decreasing cost (pods in their schedulable groups), ties by index
 __global__ void lpt_rank_kernel(const long long* __restrict__ cost, int t_begin, int nt, int32_t* __restrict__ perm) {
   __shared__ long long tile[256];
@@ -1429,40 +1471,11 @@ __global__ void lpt_rank_kernel(const long long* __restrict__ cost, int t_begin,
   if (i < nt) perm[rank] = t_begin + i;
 }
 
-template <int A, int TPB>
-static int launch_binpack_at(Engine* e, int blocks_wanted, size_t smem, const BpParams& p, int* blocks_out, bool query_only) {
-  auto kern = p.win ? binpack_kernel<A, TPB, true, false> : binpack_kernel<A, TPB, false, false>;
-  CAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  CAE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, smem));
-  if (per_sm < 1) { set_error("binpack_kernel does not fit an SM"); return -1; }
-  const int blocks = std::max(1, std::min(blocks_wanted, per_sm * e->sm_count));
-  *blocks_out = blocks;
-  if (query_only) return 0;
-  kern<<<blocks, TPB, smem, e->stream>>>(e->dobj, e->dyn, p);
-  return 0;
-}
-template <int A>
-static int launch_binpack_a(Engine* e, int blocks_wanted, size_t smem, const BpParams& p, int* blocks_out, bool query_only) {
-  if constexpr (A == 3) {   // experiment: CAE_BP_TPB=128
-    static const int tpb = getenv("CAE_BP_TPB") ? atoi(getenv("CAE_BP_TPB")) : 256;
-    if (tpb == 128) return launch_binpack_at<A, 128>(e, blocks_wanted, smem, p, blocks_out, query_only);
-  }
-  return launch_binpack_at<A, 256>(e, blocks_wanted, smem, p, blocks_out, query_only);
-}
-
-static int launch_binpack_any(Engine* e, int blocks_wanted, size_t smem, const BpParams& p, int* blocks_out, bool query_only) {
-  switch (e->A) {
-    case 0: return launch_binpack_a<0>(e, blocks_wanted, smem, p, blocks_out, query_only);
-    case 1: return launch_binpack_a<1>(e, blocks_wanted, smem, p, blocks_out, query_only);
-    case 2: return launch_binpack_a<2>(e, blocks_wanted, smem, p, blocks_out, query_only);
-    case 3: return launch_binpack_a<3>(e, blocks_wanted, smem, p, blocks_out, query_only);
-    case 4: return launch_binpack_a<4>(e, blocks_wanted, smem, p, blocks_out, query_only);
-    case 5: return launch_binpack_a<5>(e, blocks_wanted, smem, p, blocks_out, query_only);
-    case 6: return launch_binpack_a<6>(e, blocks_wanted, smem, p, blocks_out, query_only);
-    case 7: return launch_binpack_a<7>(e, blocks_wanted, smem, p, blocks_out, query_only);
-    default: return launch_binpack_a<8>(e, blocks_wanted, smem, p, blocks_out, query_only);
-  }
+static int launch_binpack_any(Engine* e, int blocks_wanted, size_t smem, const BpParams& p, int* blocks_out, bool query_only, bool filter = false) {
+  const int A = std::min(e->A, 8);
+  if (A <= 2) return bp_launch_part0(e, A, blocks_wanted, smem, p, blocks_out, query_only, filter);
+  if (A <= 5) return bp_launch_part1(e, A, blocks_wanted, smem, p, blocks_out, query_only, filter);
+  return bp_launch_part2(e, A, blocks_wanted, smem, p, blocks_out, query_only, filter);
 }
 
 int launch_binpack(Engine* e) {
@@ -1574,11 +1587,6 @@ __global__ void run_rec_kernel(DevObjects o, DynTables d, int runs, const int32_
   out[r] = g;
 }
 
-template <int A>
-static void launch_filter_a(cudaStream_t st, const DevObjects& o, const DynTables& d, const BpParams& p) {
-  binpack_kernel<A, 512, false, true><<<1, 512, 0, st>>>(o, d, p);
-}
-
 // HintingSimulator.TrySchedulePods on the cluster snapshot (one thread block).  `f` = device blob laid out by
 // cae_filter_schedulable (api.cu); class marks and controller counters are zeroed there.
 int launch_filter(Engine* e, const FilterLaunch& f) {
@@ -1624,20 +1632,11 @@ int launch_filter(Engine* e, const FilterLaunch& f) {
   CAE_CUDA(cudaMemsetAsync(e->d_work_counter, 0, sizeof(int32_t) * 2, e->stream));
   run_rec_kernel<<<(f.runs + 127) / 128, 128, 0, e->stream>>>(e->dobj, e->dyn, f.runs, f.run_off, f.pods, e->A, e->d_act_dim, p.has_dyn,
                                                              e->d_spec_sc, e->d_spec_dc, e->d_pc_of, e->d_port_conf, d_rec);
-  switch (e->A) {
-    case 0: launch_filter_a<0>(e->stream, e->dobj, e->dyn, p); break;
-    case 1: launch_filter_a<1>(e->stream, e->dobj, e->dyn, p); break;
-    case 2: launch_filter_a<2>(e->stream, e->dobj, e->dyn, p); break;
-    case 3: launch_filter_a<3>(e->stream, e->dobj, e->dyn, p); break;
-    case 4: launch_filter_a<4>(e->stream, e->dobj, e->dyn, p); break;
-    case 5: launch_filter_a<5>(e->stream, e->dobj, e->dyn, p); break;
-    case 6: launch_filter_a<6>(e->stream, e->dobj, e->dyn, p); break;
-    case 7: launch_filter_a<7>(e->stream, e->dobj, e->dyn, p); break;
-    default: launch_filter_a<8>(e->stream, e->dobj, e->dyn, p); break;
-  }
+  { int unused = 0; if (launch_binpack_any(e, 1, 0, p, &unused, false, true)) return -1; }
   e->stats.kernel_launches += 2;
   CAE_KERNEL_OK();
   return 0;
 }
+#endif  // BP_PART == 0
 
 }  // namespace cae
