@@ -527,12 +527,15 @@ class Encoder:
         if ns.name in self.namespaces.ids:
             self.b.declare_namespace(self.namespaces.ids[ns.name], self._labelset(ns.labels), True)
 
-    def podspec(self, pod: Pod) -> int:
+    def podspec(self, pod: Pod, resident: bool = False) -> int:
+        """resident: a pod already running on a cluster node.  The volume / DRA filters (VolumeRestrictions, VolumeBinding,
+        VolumeZone, NodeVolumeLimits, DynamicResources) only ever reject an INCOMING pod that carries volumes or claims, so
+        residents with volumes are harmless as long as no pending (or template DaemonSet) pod has any — those are refused."""
+        if pod.has_volumes_or_claims and not resident:
+            raise Unsupported("pod %s/%s uses volumes or resource claims" % (pod.namespace, pod.name))
         cached = self._podspec_cache.get(id(pod))
         if cached is not None:
             return cached
-        if pod.has_volumes_or_claims:
-            raise Unsupported("pod %s/%s uses volumes or resource claims" % (pod.namespace, pod.name))
         b = self.b
         ns = self._ns(pod.namespace)
         tols = b.toleration_list([
@@ -589,7 +592,7 @@ class Encoder:
         self._podspec_cache[id(pod)] = sid
         return sid
 
-    def _node_args(self, ni: NodeInfo):
+    def _node_args(self, ni: NodeInfo, resident: bool = False):
         n = ni.node
         taints = self.b.taint_list([(self._key(t.key), self._val(t.value) if t.value else -1,
                                      _EFFECTS[t.effect]) for t in n.taints])
@@ -598,10 +601,10 @@ class Encoder:
                     allowed_pods=int(n.allocatable.get("pods", 0)),
                     cap_cpu=int(n.capacity.get("cpu", 0)), cap_mem=int(n.capacity.get("memory", 0)),
                     has_alloc_cpu="cpu" in n.allocatable, has_alloc_mem="memory" in n.allocatable,
-                    pod_specs=[self.podspec(p) for p in ni.pods])
+                    pod_specs=[self.podspec(p, resident) for p in ni.pods])
 
     def add_cluster_node(self, ni: NodeInfo) -> int:
-        return self.b.cluster_node(**self._node_args(ni))
+        return self.b.cluster_node(**self._node_args(ni, resident=True))
 
     def add_template(self, ni: NodeInfo) -> int:
         return self.b.template(**self._node_args(ni))

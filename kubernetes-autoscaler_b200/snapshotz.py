@@ -107,8 +107,9 @@ def pod_from_json(p: Dict[str, Any]) -> Pod:
     pod.priority = int(spec.get("priority") or 0)
     # pods the engine must hand to the stock path (SURVEY §7 hard part 7): PVC / ephemeral volumes, DRA claims
     vols = spec.get("volumes") or []
-    pod.has_volumes_or_claims = bool(spec.get("resourceClaims")) or any(
-        ("persistentVolumeClaim" in v) or ("ephemeral" in v) for v in vols)
+    # ... and the in-tree / inline-CSI volumes VolumeRestrictions and NodeVolumeLimits look at
+    _VOL = ("persistentVolumeClaim", "ephemeral", "gcePersistentDisk", "awsElasticBlockStore", "rbd", "iscsi", "csi")
+    pod.has_volumes_or_claims = bool(spec.get("resourceClaims")) or any(any(k in v for k in _VOL) for v in vols)
     for ref in (meta.get("ownerReferences") or []):
         if ref.get("controller"):
             pod.owner_uid, pod.owner_kind = ref.get("uid", ""), ref.get("kind", "")

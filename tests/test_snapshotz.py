@@ -77,3 +77,25 @@ def test_golden_fixture_engine():
     assert nc.tolist() == exp["node_count"] and pc.tolist() == exp["pod_count"]
     assert sched.tolist() == exp["sched_count"] and order.tolist() == exp["order"]
     eng.close()
+
+
+def test_volumes_refuse_pending_pods_only():
+    """A RESIDENT pod with a PVC cannot make a volume filter reject anybody (they only look at the incoming pod's volumes):
+    the tick stays on the engine; a PENDING pod with volumes is handed to the stock path (encode.Unsupported)."""
+    from kubernetes_autoscaler_b200.encode import Unsupported, encode
+    from kubernetes_autoscaler_b200.objects import BuildTestNode, BuildTestPod, NodeInfo, makePodEquivalenceGroup
+    resident = BuildTestPod("db-0", 100, 1 << 20)
+    resident.has_volumes_or_claims = True
+    cluster = [NodeInfo(BuildTestNode("n1", 1000, 1 << 30), [resident])]
+    templates = [NodeInfo(BuildTestNode("t1", 1000, 1 << 30))]
+    enc = encode(cluster, templates, [makePodEquivalenceGroup(BuildTestPod("web", 100, 1 << 20), 3)])
+    assert enc.P == 3
+    pending = BuildTestPod("db-1", 100, 1 << 20)
+    pending.has_volumes_or_claims = True
+    with pytest.raises(Unsupported):
+        encode(cluster, templates, [makePodEquivalenceGroup(pending, 1)])
+    from kubernetes_autoscaler_b200.snapshotz import pod_from_json
+    p = pod_from_json({"metadata": {"name": "x", "namespace": "d"}, "spec": {"volumes": [{"name": "v", "gcePersistentDisk": {"pdName": "d"}}], "containers": []}})
+    assert p.has_volumes_or_claims
+    p = pod_from_json({"metadata": {"name": "x", "namespace": "d"}, "spec": {"volumes": [{"name": "v", "configMap": {"name": "c"}}], "containers": []}})
+    assert not p.has_volumes_or_claims
