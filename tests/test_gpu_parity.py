@@ -462,3 +462,33 @@ def test_last_index_carried_in_and_out(eng, oracle):
             nc, pc, sched, order, lo = eng.estimate_all_li(caps, li)
             assert (nc[t], pc[t], lo[t]) == (want[0][t], want[1][t], want[4][t]) and np.array_equal(sched[t], want[2][t])
             carry = int(lo[t])
+
+
+def test_slab_path_and_degenerate_inputs(eng, oracle):
+    """Unlimited estimates (max_nodes = 0 -> one node per pod may be needed) with more nodes than the shared-memory window
+    holds run the estimator on its global slab (template parameter WIN = false); plus the degenerate shapes: no pending
+    pods, no templates, no cluster nodes, an empty group, a limiter that forbids every node."""
+    from kubernetes_autoscaler_b200.engine import unpack_bits
+    for enc in (synth.generate(2, pods=9_000, templates=20), synth.generate(3, pods=7_000, templates=12, cluster_nodes=40),
+                synth.generate(4, pods=7_000, templates=10, cluster_nodes=30)):
+        for caps in (np.zeros(enc.T, np.int32), np.full(enc.T, 6_500, np.int32)):
+            eng.load(enc)
+            nc, pc, sched, order = eng.estimate_all(caps)
+            onc, opc, osched, oorder, _ = oracle.estimate_all(enc, caps)
+            assert np.array_equal(nc, onc) and np.array_equal(pc, opc) and np.array_equal(sched, osched) and np.array_equal(order, oorder)
+    base = synth.generate(3, pods=600, templates=6, cluster_nodes=12)
+    empty = base.slice_pods(0, 0)                                   # no pending pods at all
+    eng.load(empty)
+    bits, reasons, count = eng.feasibility()
+    assert not count.any()
+    nc, pc, sched, order = eng.estimate_all(np.full(empty.T, 10, np.int32))
+    assert not nc.any() and not pc.any() and not sched.any()
+    for enc in (synth.generate(3, pods=400, templates=5, cluster_nodes=0), synth.generate(2, pods=300, templates=1)):
+        eng.load(enc)
+        for caps in (np.full(enc.T, -1, np.int32), np.full(enc.T, 1, np.int32), np.zeros(enc.T, np.int32)):
+            nc, pc, sched, order = eng.estimate_all(caps)
+            onc, opc, osched, oorder, _ = oracle.estimate_all(enc, caps)
+            assert np.array_equal(nc, onc) and np.array_equal(pc, opc) and np.array_equal(sched, osched) and np.array_equal(order, oorder)
+        bits, reasons, count = eng.feasibility()
+        want, _ = oracle.feasibility_dense(enc)
+        assert np.array_equal(unpack_bits(bits, enc.P), want == 0)
