@@ -154,7 +154,7 @@ struct Engine {
   void* d_pack_scratch = nullptr;
   size_t pack_scratch_bytes = 0;
   size_t pack_layout_sig = 0;
-  // filter-out-schedulable pass (pack.cu, FM): own slab + input blob
+  // filter-out-schedulable pass (binpack.cu, FM): own slab + input blob
   void* d_fm_scratch = nullptr;
   size_t fm_scratch_bytes = 0, fm_layout_sig = 0;
   int32_t* d_fm_blob = nullptr;
@@ -164,7 +164,6 @@ struct Engine {
   int32_t* d_xbuf = nullptr;              // [2 parities][PEER_MAX][PEER_CAP] (count, step tag) slots + done counter, status
   int peer_world = 0;
   int32_t* peer_base[PEER_MAX] = {nullptr};
-  int64_t peer_uses[2] = {0, 0};
   int64_t peer_step = 0;
   int32_t* d_work_counter = nullptr;
   // host copies needed by host-side steps

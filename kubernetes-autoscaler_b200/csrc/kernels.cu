@@ -2,7 +2,7 @@
 //
 //   class_matrix_kernel   (static class x universe node) -> reason/flag byte     [tables.cuh static_code]
 //   pack_ok_bits_kernel   byte matrix -> per-class template bit words
-//   (K1, the dense pods x templates pass, lives in feas.cu; K3, the pack, in pack.cu)
+//   (K1, the dense pods x templates pass, lives in feas.cu; K3, the estimator, in binpack.cu)
 //   group_reason_kernel   exemplar x template reasons (what SchedulablePodGroups asks)
 //   order_kernel          K0: DecreasingPodOrderer per template (float64 score, stable bitonic sort)
 //   waste_kernel          K4: least-waste score per option
