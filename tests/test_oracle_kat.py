@@ -175,3 +175,16 @@ def test_run_filters_until_passing_node_kat(oracle, cpu, expected):
         assert cluster[int(assigned[0])].node.name in expected
     else:
         assert int(assigned[0]) == -1
+
+
+def test_debug_info_kat(oracle):
+    """plugin_runner_test.go:296-324 (TestDebugInfo, default config): a node with a NoSchedule and a NoExecute taint rejects a
+    pod without tolerations; the failing predicate is TaintToleration with its reference reason string."""
+    from kubernetes_autoscaler_b200 import capi
+    from kubernetes_autoscaler_b200.objects import BuildTestNode, Taint
+    n1 = BuildTestNode("n1", 1000, 2000000)
+    n1.taints = [Taint("SomeTaint", "WhyNot?", "NoSchedule"), Taint("RandomTaint", "JustBecause", "NoExecute")]
+    enc = encode([], [NodeInfo(n1)], [makePodEquivalenceGroup(BuildTestPod("p1", 0, 0), 1)])
+    reasons, _ = oracle.feasibility_dense(enc)
+    plugin, reason = capi.REASON_PLUGIN[int(reasons[0][0])]
+    assert (plugin, reason) == ("TaintToleration", "node(s) had untolerated taint(s)")
