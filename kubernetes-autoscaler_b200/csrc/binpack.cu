@@ -84,6 +84,7 @@ struct BpShared {
   int ri[2][32][3];
   int hist[BP_HIST + 1];      // #nodes per capacity value (closed-form lap count)
   int t, L, rem, pre_s, log_n, overflow, newly, need_log, mlast, lastnode;
+  long long dead[4][CAE_MAX_RES];   // requests (no host ports) whose sweep found no room since the node state last changed
 };
 
 __device__ __forceinline__ int bp_wsum(int v) { return __reduce_add_sync(0xffffffffu, v); }   // REDUX: one instruction
@@ -310,6 +311,10 @@ __global__ void __launch_bounds__(TPB, FM ? 1 : BP_MIN_CTAS * 256 / TPB) binpack
     int maxslots = INT_MIN;
 #pragma unroll
     for (int a = 0; a < A; ++a) maxfree[a] = LLONG_MIN;
+    // A request that found NO room in a sweep stays dead until a node is ADDED (placements only shrink what is free): a later
+    // plain group asking at least as much in every dimension skips its sweep.  Only port-free requests are remembered
+    // (a request with host ports can fail for its ports alone); the last four, a ring.
+    int n_dead = 0, dead_next = 0;
     auto refresh_bounds = [&]() {
       long long mf[A1];
       int msl = INT_MIN;
@@ -521,6 +526,14 @@ __global__ void __launch_bounds__(TPB, FM ? 1 : BP_MIN_CTAS * 256 / TPB) binpack
       bool can_existing = n_new > 0 && static_new && maxslots >= 1;   // some added node may still take this pod
 #pragma unroll
       for (int a = 0; a < A; ++a) can_existing = can_existing && !(req[a] > 0 && req[a] > maxfree[a]);
+      if (!FM && dc == 0 && can_existing) {
+        for (int i = 0; i < n_dead; ++i) {
+          bool dom = true;
+#pragma unroll
+          for (int a = 0; a < A; ++a) dom = dom && req[a] >= S.dead[i][a];
+          if (dom) { can_existing = false; break; }
+        }
+      }
       int placed = 0;
 
       // spare capacity of node x for this pod by NodePorts + NodeResourcesFit alone (pod slots, free resources)
@@ -606,6 +619,7 @@ __global__ void __launch_bounds__(TPB, FM ? 1 : BP_MIN_CTAS * 256 / TPB) binpack
         if (k_new > 0) { nodes_with_pods += add; placed += fill; n -= fill; }
         n_new += add;
         if (add > 0) {
+          n_dead = 0; dead_next = 0;
           maxslots = max(maxslots, tslots);
 #pragma unroll
           for (int a = 0; a < A; ++a) maxfree[a] = max(maxfree[a], tfree[a]);
@@ -760,7 +774,16 @@ __global__ void __launch_bounds__(TPB, FM ? 1 : BP_MIN_CTAS * 256 / TPB) binpack
             if (jl >= n_new) jl -= n_new;
             last_index = (N + jl + 1) % (N + n_new);
           }
-          if (got == 0) refresh_bounds(); else __syncthreads();
+          if (got == 0) {
+            refresh_bounds();
+            if (!has_ports) {     // remember the dead request (ring of four)
+#pragma unroll
+              for (int a = 0; a < A; ++a) if (tid == a) S.dead[dead_next][a] = req[a];
+              dead_next = (dead_next + 1) & 3;
+              n_dead = min(n_dead + 1, 4);
+              __syncthreads();
+            }
+          } else __syncthreads();
         }
         BP_PROF_END(0);
         BP_PROF_BEGIN();
@@ -1280,6 +1303,7 @@ __global__ void __launch_bounds__(TPB, FM ? 1 : BP_MIN_CTAS * 256 / TPB) binpack
             }
           }
           n_new += 1;       // recompute() below must see the new node's hostname domain
+          n_dead = 0; dead_next = 0;
           maxslots = max(maxslots, tslots);
 #pragma unroll
           for (int a = 0; a < A; ++a) maxfree[a] = max(maxfree[a], tfree[a]);
