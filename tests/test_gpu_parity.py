@@ -492,3 +492,20 @@ def test_slab_path_and_degenerate_inputs(eng, oracle):
         bits, reasons, count = eng.feasibility()
         want, _ = oracle.feasibility_dense(enc)
         assert np.array_equal(unpack_bits(bits, enc.P), want == 0)
+
+
+def test_more_than_256_pods_per_node(eng, oracle):
+    """Per-node capacities above the 256-bin histogram of the lap count (tiny pods on nodes that allow thousands): the binary
+    search over laps must give the reference's round-robin, partial final lap included."""
+    node = BuildTestNode("big", 64_000, 512 << 30)
+    node.allocatable["pods"] = 5_000
+    node.capacity["pods"] = 5_000
+    small = BuildTestNode("small", 8_000, 64 << 30)
+    small.allocatable["pods"] = 700
+    small.capacity["pods"] = 700
+    groups = [makePodEquivalenceGroup(BuildTestPod("a", 50, 64 << 20), 1_500), makePodEquivalenceGroup(BuildTestPod("b", 10, 16 << 20), 2_900),
+              makePodEquivalenceGroup(BuildTestPod("c", 5, 8 << 20), 3_333), makePodEquivalenceGroup(BuildTestPod("d", 1, 1 << 20), 777),
+              makePodEquivalenceGroup(BuildTestPod("e", 2, 1 << 20), 4_001)]
+    enc = encode([], [NodeInfo(node), NodeInfo(small)], groups)
+    for caps in ([0, 0], [3, 7], [2, 2]):
+        _check_estimate(eng, oracle, enc, caps)
