@@ -16,14 +16,19 @@
 //   * tryToScheduleOnNewNodes (:168-247): only the last added node is tried, so each new node takes
 //     min(remaining, k_new) until the limiter denies (:222); an empty last node stops the group (:212);
 //     a pod that fits no fresh node still adds one (:227-240).
-// Hostname-spread groups whose global minimum is PINNED at 0 (one DoNotSchedule constraint on
-// kubernetes.io/hostname counting only the group's own pods, and an eligible empty domain that can never
-// take a pod): the skew rule is then a per-node capacity (maxSkew - self - count) / weight + 1, so the
-// same round-robin closed form applies to the added nodes AND to the fallback of :186-205, which deals
-// the pods the last node refuses for skew over the CLUSTER nodes in cyclic order.
-// Every other dynamic group (dyn.cuh) runs the reference's per-pod loop against incremental counters
-// (copy-on-write over the cluster base counts): per pod one block-wide evaluation of every open node,
-// a block-wide arg-min of the cyclic distance, one placement.
+// Groups under topology counters (dyn.cuh) take the CAPACITY FORM when every counter is a per-node capacity or a budget:
+//   * hostname-key counters see one domain per node: a DoNotSchedule spread constraint whose global minimum is PINNED
+//     at 0 (proved per group) admits (maxSkew - self - count) / weight + 1 pods on a node, an (existing-)anti-affinity
+//     counter one pod; the same round-robin closed form then applies to the added nodes AND to the fallback of
+//     :186-205, which deals the pods the last node refuses FOR SKEW over the CLUSTER nodes in cyclic order;
+//   * counters on any other key see ONE domain for all added nodes and bound the pods the group can place at all.
+// Every other group runs the reference's per-pod loop against incremental counters (copy-on-write over the cluster
+// base counts): per pod one block-wide evaluation of every open node, a block-wide arg-min of the cyclic distance,
+// one placement.
+// Per (template, group) step the block reads ONE 144-byte group record that travelled one group ahead (cp.async);
+// groups that provably find no room (per-template capacity bounds, a ring of dead requests) skip their sweep.
+// FM = true is HintingSimulator.TrySchedulePods on the cluster nodes (the filter-out-schedulable pass), see the
+// kernel's comment.  The file is compiled in three parts (BP_PART) so that build() can run them in parallel.
 #include <algorithm>
 #include <climits>
 #include <cstdio>
